@@ -1,0 +1,1724 @@
+// b200mj.cu — B200 (sm_100a) batched forward-dynamics engine: ONE WARP PER ENVIRONMENT.
+//
+// Stands where the un-vendored `mujoco.mj_step / mj_step1 / mj_step2 / mj_forward` calls stand in
+// dm_control/mujoco/engine.py:147-176,306-343. Stage list: SURVEY.md §8a. C ABI: include/b200mj.h.
+//
+// Layout: batched state is row-major [batch, n] in HBM, so the warp that owns environment e reads its
+// row with consecutive lanes on consecutive doubles (coalesced). Everything between the load of
+// (qpos, qvel, act, qacc_warmstart, ctrl) and the store of the new state + observation-contract outputs
+// lives in a per-warp shared-memory workspace (struct Lay) — `nstep` physics steps are fused into one
+// launch. Lanes parallelise over bodies of a tree level, dofs, geom pairs or constraint rows; reductions
+// are fixed-order xor-shuffle trees so results are bit-reproducible run to run.
+//
+// No CPU fallback exists: if this library is missing the Python facade raises.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200mj.h"
+#include "../../include/b200mj_model_fields.h"
+
+#define FULL 0xffffffffu
+#define FOR_LANES(i, n) for (int i = lane; i < (n); i += 32)
+
+// ------------------------------------------------------------------------------------------------
+// device model view + workspace layout
+// ------------------------------------------------------------------------------------------------
+struct DevModel {
+#define DECL_I(name) const int* name;
+#define DECL_R(name) const double* name;
+  B200MJ_MODEL_FIELDS(DECL_I, DECL_R)
+#undef DECL_I
+#undef DECL_R
+  int nq, nv, nu, na, nbody, njnt, ngeom, nsite, ntendon, neq, nsensor, nsensordata, npair, nlevel, nconmax, njmax;
+  int ldv;          // padded row length of nv-wide matrices (odd => conflict-free column walks)
+  int integrator, iterations, ls_iterations, disableflags;
+  int any_damping, acc_sensors;
+  double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
+};
+
+// offsets (in doubles) into one environment's workspace
+struct Lay {
+  int qpos, qvel, act, ctrl, qaccws, actdot;
+  int xpos, xquat, xmat, xipos, xanchor, xaxis, gxpos, gxmat, scom, slinvel;
+  int cinert, crb, cdof, cdofdot, cvel, cacc, cfrc, cfrcext;
+  int tenlen, tenJ, actforce;
+  int M, LM, H;
+  int J, efcD, efcSD, aref, jar, jv, force, eqflag;
+  int bias, passive, qfact, smooth, qaccs, qacc, qcon, Ma, grad, search, Mv, tmpv;
+  int con;                               // contact records, 16 doubles each
+  int rk;                                // RK4 scratch: X0q, X0v, X0a, accv, acca, accd
+  int sens;                              // sensordata staging
+  int total;
+};
+
+struct b200mj_model {
+  DevModel dm;
+  Lay lay;
+  int* d_idata;
+  double* d_rdata;
+  int envs_per_block;
+  size_t smem_per_env;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device math
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; }
+__device__ __forceinline__ void cross3(double* r, const double* a, const double* b) {
+  double x = a[1]*b[2] - a[2]*b[1], y = a[2]*b[0] - a[0]*b[2], z = a[0]*b[1] - a[1]*b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ double norm3(const double* a) { return sqrt(dot3(a, a)); }
+__device__ __forceinline__ double normalize3(double* a) {
+  double n = norm3(a);
+  if (n < BMJ_MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; } else { a[0] /= n; a[1] /= n; a[2] /= n; }
+  return n;
+}
+__device__ __forceinline__ void mul_quat(double* r, const double* a, const double* b) {
+  double w = a[0]*b[0] - a[1]*b[1] - a[2]*b[2] - a[3]*b[3];
+  double x = a[0]*b[1] + a[1]*b[0] + a[2]*b[3] - a[3]*b[2];
+  double y = a[0]*b[2] - a[1]*b[3] + a[2]*b[0] + a[3]*b[1];
+  double z = a[0]*b[3] + a[1]*b[2] - a[2]*b[1] + a[3]*b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+__device__ __forceinline__ void normalize4(double* q) {
+  double n = sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
+  if (n < BMJ_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n; }
+}
+__device__ __forceinline__ void quat2mat(double* m, const double* q) {
+  double q00 = q[0]*q[0], q11 = q[1]*q[1], q22 = q[2]*q[2], q33 = q[3]*q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2*(q[1]*q[2] - q[0]*q[3]); m[2] = 2*(q[1]*q[3] + q[0]*q[2]);
+  m[3] = 2*(q[1]*q[2] + q[0]*q[3]); m[5] = 2*(q[2]*q[3] - q[0]*q[1]);
+  m[6] = 2*(q[1]*q[3] - q[0]*q[2]); m[7] = 2*(q[2]*q[3] + q[0]*q[1]);
+}
+__device__ __forceinline__ void mat_vec(double* r, const double* m, const double* v) {
+  double x = m[0]*v[0] + m[1]*v[1] + m[2]*v[2], y = m[3]*v[0] + m[4]*v[1] + m[5]*v[2], z = m[6]*v[0] + m[7]*v[1] + m[8]*v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void matT_vec(double* r, const double* m, const double* v) {
+  double x = m[0]*v[0] + m[3]*v[1] + m[6]*v[2], y = m[1]*v[0] + m[4]*v[1] + m[7]*v[2], z = m[2]*v[0] + m[5]*v[1] + m[8]*v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void rot_vec_quat(double* r, const double* v, const double* q) {
+  double m[9]; quat2mat(m, q); mat_vec(r, m, v);
+}
+__device__ __forceinline__ void axis_angle2quat(double* q, const double* axis, double angle) {
+  if (angle == 0) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  double s, c; sincos(angle * 0.5, &s, &c);
+  q[0] = c; q[1] = axis[0]*s; q[2] = axis[1]*s; q[3] = axis[2]*s;
+}
+__device__ __forceinline__ void quat_integrate(double* q, const double* w, double h) {
+  double ax[3] = {w[0], w[1], w[2]};
+  double n = norm3(ax);
+  if (n < BMJ_MINVAL) return;
+  ax[0] /= n; ax[1] /= n; ax[2] /= n;
+  double dq[4], r[4];
+  axis_angle2quat(dq, ax, h * n);
+  normalize4(q);
+  mul_quat(r, q, dq);
+  q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3];
+}
+__device__ __forceinline__ void mul_inert_vec(double* r, const double* i, const double* v) {
+  r[0] = i[0]*v[0] + i[3]*v[1] + i[4]*v[2] - i[8]*v[4] + i[7]*v[5];
+  r[1] = i[3]*v[0] + i[1]*v[1] + i[5]*v[2] + i[8]*v[3] - i[6]*v[5];
+  r[2] = i[4]*v[0] + i[5]*v[1] + i[2]*v[2] - i[7]*v[3] + i[6]*v[4];
+  r[3] = i[8]*v[1] - i[7]*v[2] + i[9]*v[3];
+  r[4] = i[6]*v[2] - i[8]*v[0] + i[9]*v[4];
+  r[5] = i[7]*v[0] - i[6]*v[1] + i[9]*v[5];
+}
+__device__ __forceinline__ void cross_motion(double* r, const double* vel, const double* v) {
+  double a[3], b[3], c[3];
+  cross3(a, vel, v); cross3(b, vel, v + 3); cross3(c, vel + 3, v);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+__device__ __forceinline__ void cross_force(double* r, const double* vel, const double* f) {
+  double a[3], b[3], c[3];
+  cross3(a, vel, f); cross3(b, vel + 3, f + 3); cross3(c, vel, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+__device__ __forceinline__ double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ bool bad_value(double x) { return isnan(x) || x > BMJ_MAXVAL || x < -BMJ_MAXVAL; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// exclusive prefix sum over lanes; *total = sum over all lanes
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+  *total = __shfl_sync(FULL, x, 31);
+  return x - v;
+}
+
+struct Ctx {
+  const DevModel& m; const Lay& L; double* ws; int lane; int disableflags;
+  __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df) {}
+};
+#define W(name) (c.ws + c.L.name)
+
+// ------------------------------------------------------------------------------------------------
+// dense Cholesky in the workspace: A (n x n, row stride ld) -> lower factor Lm, same stride
+// ------------------------------------------------------------------------------------------------
+__device__ void chol_factor(const double* A, double* Lm, int n, int ld, int lane) {
+  for (int j = 0; j < n; j++) {
+    for (int i = lane; i < n; i += 32) {
+      if (i >= j) {
+        double t = A[i * ld + j];
+        const double* Li = Lm + i * ld; const double* Lj = Lm + j * ld;
+        for (int k = 0; k < j; k++) t -= Li[k] * Lj[k];
+        Lm[i * ld + j] = t;
+      }
+    }
+    __syncwarp();
+    double piv = Lm[j * ld + j];
+    if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+    double s = sqrt(piv);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      if (i > j) Lm[i * ld + j] = Lm[i * ld + j] / s;
+      else if (i == j) Lm[i * ld + j] = s;
+    }
+    __syncwarp();
+  }
+}
+
+// solve (L L^T) x = b; b, x are workspace vectors (may alias); n <= 64
+__device__ void chol_solve(const double* Lm, const double* b, double* x, int n, int ld, int lane) {
+  double x0 = lane < n ? b[lane] : 0.0, x1 = lane + 32 < n ? b[lane + 32] : 0.0;
+  for (int j = 0; j < n; j++) {
+    double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
+    double yj = v / Lm[j * ld + j];
+    if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= Lm[lane * ld + j] * yj; if (lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
+    else { if (lane + 32 == j) x1 = yj; else if (lane + 32 > j && lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
+  }
+  for (int j = n - 1; j >= 0; j--) {
+    double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
+    double yj = v / Lm[j * ld + j];
+    if (j < 32) { if (lane == j) x0 = yj; else if (lane < j) x0 -= Lm[j * ld + lane] * yj; }
+    else { if (lane + 32 == j) x1 = yj; else if (lane + 32 < j) x1 -= Lm[j * ld + lane + 32] * yj; if (lane < n) x0 -= Lm[j * ld + lane] * yj; }
+  }
+  __syncwarp();
+  if (lane < n) x[lane] = x0;
+  if (lane + 32 < n) x[lane + 32] = x1;
+  __syncwarp();
+}
+
+// bottom-up accumulation child -> parent for a [nbody, width] table; deterministic (parent gathers children)
+__device__ void tree_accumulate(const Ctx& c, double* tab, int width, bool into_world) {
+  const DevModel& m = c.m; int lane = c.lane;
+  for (int l = m.nlevel - 2; l >= (into_world ? 0 : 1); l--) {
+    int a0 = m.level_adr[l], a1 = m.level_adr[l + 1], a2 = m.level_adr[l + 2];
+    for (int k = a0 + lane; k < a1; k += 32) {
+      int p = m.level_body[k];
+      for (int q = a1; q < a2; q++) {
+        int ch = m.level_body[q];
+        if (m.body_parentid[ch] == p) for (int i = 0; i < width; i++) tab[p * width + i] += tab[ch * width + i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// position stage
+// ------------------------------------------------------------------------------------------------
+__device__ void kinematics(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane;
+  double* qpos = W(qpos); double* xpos = W(xpos); double* xquat = W(xquat); double* xmat = W(xmat);
+  if (lane == 0) {
+    xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
+    for (int i = 0; i < 9; i++) xmat[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  FOR_LANES(j, m.njnt) {
+    int t = m.jnt_type[j];
+    if (t == BMJ_JNT_FREE) normalize4(qpos + m.jnt_qposadr[j] + 3);
+    else if (t == BMJ_JNT_BALL) normalize4(qpos + m.jnt_qposadr[j]);
+  }
+  __syncwarp();
+  for (int l = 1; l < m.nlevel; l++) {
+    int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
+    for (int k = a0 + lane; k < a1; k += 32) {
+      int b = m.level_body[k], p = m.body_parentid[b];
+      double pos[3], quat[4], tmp[3], bp[3] = {m.body_pos[3*b], m.body_pos[3*b+1], m.body_pos[3*b+2]};
+      double bq[4] = {m.body_quat[4*b], m.body_quat[4*b+1], m.body_quat[4*b+2], m.body_quat[4*b+3]};
+      mat_vec(tmp, xmat + 9 * p, bp);
+      for (int i = 0; i < 3; i++) pos[i] = xpos[3 * p + i] + tmp[i];
+      mul_quat(quat, xquat + 4 * p, bq);
+      int j0 = m.body_jntadr[b], jn = m.body_jntnum[b];
+      for (int j = j0; j < j0 + jn; j++) {
+        int qa = m.jnt_qposadr[j], t = m.jnt_type[j];
+        double* anchor = W(xanchor) + 3 * j; double* axis = W(xaxis) + 3 * j;
+        double jax[3] = {m.jnt_axis[3*j], m.jnt_axis[3*j+1], m.jnt_axis[3*j+2]};
+        double jp[3] = {m.jnt_pos[3*j], m.jnt_pos[3*j+1], m.jnt_pos[3*j+2]};
+        if (t == BMJ_JNT_FREE) {
+          for (int i = 0; i < 3; i++) pos[i] = qpos[qa + i];
+          for (int i = 0; i < 4; i++) quat[i] = qpos[qa + 3 + i];
+          for (int i = 0; i < 3; i++) anchor[i] = pos[i];
+          rot_vec_quat(axis, jax, quat);
+          continue;
+        }
+        rot_vec_quat(tmp, jp, quat);
+        for (int i = 0; i < 3; i++) anchor[i] = pos[i] + tmp[i];
+        double ax[3]; rot_vec_quat(ax, jax, quat);
+        for (int i = 0; i < 3; i++) axis[i] = ax[i];
+        if (t == BMJ_JNT_SLIDE) {
+          double q = qpos[qa] - m.qpos0[qa];
+          for (int i = 0; i < 3; i++) pos[i] += ax[i] * q;
+        } else {
+          double ql[4], r[4];
+          if (t == BMJ_JNT_HINGE) axis_angle2quat(ql, jax, qpos[qa] - m.qpos0[qa]);
+          else for (int i = 0; i < 4; i++) ql[i] = qpos[qa + i];
+          mul_quat(r, quat, ql);
+          for (int i = 0; i < 4; i++) quat[i] = r[i];
+          rot_vec_quat(tmp, jp, quat);
+          for (int i = 0; i < 3; i++) pos[i] = anchor[i] - tmp[i];
+        }
+      }
+      normalize4(quat);
+      for (int i = 0; i < 3; i++) xpos[3 * b + i] = pos[i];
+      for (int i = 0; i < 4; i++) xquat[4 * b + i] = quat[i];
+      quat2mat(xmat + 9 * b, quat);
+    }
+    __syncwarp();
+  }
+  // inertial frames' origins and geom frames
+  FOR_LANES(b, m.nbody) {
+    double tmp[3], ip[3] = {m.body_ipos[3*b], m.body_ipos[3*b+1], m.body_ipos[3*b+2]};
+    mat_vec(tmp, xmat + 9 * b, ip);
+    for (int i = 0; i < 3; i++) W(xipos)[3 * b + i] = xpos[3 * b + i] + tmp[i];
+  }
+  FOR_LANES(g, m.ngeom) {
+    int b = m.geom_bodyid[g];
+    double tmp[3], q[4], gp[3] = {m.geom_pos[3*g], m.geom_pos[3*g+1], m.geom_pos[3*g+2]};
+    double gq[4] = {m.geom_quat[4*g], m.geom_quat[4*g+1], m.geom_quat[4*g+2], m.geom_quat[4*g+3]};
+    mat_vec(tmp, xmat + 9 * b, gp);
+    for (int i = 0; i < 3; i++) W(gxpos)[3 * g + i] = xpos[3 * b + i] + tmp[i];
+    mul_quat(q, xquat + 4 * b, gq);
+    quat2mat(W(gxmat) + 9 * g, q);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void site_frame(const Ctx& c, int s, double* pos, double* mat) {
+  const DevModel& m = c.m;
+  int b = m.site_bodyid[s];
+  double tmp[3], q[4], sp[3] = {m.site_pos[3*s], m.site_pos[3*s+1], m.site_pos[3*s+2]};
+  double sq[4] = {m.site_quat[4*s], m.site_quat[4*s+1], m.site_quat[4*s+2], m.site_quat[4*s+3]};
+  mat_vec(tmp, W(xmat) + 9 * b, sp);
+  for (int i = 0; i < 3; i++) pos[i] = W(xpos)[3 * b + i] + tmp[i];
+  mul_quat(q, W(xquat) + 4 * b, sq);
+  quat2mat(mat, q);
+}
+
+__device__ void com_pos(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane;
+  double* sc = W(scom); double* xipos = W(xipos);
+  FOR_LANES(b, m.nbody) { double ms = m.body_mass[b]; for (int i = 0; i < 3; i++) sc[3 * b + i] = ms * xipos[3 * b + i]; }
+  __syncwarp();
+  tree_accumulate(c, sc, 3, true);
+  FOR_LANES(b, m.nbody) {
+    double sm = m.body_subtreemass[b];
+    if (sm < BMJ_MINVAL) for (int i = 0; i < 3; i++) sc[3 * b + i] = xipos[3 * b + i];
+    else for (int i = 0; i < 3; i++) sc[3 * b + i] /= sm;
+  }
+  __syncwarp();
+  FOR_LANES(b, m.nbody) {
+    double* ci = W(cinert) + 10 * b;
+    if (b == 0) { for (int i = 0; i < 10; i++) ci[i] = 0; continue; }
+    double q[4], mat[9], iq[4] = {m.body_iquat[4*b], m.body_iquat[4*b+1], m.body_iquat[4*b+2], m.body_iquat[4*b+3]};
+    mul_quat(q, W(xquat) + 4 * b, iq);
+    quat2mat(mat, q);
+    int root = m.body_rootid[b];
+    double dif[3];
+    for (int i = 0; i < 3; i++) dif[i] = xipos[3 * b + i] - sc[3 * root + i];
+    double mass = m.body_mass[b], in0 = m.body_inertia[3*b], in1 = m.body_inertia[3*b+1], in2 = m.body_inertia[3*b+2];
+    double t[9];
+    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+      t[3 * r + cc] = mat[3 * r] * in0 * mat[3 * cc] + mat[3 * r + 1] * in1 * mat[3 * cc + 1] + mat[3 * r + 2] * in2 * mat[3 * cc + 2];
+    ci[0] = t[0] + mass * (dif[1]*dif[1] + dif[2]*dif[2]);
+    ci[1] = t[4] + mass * (dif[0]*dif[0] + dif[2]*dif[2]);
+    ci[2] = t[8] + mass * (dif[0]*dif[0] + dif[1]*dif[1]);
+    ci[3] = t[1] - mass * dif[0]*dif[1];
+    ci[4] = t[2] - mass * dif[0]*dif[2];
+    ci[5] = t[5] - mass * dif[1]*dif[2];
+    ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
+  }
+  FOR_LANES(j, m.njnt) {
+    int b = m.jnt_bodyid[j], root = m.body_rootid[b], da = m.jnt_dofadr[j], t = m.jnt_type[j];
+    double off[3];
+    for (int i = 0; i < 3; i++) off[i] = sc[3 * root + i] - W(xanchor)[3 * j + i];
+    double* cd = W(cdof) + 6 * da;
+    if (t == BMJ_JNT_FREE) {
+      for (int k = 0; k < 3; k++) { for (int i = 0; i < 6; i++) cd[6 * k + i] = 0; cd[6 * k + 3 + k] = 1; }
+      cd += 18;
+    }
+    if (t == BMJ_JNT_FREE || t == BMJ_JNT_BALL) {
+      const double* xm = W(xmat) + 9 * b;
+      for (int k = 0; k < 3; k++) {
+        double ax[3] = {xm[k], xm[3 + k], xm[6 + k]};
+        for (int i = 0; i < 3; i++) cd[6 * k + i] = ax[i];
+        cross3(cd + 6 * k + 3, ax, off);
+      }
+    } else if (t == BMJ_JNT_SLIDE) {
+      for (int i = 0; i < 3; i++) { cd[i] = 0; cd[3 + i] = W(xaxis)[3 * j + i]; }
+    } else {
+      double ax[3] = {W(xaxis)[3*j], W(xaxis)[3*j+1], W(xaxis)[3*j+2]};
+      for (int i = 0; i < 3; i++) cd[i] = ax[i];
+      cross3(cd + 3, ax, off);
+    }
+  }
+  // fixed tendons: length and (dense) Jacobian row
+  FOR_LANES(t, m.ntendon) {
+    double* row = W(tenJ) + t * m.ldv;
+    for (int i = 0; i < m.nv; i++) row[i] = 0;
+    double len = 0;
+    for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) {
+      int j = m.wrap_objid[w];
+      len += m.wrap_prm[w] * W(qpos)[m.jnt_qposadr[j]];
+      row[m.jnt_dofadr[j]] += m.wrap_prm[w];
+    }
+    W(tenlen)[t] = len;
+  }
+  __syncwarp();
+}
+
+__device__ void crb_and_factor(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  double* crb = W(crb); double* M = W(M);
+  for (int i = lane; i < 10 * m.nbody; i += 32) crb[i] = W(cinert)[i];
+  for (int i = lane; i < nv * ld; i += 32) M[i] = 0;
+  __syncwarp();
+  tree_accumulate(c, crb, 10, false);
+  FOR_LANES(i, nv) {
+    double buf[6], cd[6];
+    for (int k = 0; k < 6; k++) cd[k] = W(cdof)[6 * i + k];
+    mul_inert_vec(buf, crb + 10 * m.dof_bodyid[i], cd);
+    for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+      const double* cj = W(cdof) + 6 * j;
+      double s = 0;
+      for (int k = 0; k < 6; k++) s += cj[k] * buf[k];
+      if (j == i) s += m.dof_armature[i];
+      M[i * ld + j] = s; M[j * ld + i] = s;
+    }
+  }
+  __syncwarp();
+  chol_factor(M, W(LM), nv, ld, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// collision (narrow phase per candidate pair; lanes = pairs; ordered compaction keeps pair order)
+// ------------------------------------------------------------------------------------------------
+#define MAXPC 4   // contacts one geom pair can emit
+struct PairCon { int n; double dist[MAXPC]; double pos[MAXPC][3]; double nrm[MAXPC][3]; double tan[3]; };
+
+__device__ __forceinline__ int raw_plane_sphere(PairCon& pc, double margin, const double* ppos, const double* n, const double* spos, double radius) {
+  double dif[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
+  double cdist = dot3(dif, n);
+  if (cdist > margin + radius) return 0;
+  int k = pc.n++;
+  pc.dist[k] = cdist - radius;
+  for (int i = 0; i < 3; i++) { pc.nrm[k][i] = n[i]; pc.pos[k][i] = spos[i] - n[i] * (radius + 0.5 * pc.dist[k]); }
+  return 1;
+}
+__device__ __forceinline__ int raw_sphere_sphere(PairCon& pc, double margin, const double* p1, double r1, const double* p2, double r2) {
+  double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double cdist = norm3(dif);
+  if (cdist > margin + r1 + r2) return 0;
+  int k = pc.n++;
+  pc.dist[k] = cdist - r1 - r2;
+  if (cdist < BMJ_MINVAL) { pc.nrm[k][0] = 1; pc.nrm[k][1] = pc.nrm[k][2] = 0; }
+  else for (int i = 0; i < 3; i++) pc.nrm[k][i] = dif[i] / cdist;
+  for (int i = 0; i < 3; i++) pc.pos[k][i] = p1[i] + pc.nrm[k][i] * (r1 + 0.5 * pc.dist[k]);
+  return 1;
+}
+
+__device__ void narrowphase(PairCon& pc, int t1, int t2, double margin, const double* p1, const double* m1, const double* s1,
+                            const double* p2, const double* m2, const double* s2) {
+  pc.n = 0; pc.tan[0] = pc.tan[1] = pc.tan[2] = 0;
+  if (t1 == BMJ_GEOM_PLANE) {
+    double n[3] = {m1[2], m1[5], m1[8]};
+    if (t2 == BMJ_GEOM_SPHERE) { raw_plane_sphere(pc, margin, p1, n, p2, s2[0]); return; }
+    if (t2 == BMJ_GEOM_CAPSULE) {
+      double ax[3] = {m2[2], m2[5], m2[8]}, e[3];
+      for (int i = 0; i < 3; i++) e[i] = p2[i] + ax[i] * s2[1];
+      raw_plane_sphere(pc, margin, p1, n, e, s2[0]);
+      for (int i = 0; i < 3; i++) e[i] = p2[i] - ax[i] * s2[1];
+      raw_plane_sphere(pc, margin, p1, n, e, s2[0]);
+      if (pc.n) for (int i = 0; i < 3; i++) pc.tan[i] = ax[i];
+      return;
+    }
+    if (t2 == BMJ_GEOM_ELLIPSOID) {
+      double nl[3]; matT_vec(nl, m2, n);
+      double sv[3] = {nl[0] * s2[0], nl[1] * s2[1], nl[2] * s2[2]};
+      double len = norm3(sv);
+      if (len < BMJ_MINVAL) return;
+      double loc[3] = {-s2[0] * sv[0] / len, -s2[1] * sv[1] / len, -s2[2] * sv[2] / len}, pt[3];
+      mat_vec(pt, m2, loc);
+      for (int i = 0; i < 3; i++) pt[i] += p2[i];
+      double dif[3] = {pt[0] - p1[0], pt[1] - p1[1], pt[2] - p1[2]};
+      double dist = dot3(dif, n);
+      if (dist > margin) return;
+      pc.n = 1; pc.dist[0] = dist;
+      for (int i = 0; i < 3; i++) { pc.nrm[0][i] = n[i]; pc.pos[0][i] = pt[i] - n[i] * dist * 0.5; }
+      return;
+    }
+    if (t2 == BMJ_GEOM_BOX) {
+      double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      double dist0 = dot3(dif, n);
+      for (int k = 0; k < 8 && pc.n < MAXPC; k++) {
+        double loc[3] = {(k & 1 ? s2[0] : -s2[0]), (k & 2 ? s2[1] : -s2[1]), (k & 4 ? s2[2] : -s2[2])}, corner[3];
+        mat_vec(corner, m2, loc);
+        double ldist = dot3(n, corner);
+        if (dist0 + ldist > margin || ldist > 0) continue;
+        int q = pc.n++;
+        pc.dist[q] = dist0 + ldist;
+        for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + corner[i] - n[i] * pc.dist[q] * 0.5; }
+      }
+      return;
+    }
+    if (t2 == BMJ_GEOM_CYLINDER) {
+      double ax[3] = {m2[2], m2[5], m2[8]};
+      double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      double dist0 = dot3(dif, n), prjaxis = dot3(n, ax);
+      if (prjaxis > 0) { for (int i = 0; i < 3; i++) ax[i] = -ax[i]; prjaxis = -prjaxis; }
+      double vec[3], len_sq = 0;
+      for (int i = 0; i < 3; i++) { vec[i] = ax[i] * prjaxis - n[i]; len_sq += vec[i] * vec[i]; }
+      double len = sqrt(len_sq);
+      if (len < 1e-12) { vec[0] = m2[0] * s2[0]; vec[1] = m2[3] * s2[0]; vec[2] = m2[6] * s2[0]; }
+      else for (int i = 0; i < 3; i++) vec[i] *= s2[0] / len;
+      double prjvec = dot3(vec, n), axl[3];
+      for (int i = 0; i < 3; i++) axl[i] = ax[i] * s2[1];
+      double prjax = prjaxis * s2[1];
+      if (dist0 + prjax + prjvec > margin) return;
+      int q = pc.n++; pc.dist[q] = dist0 + prjax + prjvec;
+      for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + vec[i] + axl[i] - n[i] * pc.dist[q] * 0.5; }
+      if (dist0 - prjax + prjvec <= margin) {
+        q = pc.n++; pc.dist[q] = dist0 - prjax + prjvec;
+        for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + vec[i] - axl[i] - n[i] * pc.dist[q] * 0.5; }
+      }
+      double prjvec1 = -prjvec * 0.5;
+      if (dist0 + prjax + prjvec1 <= margin) {
+        double v1[3]; cross3(v1, vec, ax);
+        double l1 = norm3(v1);
+        if (l1 > BMJ_MINVAL) {
+          for (int i = 0; i < 3; i++) v1[i] *= s2[0] * sqrt(3.0) * 0.5 / l1;
+          for (int sgn = -1; sgn <= 1 && pc.n < MAXPC; sgn += 2) {
+            q = pc.n++; pc.dist[q] = dist0 + prjax + prjvec1;
+            for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + sgn * v1[i] + axl[i] - vec[i] * 0.5 - n[i] * pc.dist[q] * 0.5; }
+          }
+        }
+      }
+      return;
+    }
+    return;
+  }
+  if (t1 == BMJ_GEOM_SPHERE) {
+    if (t2 == BMJ_GEOM_SPHERE) { raw_sphere_sphere(pc, margin, p1, s1[0], p2, s2[0]); return; }
+    if (t2 == BMJ_GEOM_CAPSULE) {
+      double ax[3] = {m2[2], m2[5], m2[8]}, w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+      double x = clampd(dot3(ax, w), -s2[1], s2[1]), nearp[3];
+      for (int i = 0; i < 3; i++) nearp[i] = p2[i] + ax[i] * x;
+      raw_sphere_sphere(pc, margin, p1, s1[0], nearp, s2[0]);
+      return;
+    }
+    if (t2 == BMJ_GEOM_BOX) {
+      double w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, loc[3], cl[3], nl[3], dist;
+      matT_vec(loc, m2, w);
+      bool inside = true;
+      for (int i = 0; i < 3; i++) { cl[i] = clampd(loc[i], -s2[i], s2[i]); if (cl[i] != loc[i]) inside = false; }
+      if (!inside) {
+        double dl[3] = {loc[0] - cl[0], loc[1] - cl[1], loc[2] - cl[2]};
+        double dn = norm3(dl);
+        if (dn - s1[0] > margin) return;
+        dist = dn - s1[0];
+        for (int i = 0; i < 3; i++) nl[i] = -dl[i] / dn;
+      } else {
+        int best = 0; double bd = 1e300;
+        for (int i = 0; i < 3; i++) { double dd = s2[i] - fabs(loc[i]); if (dd < bd) { bd = dd; best = i; } }
+        nl[0] = nl[1] = nl[2] = 0; nl[best] = loc[best] > 0 ? -1 : 1;
+        dist = -bd - s1[0];
+      }
+      double nw[3]; mat_vec(nw, m2, nl);
+      pc.n = 1; pc.dist[0] = dist;
+      for (int i = 0; i < 3; i++) { pc.nrm[0][i] = nw[i]; pc.pos[0][i] = p1[i] + nw[i] * (s1[0] + 0.5 * dist); }
+      return;
+    }
+    return;
+  }
+  if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE) {
+    double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
+    double dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    double ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2);
+    double u = -dot3(a1, dif), v = dot3(a2, dif);
+    double det = ma * mc - mb * mb, len1 = s1[1], len2 = s2[1];
+    if (fabs(det) >= BMJ_MINVAL) {
+      double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+      if (x1 > len1) { x1 = len1; x2 = (v - mb * len1) / mc; }
+      else if (x1 < -len1) { x1 = -len1; x2 = (v + mb * len1) / mc; }
+      if (x2 > len2) { x2 = len2; x1 = clampd((u - mb * len2) / ma, -len1, len1); }
+      else if (x2 < -len2) { x2 = -len2; x1 = clampd((u + mb * len2) / ma, -len1, len1); }
+      double v1[3], v2[3];
+      for (int i = 0; i < 3; i++) { v1[i] = p1[i] + a1[i] * x1; v2[i] = p2[i] + a2[i] * x2; }
+      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+      return;
+    }
+    for (int e = 0; e < 2 && pc.n < 2; e++) {
+      double x1 = e == 0 ? len1 : -len1, v1[3], v2[3];
+      for (int i = 0; i < 3; i++) v1[i] = p1[i] + a1[i] * x1;
+      double w[3] = {v1[0] - p2[0], v1[1] - p2[1], v1[2] - p2[2]};
+      double x2 = dot3(w, a2);
+      if (x2 < -len2 || x2 > len2) continue;
+      for (int i = 0; i < 3; i++) v2[i] = p2[i] + a2[i] * x2;
+      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+    }
+    for (int e = 0; e < 2 && pc.n < 2; e++) {
+      double x2 = e == 0 ? len2 : -len2, v1[3], v2[3];
+      for (int i = 0; i < 3; i++) v2[i] = p2[i] + a2[i] * x2;
+      double w[3] = {v2[0] - p1[0], v2[1] - p1[1], v2[2] - p1[2]};
+      double x1 = dot3(w, a1);
+      if (x1 <= -len1 || x1 >= len1) continue;
+      for (int i = 0; i < 3; i++) v1[i] = p1[i] + a1[i] * x1;
+      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+    }
+    if (pc.n == 0) {
+      double x1 = clampd(u / ma, -len1, len1), v1[3], v2[3];
+      for (int i = 0; i < 3; i++) v1[i] = p1[i] + a1[i] * x1;
+      double w[3] = {v1[0] - p2[0], v1[1] - p2[1], v1[2] - p2[2]};
+      double x2 = clampd(dot3(w, a2), -len2, len2);
+      for (int i = 0; i < 3; i++) v2[i] = p2[i] + a2[i] * x2;
+      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+    }
+    return;
+  }
+}
+
+__device__ __forceinline__ void make_frame(double* frame, const double* normal, const double* tangent) {
+  double x[3] = {normal[0], normal[1], normal[2]};
+  normalize3(x);
+  double y[3] = {tangent[0], tangent[1], tangent[2]};
+  if (norm3(y) < 0.5) {
+    y[0] = y[1] = y[2] = 0;
+    if (x[1] < 0.5 && x[1] > -0.5) y[1] = 1; else y[2] = 1;
+  }
+  double dp = dot3(x, y);
+  for (int i = 0; i < 3; i++) y[i] -= dp * x[i];
+  normalize3(y);
+  double z[3]; cross3(z, x, y);
+  for (int i = 0; i < 3; i++) { frame[i] = x[i]; frame[3 + i] = y[i]; frame[6 + i] = z[i]; }
+}
+
+// contact record: [0] dist, [1..3] pos, [4..12] frame, [13] mu, [14] (geom1,geom2), [15] (dim, efc_address)
+#define CON_STRIDE 16
+__device__ __forceinline__ int* con_ints(double* rec) { return reinterpret_cast<int*>(rec + 14); }
+
+__device__ int collision(const Ctx& c, int* warn_contactfull) {
+  const DevModel& m = c.m; int lane = c.lane;
+  int ncon = 0;
+  if (c.disableflags & (BMJ_DSBL_CONTACT | BMJ_DSBL_CONSTRAINT)) return 0;
+  for (int base = 0; base < m.npair; base += 32) {
+    int p = base + lane;
+    PairCon pc; pc.n = 0;
+    int g1 = 0, g2 = 0;
+    if (p < m.npair) {
+      g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
+      int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+      double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
+      const double* p1 = W(gxpos) + 3 * g1; const double* p2 = W(gxpos) + 3 * g2;
+      const double* m1 = W(gxmat) + 9 * g1; const double* m2 = W(gxmat) + 9 * g2;
+      bool keep;
+      double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      if (t1 == BMJ_GEOM_PLANE) {
+        double n[3] = {m1[2], m1[5], m1[8]};
+        keep = dot3(dif, n) <= m.geom_rbound[g2] + margin;
+      } else {
+        double bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
+        keep = dot3(dif, dif) <= bound * bound;
+      }
+      if (keep) {
+        double s1[3] = {m.geom_size[3*g1], m.geom_size[3*g1+1], m.geom_size[3*g1+2]};
+        double s2[3] = {m.geom_size[3*g2], m.geom_size[3*g2+1], m.geom_size[3*g2+2]};
+        narrowphase(pc, t1, t2, margin, p1, m1, s1, p2, m2, s2);
+      }
+    }
+    int total;
+    int off = warp_excl_scan(pc.n, lane, &total);
+    if (total == 0) continue;
+    for (int k = 0; k < pc.n; k++) {
+      int idx = ncon + off + k;
+      if (idx >= m.nconmax) continue;
+      double* rec = W(con) + idx * CON_STRIDE;
+      rec[0] = pc.dist[k];
+      for (int i = 0; i < 3; i++) rec[1 + i] = pc.pos[k][i];
+      make_frame(rec + 4, pc.nrm[k], pc.tan);
+      int pr1 = m.geom_priority[g1], pr2 = m.geom_priority[g2];
+      int condim; double mu;
+      if (pr1 != pr2) { int gp = pr1 > pr2 ? g1 : g2; condim = m.geom_condim[gp]; mu = m.geom_friction[3 * gp]; }
+      else { condim = max(m.geom_condim[g1], m.geom_condim[g2]); mu = fmax(m.geom_friction[3 * g1], m.geom_friction[3 * g2]); }
+      rec[13] = mu;
+      int* ii = con_ints(rec);
+      ii[0] = g1; ii[1] = g2; ii[2] = condim; ii[3] = -1;
+    }
+    ncon += total;
+    if (ncon > m.nconmax) { ncon = m.nconmax; *warn_contactfull = 1; break; }
+  }
+  __syncwarp();
+  return ncon;
+}
+
+// ------------------------------------------------------------------------------------------------
+// constraint rows: Jacobian, regulariser D = 1/R and reference acceleration, fused
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double impedance_fn(const double* solimp, double pos, double margin) {
+  double d0 = clampd(solimp[0], BMJ_MINIMP, BMJ_MAXIMP), dmax = clampd(solimp[1], BMJ_MINIMP, BMJ_MAXIMP);
+  double width = fmax(BMJ_MINVAL, solimp[2]), mid = clampd(solimp[3], BMJ_MINIMP, BMJ_MAXIMP), power = fmax(1.0, solimp[4]);
+  double x = fabs(pos - margin) / width;
+  if (x >= 1) return dmax;
+  if (x <= 0) return d0;
+  double y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = pow(x / mid, power) * mid;
+  else y = 1 - pow((1 - x) / (1 - mid), power) * (1 - mid);
+  return d0 + y * (dmax - d0);
+}
+// -> R (before the pyramid rescale) and aref for one row
+__device__ __forceinline__ void row_params(const Ctx& c, const double* solref, const double* solimp, double pos, double margin,
+                                           double diag, double vel, double* R, double* aref, double* imp_out) {
+  double imp = impedance_fn(solimp, pos, margin);
+  double dmax = clampd(solimp[1], BMJ_MINIMP, BMJ_MAXIMP);
+  double K, B;
+  if (solref[0] > 0) {
+    double tc = solref[0], dr = solref[1];
+    if (!(c.disableflags & BMJ_DSBL_REFSAFE)) tc = fmax(tc, 2 * c.m.timestep);
+    K = 1 / fmax(BMJ_MINVAL, dmax * dmax * tc * tc * dr * dr);
+    B = 2 / fmax(BMJ_MINVAL, dmax * tc);
+  } else { K = -solref[0] / fmax(BMJ_MINVAL, dmax * dmax); B = -solref[1] / fmax(BMJ_MINVAL, dmax); }
+  *R = fmax(BMJ_MINVAL, (1 - imp) * diag / imp);
+  *aref = -B * vel - K * imp * (pos - margin);
+  *imp_out = imp;
+}
+
+__device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  double* J = W(J); double* qvel = W(qvel);
+  int nefc = 0;
+  if (c.disableflags & BMJ_DSBL_CONSTRAINT) return 0;
+  // ---- equality (all lanes build one row at a time) ----
+  if (!(c.disableflags & BMJ_DSBL_EQUALITY)) {
+    for (int e = 0; e < m.neq; e++) {
+      if (!m.eq_active0[e]) continue;
+      if (nefc >= m.njmax) { *warn_cnstrfull = 1; return nefc; }
+      const double* data = m.eq_data + 11 * e;
+      int o1 = m.eq_obj1id[e], o2 = m.eq_obj2id[e], et = m.eq_type[e];
+      double pos, diag, deriv = 0;
+      if (et == BMJ_EQ_TENDON) {
+        pos = W(tenlen)[o1] - m.tendon_length0[o1]; diag = m.tendon_invweight0[o1];
+        if (o2 >= 0) {
+          double dif = W(tenlen)[o2] - m.tendon_length0[o2];
+          pos -= data[0] + data[1]*dif + data[2]*dif*dif + data[3]*dif*dif*dif + data[4]*dif*dif*dif*dif;
+          deriv = data[1] + 2*data[2]*dif + 3*data[3]*dif*dif + 4*data[4]*dif*dif*dif;
+          diag += m.tendon_invweight0[o2];
+        } else pos -= data[0];
+      } else {  // joint
+        int qa1 = m.jnt_qposadr[o1];
+        pos = W(qpos)[qa1] - m.qpos0[qa1]; diag = m.dof_invweight0[m.jnt_dofadr[o1]];
+        if (o2 >= 0) {
+          int qa2 = m.jnt_qposadr[o2];
+          double dif = W(qpos)[qa2] - m.qpos0[qa2];
+          pos -= data[0] + data[1]*dif + data[2]*dif*dif + data[3]*dif*dif*dif + data[4]*dif*dif*dif*dif;
+          deriv = data[1] + 2*data[2]*dif + 3*data[3]*dif*dif + 4*data[4]*dif*dif*dif;
+          diag += m.dof_invweight0[m.jnt_dofadr[o2]];
+        } else pos -= data[0];
+      }
+      double part = 0;
+      FOR_LANES(i, nv) {
+        double v;
+        if (et == BMJ_EQ_TENDON) v = W(tenJ)[o1 * ld + i] - (o2 >= 0 ? deriv * W(tenJ)[o2 * ld + i] : 0.0);
+        else v = (i == m.jnt_dofadr[o1] ? 1.0 : 0.0) - ((o2 >= 0 && i == m.jnt_dofadr[o2]) ? deriv : 0.0);
+        J[nefc * ld + i] = v;
+        part += v * qvel[i];
+      }
+      double vel = warp_sum(part), R, aref, imp;
+      row_params(c, m.eq_solref + 2 * e, m.eq_solimp + 5 * e, pos, 0.0, diag, vel, &R, &aref, &imp);
+      if (lane == 0) { W(efcD)[nefc] = 1 / R; W(aref)[nefc] = aref; reinterpret_cast<int*>(W(eqflag))[nefc] = 1; }
+      nefc++;
+    }
+  }
+  __syncwarp();
+  // ---- joint limits (one lane per joint; ordered compaction) ----
+  if (!(c.disableflags & BMJ_DSBL_LIMIT)) {
+    for (int base = 0; base < m.njnt; base += 32) {
+      int j = base + lane;
+      int cnt = 0; double dist[2]; int side[2];
+      if (j < m.njnt && m.jnt_limited[j]) {
+        int t = m.jnt_type[j];
+        if (t == BMJ_JNT_SLIDE || t == BMJ_JNT_HINGE) {
+          double value = W(qpos)[m.jnt_qposadr[j]], margin = m.jnt_margin[j];
+          for (int s = -1; s <= 1; s += 2) {
+            double d = s * (m.jnt_range[2 * j + (s + 1) / 2] - value);
+            if (d < margin) { dist[cnt] = d; side[cnt] = s; cnt++; }
+          }
+        }
+      }
+      int total, off = warp_excl_scan(cnt, lane, &total);
+      for (int k = 0; k < cnt; k++) {
+        int r = nefc + off + k;
+        if (r >= m.njmax) continue;
+        int da = m.jnt_dofadr[j];
+        double* row = J + r * ld;
+        for (int i = 0; i < nv; i++) row[i] = 0;
+        row[da] = -side[k];
+        double vel = -side[k] * qvel[da], R, aref, imp;
+        row_params(c, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist[k], m.jnt_margin[j], m.dof_invweight0[da], vel, &R, &aref, &imp);
+        W(efcD)[r] = 1 / R; W(aref)[r] = aref; reinterpret_cast<int*>(W(eqflag))[r] = 0;
+      }
+      nefc += total;
+      if (nefc > m.njmax) { nefc = m.njmax; *warn_cnstrfull = 1; return nefc; }
+    }
+  }
+  __syncwarp();
+  // ---- contacts (lanes = dofs) ----
+  for (int ci = 0; ci < ncon; ci++) {
+    double* rec = W(con) + ci * CON_STRIDE;
+    int* ii = con_ints(rec);
+    int g1 = ii[0], g2 = ii[1], dim = ii[2];
+    double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]), gap = fmax(m.geom_gap[g1], m.geom_gap[g2]);
+    double includemargin = margin - gap, dist = rec[0];
+    if (dist >= includemargin) continue;
+    int nrow = dim == 1 ? 1 : 4;   // condim 1 or 3 (pyramidal); model_create rejects 4/6
+    if (nefc + nrow > m.njmax) { *warn_cnstrfull = 1; break; }
+    int b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
+    double pos[3] = {rec[1], rec[2], rec[3]};
+    double fr[9];
+    for (int i = 0; i < 9; i++) fr[i] = rec[4 + i];
+    double mu = rec[13];
+    double off1[3], off2[3];
+    int r1 = m.body_rootid[b1], r2 = m.body_rootid[b2];
+    for (int i = 0; i < 3; i++) { off1[i] = pos[i] - W(scom)[3 * r1 + i]; off2[i] = pos[i] - W(scom)[3 * r2 + i]; }
+    double pv[3] = {0, 0, 0};
+    for (int i = lane; i < nv; i += 32) {
+      unsigned w1 = (unsigned)m.body_dofmask[2 * b1 + (i >> 5)], w2 = (unsigned)m.body_dofmask[2 * b2 + (i >> 5)];
+      bool in1 = (w1 >> (i & 31)) & 1, in2 = (w2 >> (i & 31)) & 1;
+      double jd[3] = {0, 0, 0};
+      if (in1 || in2) {
+        const double* cd = W(cdof) + 6 * i;
+        double tmp[3];
+        if (in2) { cross3(tmp, cd, off2); for (int k = 0; k < 3; k++) jd[k] += cd[3 + k] + tmp[k]; }
+        if (in1) { cross3(tmp, cd, off1); for (int k = 0; k < 3; k++) jd[k] -= cd[3 + k] + tmp[k]; }
+      }
+      double jn = dot3(fr, jd);
+      if (dim == 1) { J[nefc * ld + i] = jn; pv[0] += jn * qvel[i]; }
+      else {
+        double jt1 = dot3(fr + 3, jd), jt2 = dot3(fr + 6, jd);
+        J[nefc * ld + i] = jn + mu * jt1; J[(nefc + 1) * ld + i] = jn - mu * jt1;
+        J[(nefc + 2) * ld + i] = jn + mu * jt2; J[(nefc + 3) * ld + i] = jn - mu * jt2;
+        pv[0] += jn * qvel[i]; pv[1] += jt1 * qvel[i]; pv[2] += jt2 * qvel[i];
+      }
+    }
+    double vn = warp_sum(pv[0]);
+    // contact parameter mixing (solref / solimp)
+    double solref[2], solimp[5];
+    int pr1 = m.geom_priority[g1], pr2 = m.geom_priority[g2];
+    if (pr1 != pr2) {
+      int gp = pr1 > pr2 ? g1 : g2;
+      for (int i = 0; i < 2; i++) solref[i] = m.geom_solref[2 * gp + i];
+      for (int i = 0; i < 5; i++) solimp[i] = m.geom_solimp[5 * gp + i];
+    } else {
+      double s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2], mix;
+      if (s1 >= BMJ_MINVAL && s2 >= BMJ_MINVAL) mix = s1 / (s1 + s2);
+      else if (s1 < BMJ_MINVAL && s2 < BMJ_MINVAL) mix = 0.5;
+      else if (s1 < BMJ_MINVAL) mix = 0.0; else mix = 1.0;
+      if (m.geom_solref[2 * g1] > 0 && m.geom_solref[2 * g2] > 0)
+        for (int i = 0; i < 2; i++) solref[i] = mix * m.geom_solref[2 * g1 + i] + (1 - mix) * m.geom_solref[2 * g2 + i];
+      else
+        for (int i = 0; i < 2; i++) solref[i] = fmin(m.geom_solref[2 * g1 + i], m.geom_solref[2 * g2 + i]);
+      for (int i = 0; i < 5; i++) solimp[i] = mix * m.geom_solimp[5 * g1 + i] + (1 - mix) * m.geom_solimp[5 * g2 + i];
+    }
+    double tran = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+    if (dim == 1) {
+      double R, aref, imp;
+      row_params(c, solref, solimp, dist, includemargin, tran, vn, &R, &aref, &imp);
+      if (lane == 0) { W(efcD)[nefc] = 1 / R; W(aref)[nefc] = aref; reinterpret_cast<int*>(W(eqflag))[nefc] = 0; }
+    } else {
+      double vt1 = warp_sum(pv[1]), vt2 = warp_sum(pv[2]);
+      double mureg = mu / sqrt(fmax(BMJ_MINVAL, m.impratio));
+      if (lane < 4) {
+        double vel = vn + ((lane & 1) ? -mu : mu) * (lane < 2 ? vt1 : vt2);
+        double R, aref, imp;
+        // every edge: same pos / margin / diagApprox (tran + mu^2 tran); shared R_py = 2 mu^2 R(first edge)
+        row_params(c, solref, solimp, dist, includemargin, tran + mu * mu * tran, vel, &R, &aref, &imp);
+        double Rpy = fmax(BMJ_MINVAL, 2 * mureg * mureg * R);
+        W(efcD)[nefc + lane] = 1 / Rpy; W(aref)[nefc + lane] = aref; reinterpret_cast<int*>(W(eqflag))[nefc + lane] = 0;
+      }
+    }
+    if (lane == 0) ii[3] = nefc;
+    nefc += nrow;
+  }
+  __syncwarp();
+  return nefc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// velocity stage: cvel, cdof_dot, passive forces, RNE bias
+// ------------------------------------------------------------------------------------------------
+__device__ void fwd_velocity(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane;
+  double* cvel = W(cvel); double* cacc = W(cacc); double* cfrc = W(cfrc); double* qvel = W(qvel);
+  if (lane < 6) { cvel[lane] = 0; cfrc[lane] = 0; cacc[lane] = 0; }
+  if (lane < 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) cacc[3 + lane] = -m.gravity[lane];
+  __syncwarp();
+  for (int l = 1; l < m.nlevel; l++) {
+    int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
+    for (int k = a0 + lane; k < a1; k += 32) {
+      int b = m.level_body[k], p = m.body_parentid[b];
+      double cv[6], ca[6];
+      for (int i = 0; i < 6; i++) { cv[i] = cvel[6 * p + i]; ca[i] = cacc[6 * p + i]; }
+      int j0 = m.body_jntadr[b], jn = m.body_jntnum[b];
+      for (int j = j0; j < j0 + jn; j++) {
+        int da = m.jnt_dofadr[j], t = m.jnt_type[j];
+        double* cdd = W(cdofdot); const double* cd = W(cdof);
+        if (t == BMJ_JNT_FREE) {
+          for (int i = 0; i < 18; i++) cdd[6 * da + i] = 0;
+          for (int q = 0; q < 3; q++) for (int i = 0; i < 6; i++) cv[i] += cd[6 * (da + q) + i] * qvel[da + q];
+          da += 3;
+        }
+        if (t == BMJ_JNT_FREE || t == BMJ_JNT_BALL) {
+          for (int q = 0; q < 3; q++) { double r[6]; cross_motion(r, cv, cd + 6 * (da + q)); for (int i = 0; i < 6; i++) cdd[6 * (da + q) + i] = r[i]; }
+          for (int q = 0; q < 3; q++) for (int i = 0; i < 6; i++) cv[i] += cd[6 * (da + q) + i] * qvel[da + q];
+        } else {
+          double r[6]; cross_motion(r, cv, cd + 6 * da);
+          for (int i = 0; i < 6; i++) { cdd[6 * da + i] = r[i]; cv[i] += cd[6 * da + i] * qvel[da]; }
+        }
+      }
+      int d0 = m.body_dofadr[b], dn = m.body_dofnum[b];
+      for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * qvel[q];
+      double t1[6], t2[6], t3[6];
+      mul_inert_vec(t1, W(cinert) + 10 * b, ca);
+      mul_inert_vec(t2, W(cinert) + 10 * b, cv);
+      cross_force(t3, cv, t2);
+      for (int i = 0; i < 6; i++) { cvel[6 * b + i] = cv[i]; cacc[6 * b + i] = ca[i]; cfrc[6 * b + i] = t1[i] + t3[i]; }
+    }
+    __syncwarp();
+  }
+  tree_accumulate(c, cfrc, 6, false);
+  FOR_LANES(k, m.nv) {
+    int b = m.dof_bodyid[k];
+    double s = 0;
+    for (int i = 0; i < 6; i++) s += W(cdof)[6 * k + i] * cfrc[6 * b + i];
+    W(bias)[k] = s;
+    double ps = 0;
+    if (!(c.disableflags & BMJ_DSBL_PASSIVE)) {
+      int j = m.dof_jntid[k], t = m.jnt_type[j];
+      if ((t == BMJ_JNT_SLIDE || t == BMJ_JNT_HINGE) && m.jnt_stiffness[j] != 0) {
+        int qa = m.jnt_qposadr[j];
+        ps -= m.jnt_stiffness[j] * (W(qpos)[qa] - m.qpos_spring[qa]);
+      }
+      ps -= m.dof_damping[k] * qvel[k];
+    }
+    W(passive)[k] = ps;
+  }
+  __syncwarp();
+}
+
+__device__ void subtree_vel(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane;
+  double* sl = W(slinvel);
+  FOR_LANES(b, m.nbody) {
+    int root = m.body_rootid[b];
+    double dif[3], tmp[3];
+    for (int i = 0; i < 3; i++) dif[i] = W(xipos)[3 * b + i] - W(scom)[3 * root + i];
+    cross3(tmp, dif, W(cvel) + 6 * b);
+    for (int i = 0; i < 3; i++) sl[3 * b + i] = m.body_mass[b] * (W(cvel)[6 * b + 3 + i] - tmp[i]);
+  }
+  __syncwarp();
+  tree_accumulate(c, sl, 3, true);
+  FOR_LANES(b, m.nbody) { double sm = fmax(BMJ_MINVAL, m.body_subtreemass[b]); for (int i = 0; i < 3; i++) sl[3 * b + i] /= sm; }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// acceleration stage
+// ------------------------------------------------------------------------------------------------
+__device__ void fwd_actuation(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  bool off = c.disableflags & BMJ_DSBL_ACTUATION;
+  FOR_LANES(a, m.nu) {
+    double force = 0;
+    int aa = m.actuator_actadr[a];
+    if (aa >= 0) W(actdot)[aa] = 0;
+    if (!off) {
+      double ctrl = W(ctrl)[a];
+      if (m.actuator_ctrllimited[a] && !(c.disableflags & BMJ_DSBL_CLAMPCTRL))
+        ctrl = clampd(ctrl, m.actuator_ctrlrange[2 * a], m.actuator_ctrlrange[2 * a + 1]);
+      double input = ctrl;
+      int dt = m.actuator_dyntype[a];
+      if (dt == BMJ_DYN_INTEGRATOR) { W(actdot)[aa] = ctrl; input = W(act)[aa]; }
+      else if (dt == BMJ_DYN_FILTER) { double tau = fmax(BMJ_MINVAL, m.actuator_dynprm[a]); W(actdot)[aa] = (ctrl - W(act)[aa]) / tau; input = W(act)[aa]; }
+      double gear = m.actuator_gear[a], length, velocity;
+      if (m.actuator_trntype[a] == BMJ_TRN_JOINT) {
+        int j = m.actuator_trnid[a];
+        length = gear * W(qpos)[m.jnt_qposadr[j]]; velocity = gear * W(qvel)[m.jnt_dofadr[j]];
+      } else {
+        int t = m.actuator_trnid[a];
+        length = gear * W(tenlen)[t];
+        double s = 0; for (int i = 0; i < nv; i++) s += gear * W(tenJ)[t * ld + i] * W(qvel)[i];
+        velocity = s;
+      }
+      const double* gp = m.actuator_gainprm + 3 * a; const double* bp = m.actuator_biasprm + 3 * a;
+      double gain = gp[0];
+      if (m.actuator_gaintype[a] == BMJ_GAIN_AFFINE) gain += gp[1] * length + gp[2] * velocity;
+      double bias = 0;
+      if (m.actuator_biastype[a] == BMJ_BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
+      force = gain * input + bias;
+      if (m.actuator_forcelimited[a]) force = clampd(force, m.actuator_forcerange[2 * a], m.actuator_forcerange[2 * a + 1]);
+    }
+    W(actforce)[a] = force;
+  }
+  __syncwarp();
+  FOR_LANES(i, nv) {
+    double s = 0;
+    for (int a = 0; a < m.nu; a++) {
+      double gear = m.actuator_gear[a], mom;
+      if (m.actuator_trntype[a] == BMJ_TRN_JOINT) mom = (m.jnt_dofadr[m.actuator_trnid[a]] == i) ? gear : 0.0;
+      else mom = gear * W(tenJ)[m.actuator_trnid[a] * ld + i];
+      s += mom * W(actforce)[a];
+    }
+    W(qfact)[i] = s;
+  }
+  __syncwarp();
+}
+
+__device__ void fwd_acceleration(const Ctx& c, const b200mj_io& io, int env) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
+  FOR_LANES(i, nv) {
+    double s = W(passive)[i] - W(bias)[i] + W(qfact)[i];
+    if (io.qfrc_applied) s += io.qfrc_applied[(size_t)env * nv + i];
+    W(smooth)[i] = s;
+  }
+  if (io.xfrc_applied) {
+    for (int b = 1; b < m.nbody; b++) {
+      const double* xf = io.xfrc_applied + ((size_t)env * m.nbody + b) * 6;
+      double f[6]; bool any = false;
+      for (int i = 0; i < 6; i++) { f[i] = xf[i]; any |= (f[i] != 0); }
+      if (!any) continue;
+      int root = m.body_rootid[b];
+      double off[3];
+      for (int i = 0; i < 3; i++) off[i] = W(xipos)[3 * b + i] - W(scom)[3 * root + i];
+      FOR_LANES(i, nv) {
+        unsigned w = (unsigned)m.body_dofmask[2 * b + (i >> 5)];
+        if (!((w >> (i & 31)) & 1)) continue;
+        const double* cd = W(cdof) + 6 * i;
+        double tmp[3]; cross3(tmp, cd, off);
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (cd[3 + k] + tmp[k]) * f[k] + cd[k] * f[3 + k];
+        W(smooth)[i] += s;
+      }
+    }
+  }
+  __syncwarp();
+  chol_solve(W(LM), W(smooth), W(qaccs), nv, m.ldv, lane);
+}
+
+// --- Newton solver ---------------------------------------------------------------------------------
+struct Primal { double cost, gauss; };
+
+// Ma = M qacc ; jar = J qacc - aref
+__device__ void compute_Ma_jar(const Ctx& c, int nefc) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  FOR_LANES(i, nv) { double s = 0; const double* Mi = W(M) + i * ld; for (int j = 0; j < nv; j++) s += Mi[j] * W(qacc)[j]; W(Ma)[i] = s; }
+  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; for (int i = 0; i < nv; i++) s += Jr[i] * W(qacc)[i]; W(jar)[r] = s - W(aref)[r]; }
+  __syncwarp();
+}
+
+__device__ Primal constraint_update(const Ctx& c, int nefc) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  const int* eqf = reinterpret_cast<const int*>(W(eqflag));
+  double cpart = 0;
+  FOR_LANES(r, nefc) {
+    double jar = W(jar)[r], D = W(efcD)[r];
+    bool act = eqf[r] || jar < 0;
+    W(efcSD)[r] = act ? D : 0.0;
+    W(force)[r] = act ? -D * jar : 0.0;
+    if (act) cpart += 0.5 * D * jar * jar;
+  }
+  __syncwarp();
+  double gpart = 0;
+  FOR_LANES(i, nv) {
+    double s = 0;
+    for (int r = 0; r < nefc; r++) s += W(J)[r * ld + i] * W(force)[r];
+    W(qcon)[i] = s;
+    gpart += (W(Ma)[i] - W(smooth)[i]) * (W(qacc)[i] - W(qaccs)[i]);
+  }
+  Primal p;
+  p.gauss = 0.5 * warp_sum(gpart);
+  p.cost = warp_sum(cpart) + p.gauss;
+  __syncwarp();
+  return p;
+}
+
+// grad, H = M + J^T diag(SD) J, factor, search = -H^-1 grad ; returns |grad|
+__device__ double newton_direction(const Ctx& c, int nefc) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  double gpart = 0;
+  FOR_LANES(i, nv) { double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; W(grad)[i] = g; gpart += g * g; }
+  double gnorm = sqrt(warp_sum(gpart));
+  // lane j owns column j of H (and column j+32)
+  for (int j = lane; j < nv; j += 32) {
+    for (int i = 0; i < nv; i++) {
+      double acc = W(M)[i * ld + j];
+      for (int r = 0; r < nefc; r++) {
+        double sd = W(efcSD)[r];
+        acc += (sd * W(J)[r * ld + i]) * W(J)[r * ld + j];
+      }
+      W(H)[i * ld + j] = acc;
+    }
+  }
+  __syncwarp();
+  chol_factor(W(H), W(H), nv, ld, lane);   // in place: column j only reads columns < j and A[.][j]
+  chol_solve(W(H), W(grad), W(search), nv, ld, lane);
+  FOR_LANES(i, nv) W(search)[i] = -W(search)[i];
+  __syncwarp();
+  return gnorm;
+}
+
+__device__ __forceinline__ void ls_eval(const Ctx& c, int nefc, double alpha, const double* qg, double* d1, double* d2) {
+  int lane = c.lane;
+  const int* eqf = reinterpret_cast<const int*>(W(eqflag));
+  double q1 = 0, q2 = 0;
+  FOR_LANES(r, nefc) {
+    double jar = W(jar)[r], jv = W(jv)[r];
+    double x = jar + alpha * jv;
+    if (eqf[r] || x < 0) { double D = W(efcD)[r]; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
+  }
+  q1 = warp_sum(q1) + qg[1]; q2 = warp_sum(q2) + qg[2];
+  *d1 = 2 * alpha * q2 + q1;
+  *d2 = 2 * q2;
+}
+
+__device__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  double sp = 0;
+  FOR_LANES(i, nv) sp += W(search)[i] * W(search)[i];
+  double snorm = sqrt(warp_sum(sp));
+  if (snorm < BMJ_MINVAL) return 0;
+  double gtol = m.tolerance * m.ls_tolerance * snorm * (m.meaninertia * max(1, nv));
+  double g1 = 0, g2 = 0;
+  FOR_LANES(i, nv) {
+    double s = 0; const double* Mi = W(M) + i * ld;
+    for (int j = 0; j < nv; j++) s += Mi[j] * W(search)[j];
+    W(Mv)[i] = s;
+    g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
+  }
+  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; for (int i = 0; i < nv; i++) s += Jr[i] * W(search)[i]; W(jv)[r] = s; }
+  double qg[3] = {pr.gauss, warp_sum(g1), warp_sum(g2)};
+  __syncwarp();
+  double d1, d2;
+  ls_eval(c, nefc, 0.0, qg, &d1, &d2);
+  if (d1 >= 0 || d2 <= 0) return 0;
+  double lo = 0, dlo = d1, hi = 0, dhi = 0; bool have_hi = false;
+  double alpha = -d1 / d2, best = 0;
+  for (int it = 0; it < m.ls_iterations; it++) {
+    double e1, e2;
+    ls_eval(c, nefc, alpha, qg, &e1, &e2);
+    best = alpha;
+    if (fabs(e1) < gtol) break;
+    if (e1 < 0) { lo = alpha; dlo = e1; } else { hi = alpha; dhi = e1; have_hi = true; }
+    double next = alpha - e1 / e2;
+    if (have_hi) { if (!(next > lo && next < hi)) next = lo + (hi - lo) * (-dlo) / (dhi - dlo); }
+    else if (next <= lo) next = 2 * alpha + 1e-12;
+    if (next == alpha) break;
+    alpha = next;
+  }
+  return best;
+}
+
+__device__ int solve_newton(const Ctx& c, int nefc) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
+  Primal pr;
+  if (!(c.disableflags & BMJ_DSBL_WARMSTART)) {
+    FOR_LANES(i, nv) W(qacc)[i] = W(qaccws)[i];
+    __syncwarp();
+    compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
+    double cost_warm = pr.cost;
+    FOR_LANES(i, nv) W(qacc)[i] = W(qaccs)[i];
+    __syncwarp();
+    compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
+    if (cost_warm < pr.cost) {
+      FOR_LANES(i, nv) W(qacc)[i] = W(qaccws)[i];
+      __syncwarp();
+      compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
+    }
+  } else {
+    FOR_LANES(i, nv) W(qacc)[i] = W(qaccs)[i];
+    __syncwarp();
+    compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
+  }
+  newton_direction(c, nefc);
+  double scale = 1 / (m.meaninertia * max(1, nv));
+  int iter = 0;
+  while (iter < m.iterations) {
+    double alpha = line_search(c, nefc, pr);
+    if (alpha == 0) break;
+    FOR_LANES(i, nv) { W(qacc)[i] += alpha * W(search)[i]; W(Ma)[i] += alpha * W(Mv)[i]; }
+    FOR_LANES(r, nefc) W(jar)[r] += alpha * W(jv)[r];
+    __syncwarp();
+    double oldcost = pr.cost;
+    pr = constraint_update(c, nefc);
+    double gnorm = newton_direction(c, nefc);
+    iter++;
+    double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
+    if (improvement < m.tolerance || gradient < m.tolerance) break;
+  }
+  return iter;
+}
+
+// cacc / cfrc_int with qacc + external contact forces (for accelerometer / force / torque sensors)
+__device__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, int ncon) {
+  const DevModel& m = c.m; int lane = c.lane;
+  double* cext = W(cfrcext); double* cacc = W(cacc); double* cint = W(cfrc);
+  for (int i = lane; i < 6 * m.nbody; i += 32) cext[i] = 0;
+  __syncwarp();
+  if (io.xfrc_applied) {
+    FOR_LANES(b, m.nbody) {
+      if (b == 0) continue;
+      const double* xf = io.xfrc_applied + ((size_t)env * m.nbody + b) * 6;
+      int root = m.body_rootid[b];
+      double dif[3], tq[3], f[3] = {xf[0], xf[1], xf[2]};
+      for (int i = 0; i < 3; i++) dif[i] = W(xipos)[3 * b + i] - W(scom)[3 * root + i];
+      cross3(tq, dif, f);
+      for (int i = 0; i < 3; i++) { cext[6 * b + i] += xf[3 + i] + tq[i]; cext[6 * b + 3 + i] += f[i]; }
+    }
+    __syncwarp();
+  }
+  // contacts: serial over contacts (lane 0) keeps the accumulation order fixed
+  if (lane == 0) {
+    for (int ci = 0; ci < ncon; ci++) {
+      double* rec = W(con) + ci * CON_STRIDE; int* ii = con_ints(rec);
+      int adr = ii[3]; if (adr < 0) continue;
+      double f[3] = {0, 0, 0}, mu = rec[13];
+      if (ii[2] == 1) f[0] = W(force)[adr];
+      else for (int k = 1; k < 3; k++) { double fp = W(force)[adr + 2 * (k - 1)], fn = W(force)[adr + 2 * (k - 1) + 1]; f[0] += fp + fn; f[k] = (fp - fn) * mu; }
+      double fw[3]; matT_vec(fw, rec + 4, f);
+      int bb[2] = {m.geom_bodyid[ii[0]], m.geom_bodyid[ii[1]]};
+      for (int side = 0; side < 2; side++) {
+        int b = bb[side]; if (b <= 0) continue;
+        double sgn = side == 0 ? -1 : 1; int root = m.body_rootid[b];
+        double dif[3], tq[3];
+        for (int i = 0; i < 3; i++) dif[i] = rec[1 + i] - W(scom)[3 * root + i];
+        cross3(tq, dif, fw);
+        for (int i = 0; i < 3; i++) { cext[6 * b + i] += sgn * tq[i]; cext[6 * b + 3 + i] += sgn * fw[i]; }
+      }
+    }
+  }
+  if (lane < 6) { cacc[lane] = 0; cint[lane] = 0; }
+  if (lane < 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) cacc[3 + lane] = -m.gravity[lane];
+  __syncwarp();
+  for (int l = 1; l < m.nlevel; l++) {
+    int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
+    for (int k = a0 + lane; k < a1; k += 32) {
+      int b = m.level_body[k], p = m.body_parentid[b];
+      double ca[6];
+      for (int i = 0; i < 6; i++) ca[i] = cacc[6 * p + i];
+      int d0 = m.body_dofadr[b], dn = m.body_dofnum[b];
+      for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * W(qvel)[q] + W(cdof)[6 * q + i] * W(qacc)[q];
+      double t1[6], t2[6], t3[6];
+      mul_inert_vec(t1, W(cinert) + 10 * b, ca);
+      mul_inert_vec(t2, W(cinert) + 10 * b, W(cvel) + 6 * b);
+      cross_force(t3, W(cvel) + 6 * b, t2);
+      for (int i = 0; i < 6; i++) { cacc[6 * b + i] = ca[i]; cint[6 * b + i] = t1[i] + t3[i] - cext[6 * b + i]; }
+    }
+    __syncwarp();
+  }
+  tree_accumulate(c, cint, 6, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sensors (stage 1 = position, 2 = velocity, 3 = acceleration); results staged in the workspace
+// ------------------------------------------------------------------------------------------------
+__device__ void sensors(const Ctx& c, int stage, int ncon) {
+  const DevModel& m = c.m; int lane = c.lane;
+  if (c.disableflags & BMJ_DSBL_SENSOR) return;
+  FOR_LANES(s, m.nsensor) {
+    if (m.sensor_needstage[s] != stage) continue;
+    double* out = W(sens) + m.sensor_adr[s];
+    int id = m.sensor_objid[s], st = m.sensor_type[s];
+    if (st == BMJ_SENS_JOINTPOS) out[0] = W(qpos)[m.jnt_qposadr[id]];
+    else if (st == BMJ_SENS_JOINTVEL) out[0] = W(qvel)[m.jnt_dofadr[id]];
+    else if (st == BMJ_SENS_ACTUATORFRC) out[0] = W(actforce)[id];
+    else if (st == BMJ_SENS_SUBTREECOM) for (int i = 0; i < 3; i++) out[i] = W(scom)[3 * id + i];
+    else if (st == BMJ_SENS_SUBTREELINVEL) for (int i = 0; i < 3; i++) out[i] = W(slinvel)[3 * id + i];
+    else if (st == BMJ_SENS_FRAMEPOS) {
+      double p[3], pm[9];
+      int ot = m.sensor_objtype[s];
+      if (ot == BMJ_OBJ_SITE) site_frame(c, id, p, pm);
+      else if (ot == BMJ_OBJ_GEOM) for (int i = 0; i < 3; i++) p[i] = W(gxpos)[3 * id + i];
+      else if (ot == BMJ_OBJ_BODY) for (int i = 0; i < 3; i++) p[i] = W(xipos)[3 * id + i];
+      else for (int i = 0; i < 3; i++) p[i] = W(xpos)[3 * id + i];
+      int rid = m.sensor_refid[s];
+      if (rid < 0) { for (int i = 0; i < 3; i++) out[i] = p[i]; }
+      else {
+        double rp[3], rm[9]; int rt = m.sensor_reftype[s];
+        if (rt == BMJ_OBJ_SITE) site_frame(c, rid, rp, rm);
+        else if (rt == BMJ_OBJ_GEOM) { for (int i = 0; i < 3; i++) rp[i] = W(gxpos)[3 * rid + i]; for (int i = 0; i < 9; i++) rm[i] = W(gxmat)[9 * rid + i]; }
+        else if (rt == BMJ_OBJ_BODY) {
+          for (int i = 0; i < 3; i++) rp[i] = W(xipos)[3 * rid + i];
+          double q[4], iq[4] = {m.body_iquat[4*rid], m.body_iquat[4*rid+1], m.body_iquat[4*rid+2], m.body_iquat[4*rid+3]};
+          mul_quat(q, W(xquat) + 4 * rid, iq); quat2mat(rm, q);
+        } else { for (int i = 0; i < 3; i++) rp[i] = W(xpos)[3 * rid + i]; for (int i = 0; i < 9; i++) rm[i] = W(xmat)[9 * rid + i]; }
+        double dif[3] = {p[0] - rp[0], p[1] - rp[1], p[2] - rp[2]};
+        matT_vec(out, rm, dif);
+      }
+    } else if (st == BMJ_SENS_VELOCIMETER || st == BMJ_SENS_GYRO || st == BMJ_SENS_ACCELEROMETER || st == BMJ_SENS_FORCE || st == BMJ_SENS_TORQUE) {
+      double sp[3], sm[9]; site_frame(c, id, sp, sm);
+      int b = m.site_bodyid[id], root = m.body_rootid[b];
+      double dif[3], tmp[3];
+      for (int i = 0; i < 3; i++) dif[i] = sp[i] - W(scom)[3 * root + i];
+      const double* cv = W(cvel) + 6 * b;
+      if (st == BMJ_SENS_GYRO) matT_vec(out, sm, cv);
+      else if (st == BMJ_SENS_VELOCIMETER) {
+        cross3(tmp, dif, cv); double lin[3] = {cv[3] - tmp[0], cv[4] - tmp[1], cv[5] - tmp[2]}; matT_vec(out, sm, lin);
+      } else if (st == BMJ_SENS_ACCELEROMETER) {
+        const double* ca = W(cacc) + 6 * b;
+        cross3(tmp, dif, ca); double lin[3] = {ca[3] - tmp[0], ca[4] - tmp[1], ca[5] - tmp[2]}, acc[3], va[3], vl[3], corr[3];
+        matT_vec(acc, sm, lin);
+        cross3(tmp, dif, cv); double vlin[3] = {cv[3] - tmp[0], cv[4] - tmp[1], cv[5] - tmp[2]};
+        matT_vec(va, sm, cv); matT_vec(vl, sm, vlin);
+        cross3(corr, va, vl);
+        for (int i = 0; i < 3; i++) out[i] = acc[i] + corr[i];
+      } else if (st == BMJ_SENS_FORCE) matT_vec(out, sm, W(cfrc) + 6 * b + 3);
+      else {
+        const double* cf = W(cfrc) + 6 * b;
+        cross3(tmp, dif, cf + 3); double tq[3] = {cf[0] - tmp[0], cf[1] - tmp[1], cf[2] - tmp[2]}; matT_vec(out, sm, tq);
+      }
+    } else if (st == BMJ_SENS_TOUCH) {
+      double sp[3], sm[9]; site_frame(c, id, sp, sm);
+      int b = m.site_bodyid[id]; double total = 0;
+      double sz[3] = {m.site_size[3*id], m.site_size[3*id+1], m.site_size[3*id+2]}; int stp = m.site_type[id];
+      for (int ci = 0; ci < ncon; ci++) {
+        double* rec = W(con) + ci * CON_STRIDE; int* ii = con_ints(rec);
+        if (ii[3] < 0) continue;
+        if (m.geom_bodyid[ii[0]] != b && m.geom_bodyid[ii[1]] != b) continue;
+        double nf = 0;
+        if (ii[2] == 1) nf = W(force)[ii[3]]; else for (int k = 0; k < 4; k++) nf += W(force)[ii[3] + k];
+        if (nf <= 0) continue;
+        double dif[3] = {rec[1] - sp[0], rec[2] - sp[1], rec[3] - sp[2]}, loc[3];
+        matT_vec(loc, sm, dif);
+        bool in = false;
+        if (stp == BMJ_GEOM_SPHERE) in = dot3(loc, loc) < sz[0] * sz[0];
+        else if (stp == BMJ_GEOM_CAPSULE) { double z = clampd(loc[2], -sz[1], sz[1]), dz = loc[2] - z; in = loc[0]*loc[0] + loc[1]*loc[1] + dz*dz < sz[0]*sz[0]; }
+        else if (stp == BMJ_GEOM_ELLIPSOID) in = (loc[0]/sz[0])*(loc[0]/sz[0]) + (loc[1]/sz[1])*(loc[1]/sz[1]) + (loc[2]/sz[2])*(loc[2]/sz[2]) < 1;
+        else if (stp == BMJ_GEOM_CYLINDER) in = fabs(loc[2]) < sz[1] && loc[0]*loc[0] + loc[1]*loc[1] < sz[0]*sz[0];
+        else if (stp == BMJ_GEOM_BOX) in = fabs(loc[0]) < sz[0] && fabs(loc[1]) < sz[1] && fabs(loc[2]) < sz[2];
+        if (in) total += nf;
+      }
+      out[0] = total;
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// integration
+// ------------------------------------------------------------------------------------------------
+// qpos <- integrate(qpos, a*vel, h)
+__device__ void integrate_pos(const Ctx& c, double* qpos, const double* vel, double a, double h) {
+  const DevModel& m = c.m; int lane = c.lane;
+  FOR_LANES(j, m.njnt) {
+    int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j], t = m.jnt_type[j];
+    if (t == BMJ_JNT_FREE) {
+      for (int i = 0; i < 3; i++) qpos[qa + i] += h * (a * vel[da + i]);
+      double w[3] = {a * vel[da + 3], a * vel[da + 4], a * vel[da + 5]};
+      quat_integrate(qpos + qa + 3, w, h);
+    } else if (t == BMJ_JNT_BALL) { double w[3] = {a * vel[da], a * vel[da + 1], a * vel[da + 2]}; quat_integrate(qpos + qa, w, h); }
+    else qpos[qa] += h * (a * vel[da]);
+  }
+  __syncwarp();
+}
+
+__device__ void advance_act(const Ctx& c, double* act, const double* actdot, double scale, double h) {
+  const DevModel& m = c.m; int lane = c.lane;
+  FOR_LANES(a, m.nu) {
+    int aa = m.actuator_actadr[a];
+    if (aa < 0) continue;
+    double v = act[aa] + h * (scale * actdot[aa]);
+    if (m.actuator_actlimited[a]) v = clampd(v, m.actuator_actrange[2 * a], m.actuator_actrange[2 * a + 1]);
+    act[aa] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+struct StepState { int ncon, nefc, niter; int warn[BMJ_NWARNING]; };
+
+__device__ bool check_bad(const Ctx& c, const double* v, int n) {
+  int lane = c.lane; int badf = 0;
+  FOR_LANES(i, n) if (bad_value(v[i])) badf = 1;
+  return __any_sync(FULL, badf);
+}
+
+__device__ void reset_state(const Ctx& c, double* time) {
+  const DevModel& m = c.m; int lane = c.lane;
+  FOR_LANES(i, m.nq) W(qpos)[i] = m.qpos0[i];
+  FOR_LANES(i, m.nv) { W(qvel)[i] = 0; W(qaccws)[i] = 0; }
+  FOR_LANES(i, m.na) W(act)[i] = 0;
+  *time = 0;
+  __syncwarp();
+}
+
+// position + velocity stages on the workspace state
+__device__ void stage_posvel(const Ctx& c, StepState& st, bool with_constraints) {
+  kinematics(c);
+  com_pos(c);
+  crb_and_factor(c);
+  st.ncon = 0; st.nefc = 0;
+  if (with_constraints) {
+    int wfull = 0;
+    st.ncon = collision(c, &wfull);
+    if (wfull) st.warn[BMJ_WARN_CONTACTFULL]++;
+    int cfull = 0;
+    st.nefc = make_constraint(c, st.ncon, &cfull);
+    if (cfull) st.warn[BMJ_WARN_CNSTRFULL]++;
+  }
+  fwd_velocity(c);
+}
+
+// acceleration stage: qacc from the current pos/vel stage results
+__device__ void stage_acc(const Ctx& c, const b200mj_io& io, int env, StepState& st) {
+  const DevModel& m = c.m; int lane = c.lane;
+  fwd_actuation(c);
+  fwd_acceleration(c, io, env);
+  if (st.nefc == 0) {
+    FOR_LANES(i, m.nv) { W(qacc)[i] = W(qaccs)[i]; W(qcon)[i] = 0; }
+    st.niter = 0;
+    __syncwarp();
+  } else st.niter = solve_newton(c, st.nefc);
+}
+
+__device__ void euler_step(const Ctx& c, double* time) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv; double h = m.timestep;
+  advance_act(c, W(act), W(actdot), 1.0, h);
+  if (m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
+    for (int j = lane; j < nv; j += 32) for (int i = 0; i < nv; i++) W(H)[i * ld + j] = W(M)[i * ld + j] + (i == j ? h * m.dof_damping[i] : 0.0);
+    FOR_LANES(i, nv) W(tmpv)[i] = W(smooth)[i] + W(qcon)[i];
+    __syncwarp();
+    chol_factor(W(H), W(H), nv, ld, lane);
+    chol_solve(W(H), W(tmpv), W(tmpv), nv, ld, lane);
+    FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
+  } else FOR_LANES(i, nv) W(qvel)[i] += h * W(qacc)[i];
+  FOR_LANES(i, nv) W(qaccws)[i] = W(qacc)[i];
+  __syncwarp();
+  integrate_pos(c, W(qpos), W(qvel), 1.0, h);
+  *time += h;
+}
+
+__device__ void write_outputs(const Ctx& c, const b200mj_io& io, int env, const StepState& st, bool posvel, bool acc, bool want_sens) {
+  const DevModel& m = c.m; int lane = c.lane;
+  size_t e = (size_t)env;
+#define OUT(ptr, src, n) if (io.ptr) { for (int i = lane; i < (n); i += 32) io.ptr[e * (n) + i] = (src)[i]; }
+  if (posvel) {
+    OUT(xpos, W(xpos), 3 * m.nbody) OUT(xquat, W(xquat), 4 * m.nbody) OUT(xmat, W(xmat), 9 * m.nbody)
+    OUT(xipos, W(xipos), 3 * m.nbody) OUT(geom_xpos, W(gxpos), 3 * m.ngeom) OUT(geom_xmat, W(gxmat), 9 * m.ngeom)
+    OUT(subtree_com, W(scom), 3 * m.nbody) OUT(subtree_linvel, W(slinvel), 3 * m.nbody) OUT(cvel, W(cvel), 6 * m.nbody)
+    OUT(qfrc_bias, W(bias), m.nv) OUT(qfrc_passive, W(passive), m.nv)
+    if (io.site_xpos || io.site_xmat) {
+      FOR_LANES(s, m.nsite) {
+        double p[3], mm[9]; site_frame(c, s, p, mm);
+        if (io.site_xpos) for (int i = 0; i < 3; i++) io.site_xpos[(e * m.nsite + s) * 3 + i] = p[i];
+        if (io.site_xmat) for (int i = 0; i < 9; i++) io.site_xmat[(e * m.nsite + s) * 9 + i] = mm[i];
+      }
+    }
+    if (io.qM) for (int i = lane; i < m.nv * m.nv; i += 32) io.qM[e * m.nv * m.nv + i] = W(M)[(i / m.nv) * m.ldv + (i % m.nv)];
+    if (io.ncon && lane == 0) io.ncon[e] = st.ncon;
+    if (io.nefc && lane == 0) io.nefc[e] = st.nefc;
+    FOR_LANES(k, st.ncon) {
+      double* rec = W(con) + k * CON_STRIDE; int* ii = con_ints(rec);
+      size_t o = e * m.nconmax + k;
+      if (io.contact_geom) { io.contact_geom[2 * o] = ii[0]; io.contact_geom[2 * o + 1] = ii[1]; }
+      if (io.contact_efc_address) io.contact_efc_address[o] = ii[3];
+      if (io.contact_dist) io.contact_dist[o] = rec[0];
+      if (io.contact_pos) for (int i = 0; i < 3; i++) io.contact_pos[3 * o + i] = rec[1 + i];
+      if (io.contact_frame) for (int i = 0; i < 9; i++) io.contact_frame[9 * o + i] = rec[4 + i];
+    }
+  }
+  if (acc) {
+    OUT(qacc, W(qacc), m.nv) OUT(qfrc_actuator, W(qfact), m.nv) OUT(actuator_force, W(actforce), m.nu)
+    OUT(qfrc_constraint, W(qcon), m.nv)
+    if (io.efc_force) FOR_LANES(r, st.nefc) io.efc_force[e * m.njmax + r] = W(force)[r];
+    if (io.solver_niter && lane == 0) io.solver_niter[e] = st.niter;
+  }
+  if (want_sens) { OUT(sensordata, W(sens), m.nsensordata) }
+#undef OUT
+}
+
+enum { MODE_STEP = 0, MODE_FORWARD = 1 };
+
+extern "C" __global__ void __launch_bounds__(128)
+b200mj_step_kernel(DevModel m, Lay L, b200mj_io io, int batch, int nstep, int flags, int mode, int extra_disable) {
+  extern __shared__ double smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= batch) return;
+  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable);
+  size_t e = (size_t)env;
+  // ---- load state ----
+  FOR_LANES(i, m.nq) W(qpos)[i] = io.qpos[e * m.nq + i];
+  FOR_LANES(i, m.nv) { W(qvel)[i] = io.qvel[e * m.nv + i]; W(qaccws)[i] = io.qacc_warmstart ? io.qacc_warmstart[e * m.nv + i] : 0.0; }
+  FOR_LANES(i, m.na) W(act)[i] = io.act[e * m.na + i];
+  FOR_LANES(i, m.nu) W(ctrl)[i] = io.ctrl ? io.ctrl[e * m.nu + i] : 0.0;
+  if (io.sensordata) FOR_LANES(i, m.nsensordata) W(sens)[i] = io.sensordata[e * m.nsensordata + i];
+  double time = io.time ? io.time[e] : 0.0;
+  StepState st; st.ncon = st.nefc = st.niter = 0;
+  for (int i = 0; i < BMJ_NWARNING; i++) st.warn[i] = 0;
+  __syncwarp();
+  bool want_sens = (flags & B200MJ_STEP_SENSORS) != 0;
+  bool has_acc_sens = m.acc_sensors != 0;
+  // ---- control check (mj_step / mj_step2 / mj_forward all start from a finite ctrl) ----
+  if (check_bad(c, W(ctrl), m.nu)) { st.warn[BMJ_WARN_BADCTRL]++; FOR_LANES(i, m.nu) W(ctrl)[i] = 0; __syncwarp(); }
+
+  if (mode == MODE_FORWARD) {
+    stage_posvel(c, st, true);
+    subtree_vel(c);
+    if (want_sens) { sensors(c, 1, st.ncon); sensors(c, 2, st.ncon); }
+    stage_acc(c, io, env, st);
+    if (want_sens) { if (has_acc_sens) rne_post_constraint(c, io, env, st.ncon); sensors(c, 3, st.ncon); }
+    write_outputs(c, io, env, st, true, true, want_sens);
+    FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];   // quaternions were normalised in place
+  } else {
+    bool legacy = (flags & B200MJ_STEP_LEGACY) != 0;
+    for (int s = 0; s < nstep; s++) {
+      bool last = (s == nstep - 1);
+      if (check_bad(c, W(qpos), m.nq)) { st.warn[BMJ_WARN_BADQPOS]++; reset_state(c, &time); }
+      if (check_bad(c, W(qvel), m.nv)) { st.warn[BMJ_WARN_BADQVEL]++; reset_state(c, &time); }
+      stage_posvel(c, st, true);
+      bool sens_now = want_sens && last;
+      if (!legacy && sens_now) { subtree_vel(c); sensors(c, 1, st.ncon); sensors(c, 2, st.ncon); }
+      stage_acc(c, io, env, st);
+      if (sens_now) { if (has_acc_sens) rne_post_constraint(c, io, env, st.ncon); sensors(c, 3, st.ncon); }
+      if (last) write_outputs(c, io, env, st, !legacy, true, false);
+      if (check_bad(c, W(qacc), m.nv)) { st.warn[BMJ_WARN_BADQACC]++; reset_state(c, &time); continue; }
+      if (m.integrator == BMJ_INT_RK4) {
+        // classic RK4 over (qpos, qvel, act); F0 is the evaluation just made
+        int nq = m.nq, nv = m.nv, na = m.na; double h = m.timestep;
+        double* X0q = W(rk); double* X0v = X0q + nq; double* X0a = X0v + nv;
+        double* accv = X0a + na; double* acca = accv + nv; double* accd = acca + nv;
+        const double A[3] = {0.5, 0.5, 1.0}, B[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+        FOR_LANES(i, nq) X0q[i] = W(qpos)[i];
+        FOR_LANES(i, nv) { X0v[i] = W(qvel)[i]; accv[i] = B[0] * W(qvel)[i]; acca[i] = B[0] * W(qacc)[i]; }
+        FOR_LANES(i, na) { X0a[i] = W(act)[i]; accd[i] = B[0] * W(actdot)[i]; }
+        __syncwarp();
+        StepState st2 = st;
+        for (int k = 1; k < 4; k++) {
+          double a = A[k - 1];
+          FOR_LANES(i, nq) W(qpos)[i] = X0q[i];
+          __syncwarp();
+          integrate_pos(c, W(qpos), W(qvel), a, h);            // uses stage k-1 velocity
+          FOR_LANES(i, nv) W(qvel)[i] = X0v[i] + h * (a * W(qacc)[i]);
+          FOR_LANES(i, na) W(act)[i] = X0a[i] + h * (a * W(actdot)[i]);
+          __syncwarp();
+          stage_posvel(c, st2, true);
+          stage_acc(c, io, env, st2);
+          FOR_LANES(i, nv) { accv[i] += B[k] * W(qvel)[i]; acca[i] += B[k] * W(qacc)[i]; }
+          FOR_LANES(i, na) accd[i] += B[k] * W(actdot)[i];
+          __syncwarp();
+        }
+        FOR_LANES(i, nq) W(qpos)[i] = X0q[i];
+        FOR_LANES(i, na) W(act)[i] = X0a[i];
+        __syncwarp();
+        advance_act(c, W(act), accd, 1.0, h);
+        FOR_LANES(i, nv) { W(qvel)[i] = X0v[i] + h * acca[i]; W(qaccws)[i] = W(qacc)[i]; }
+        __syncwarp();
+        integrate_pos(c, W(qpos), accv, 1.0, h);
+        time += h;
+      } else euler_step(c, &time);
+    }
+    if (legacy) {
+      // trailing mj_step1: position / velocity dependent fields of the NEW state
+      if (check_bad(c, W(qpos), m.nq)) { st.warn[BMJ_WARN_BADQPOS]++; reset_state(c, &time); }
+      if (check_bad(c, W(qvel), m.nv)) { st.warn[BMJ_WARN_BADQVEL]++; reset_state(c, &time); }
+      stage_posvel(c, st, (flags & B200MJ_STEP_FULL_FINAL) != 0);
+      subtree_vel(c);
+      if (want_sens) { sensors(c, 1, st.ncon); sensors(c, 2, st.ncon); }
+      write_outputs(c, io, env, st, true, false, want_sens);
+    } else if (want_sens) {
+      FOR_LANES(i, m.nsensordata) io.sensordata[e * m.nsensordata + i] = W(sens)[i];
+    }
+    // ---- store state ----
+    FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];
+    FOR_LANES(i, m.nv) { io.qvel[e * m.nv + i] = W(qvel)[i]; if (io.qacc_warmstart) io.qacc_warmstart[e * m.nv + i] = W(qaccws)[i]; }
+    FOR_LANES(i, m.na) io.act[e * m.na + i] = W(act)[i];
+    if (io.time && lane == 0) io.time[e] = time;
+  }
+  if (io.warning && lane == 0) for (int i = 0; i < BMJ_NWARNING; i++) if (st.warn[i]) io.warning[e * BMJ_NWARNING + i] += st.warn[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+static int64_t g_launches = 0;
+
+static void build_layout(b200mj_model* M) {
+  DevModel& m = M->dm; Lay& L = M->lay;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };   // keep 16-byte alignment
+  int nv = m.nv, nb = m.nbody, ld = m.ldv, nj = m.njmax;
+  L.qpos = take(m.nq); L.qvel = take(nv); L.act = take(m.na); L.ctrl = take(m.nu); L.qaccws = take(nv); L.actdot = take(m.na);
+  L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb); L.xipos = take(3 * nb);
+  L.xanchor = take(3 * m.njnt); L.xaxis = take(3 * m.njnt); L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom);
+  L.scom = take(3 * nb); L.slinvel = take(3 * nb);
+  L.cinert = take(10 * nb); L.crb = take(10 * nb); L.cdof = take(6 * nv); L.cdofdot = take(6 * nv);
+  L.cvel = take(6 * nb); L.cacc = take(6 * nb); L.cfrc = take(6 * nb); L.cfrcext = take(m.acc_sensors ? 6 * nb : 0);
+  L.tenlen = take(m.ntendon); L.tenJ = take(m.ntendon * ld); L.actforce = take(m.nu);
+  L.M = take(nv * ld); L.LM = take(nv * ld); L.H = take(nv * ld);
+  L.J = take(nj * ld); L.efcD = take(nj); L.efcSD = take(nj); L.aref = take(nj); L.jar = take(nj); L.jv = take(nj);
+  L.force = take(nj); L.eqflag = take((nj + 1) / 2);
+  L.bias = take(nv); L.passive = take(nv); L.qfact = take(nv); L.smooth = take(nv); L.qaccs = take(nv); L.qacc = take(nv);
+  L.qcon = take(nv); L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv); L.tmpv = take(nv);
+  L.con = take(m.nconmax * CON_STRIDE);
+  L.rk = take(m.integrator == BMJ_INT_RK4 ? (m.nq + 3 * nv + 2 * m.na + 8) : 0);
+  L.sens = take(m.nsensordata);
+  L.total = o;
+  M->smem_per_env = (size_t)o * sizeof(double);
+  size_t budget = 227 * 1024;
+  int epb = (int)(budget / (M->smem_per_env ? M->smem_per_env : 1));
+  if (epb > 4) epb = 4;
+  if (epb < 1) epb = 0;
+  M->envs_per_block = epb;
+}
+
+extern "C" {
+
+const char* b200mj_version(void) { return "b200mj 0.1.0 (sm_100a, warp-per-env fp64)"; }
+
+const char* b200mj_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case -1: return "bad argument";
+    case -2: return "CUDA allocation / copy failed";
+    case -3: return "model feature outside the supported subset (condim 4/6, frictionloss, nv > 64, non-Newton solver)";
+    case -4: return "per-environment workspace exceeds 227 KB of shared memory: lower nconmax / njmax";
+    case -5: return "kernel launch failed";
+    default: return "unknown error";
+  }
+}
+
+int64_t b200mj_launch_count(void) { return g_launches; }
+int64_t b200mj_workspace_bytes(const b200mj_model* m) { return m ? (int64_t)m->smem_per_env : -1; }
+int b200mj_envs_per_block(const b200mj_model* m) { return m ? m->envs_per_block : -1; }
+
+int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int nr, b200mj_model** out) {
+  if (!idata || !rdata || !out || ni <= 0 || nr <= 0) return -1;
+  b200mj_model* M = new b200mj_model();
+  memset(M, 0, sizeof(*M));
+  if (cudaMalloc(&M->d_idata, (size_t)ni * sizeof(int)) != cudaSuccess) { delete M; return -2; }
+  if (cudaMalloc(&M->d_rdata, (size_t)nr * sizeof(double)) != cudaSuccess) { cudaFree(M->d_idata); delete M; return -2; }
+  if (cudaMemcpy(M->d_idata, idata, (size_t)ni * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(M->d_rdata, rdata, (size_t)nr * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(M->d_idata); cudaFree(M->d_rdata); delete M; return -2;
+  }
+  DevModel& m = M->dm;
+  int k = 0;
+  const int *h_sizes = nullptr, *h_opti = nullptr; const double* h_optr = nullptr;
+  const int *h_condim = nullptr, *h_sens_type = nullptr; const double *h_fl = nullptr, *h_damp = nullptr;
+  int n_condim = 0, n_sens = 0, n_fl = 0;
+#define SET_I(name) { int off = idata[2*k], len = idata[2*k+1]; m.name = M->d_idata + off; \
+    if (!strcmp(#name, "sizes")) h_sizes = idata + off; if (!strcmp(#name, "opt_int")) h_opti = idata + off; \
+    if (!strcmp(#name, "geom_condim")) { h_condim = idata + off; n_condim = len; } \
+    if (!strcmp(#name, "sensor_type")) { h_sens_type = idata + off; n_sens = len; } k++; }
+#define SET_R(name) { int off = idata[2*k], len = idata[2*k+1]; m.name = M->d_rdata + off; \
+    if (!strcmp(#name, "opt_real")) h_optr = rdata + off; \
+    if (!strcmp(#name, "dof_frictionloss")) { h_fl = rdata + off; n_fl = len; } if (!strcmp(#name, "dof_damping")) h_damp = rdata + off; k++; }
+  B200MJ_MODEL_FIELDS(SET_I, SET_R)
+#undef SET_I
+#undef SET_R
+  m.nq = h_sizes[BMJ_NQ]; m.nv = h_sizes[BMJ_NV]; m.nu = h_sizes[BMJ_NU]; m.na = h_sizes[BMJ_NA]; m.nbody = h_sizes[BMJ_NBODY];
+  m.njnt = h_sizes[BMJ_NJNT]; m.ngeom = h_sizes[BMJ_NGEOM]; m.nsite = h_sizes[BMJ_NSITE]; m.ntendon = h_sizes[BMJ_NTENDON];
+  m.neq = h_sizes[BMJ_NEQ]; m.nsensor = h_sizes[BMJ_NSENSOR]; m.nsensordata = h_sizes[BMJ_NSENSORDATA];
+  m.npair = h_sizes[BMJ_NPAIR]; m.nlevel = h_sizes[BMJ_NLEVEL]; m.nconmax = h_sizes[BMJ_NCONMAX]; m.njmax = h_sizes[BMJ_NJMAX];
+  m.ldv = m.nv | 1;
+  m.integrator = h_opti[BMJ_OPT_INTEGRATOR]; m.iterations = h_opti[BMJ_OPT_ITERATIONS];
+  m.ls_iterations = h_opti[BMJ_OPT_LS_ITERATIONS]; m.disableflags = h_opti[BMJ_OPT_DISABLEFLAGS];
+  m.timestep = h_optr[BMJ_OPT_TIMESTEP];
+  for (int i = 0; i < 3; i++) m.gravity[i] = h_optr[BMJ_OPT_GRAVITY_X + i];
+  m.tolerance = h_optr[BMJ_OPT_TOLERANCE]; m.ls_tolerance = h_optr[BMJ_OPT_LS_TOLERANCE];
+  m.impratio = h_optr[BMJ_OPT_IMPRATIO]; m.meaninertia = h_optr[BMJ_OPT_MEANINERTIA];
+  m.any_damping = 0;
+  for (int i = 0; i < m.nv; i++) if (h_damp[i] > 0) m.any_damping = 1;
+  m.acc_sensors = 0;
+  for (int i = 0; i < n_sens; i++) { int t = h_sens_type[i]; if (t == BMJ_SENS_ACCELEROMETER || t == BMJ_SENS_FORCE || t == BMJ_SENS_TORQUE) m.acc_sensors = 1; }
+  bool unsupported = m.nv > 64 || h_opti[BMJ_OPT_SOLVER] != BMJ_SOL_NEWTON || h_opti[BMJ_OPT_CONE] != 0 ||
+                     (m.integrator != BMJ_INT_EULER && m.integrator != BMJ_INT_RK4);
+  for (int i = 0; i < n_condim; i++) if (h_condim[i] != 1 && h_condim[i] != 3) unsupported = true;
+  for (int i = 0; i < n_fl; i++) if (h_fl[i] != 0) unsupported = true;
+  if (unsupported) { b200mj_model_destroy(M); return -3; }
+  build_layout(M);
+  if (M->envs_per_block < 1) { b200mj_model_destroy(M); return -4; }
+  cudaFuncSetAttribute(b200mj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  *out = M;
+  return 0;
+}
+
+void b200mj_model_destroy(b200mj_model* M) {
+  if (!M) return;
+  cudaFree(M->d_idata); cudaFree(M->d_rdata);
+  delete M;
+}
+
+int b200mj_model_set_disableflags(b200mj_model* M, int disableflags) {
+  if (!M) return -1;
+  M->dm.disableflags = disableflags;
+  return 0;
+}
+
+int b200mj_model_set_capacity(b200mj_model* M, int nconmax, int njmax) {
+  if (!M || nconmax < 0 || njmax < 0) return -1;
+  M->dm.nconmax = nconmax; M->dm.njmax = njmax;
+  build_layout(M);
+  return M->envs_per_block < 1 ? -4 : 0;
+}
+
+static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, int mode, int extra, void* stream) {
+  if (!M || !io || batch <= 0 || nstep < 0) return -1;
+  if (!io->qpos || !io->qvel || (M->dm.na > 0 && !io->act)) return -1;
+  int epb = M->envs_per_block;
+  int grid = (batch + epb - 1) / epb;
+  size_t smem = M->smem_per_env * epb;
+  b200mj_step_kernel<<<grid, 32 * epb, smem, (cudaStream_t)stream>>>(M->dm, M->lay, *io, batch, nstep, flags, mode, extra);
+  g_launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int b200mj_step(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, void* stream) {
+  return launch(M, io, batch, nstep, flags, MODE_STEP, 0, stream);
+}
+
+int b200mj_forward(const b200mj_model* M, const b200mj_io* io, int batch, int extra_disableflags, int flags, void* stream) {
+  return launch(M, io, batch, 0, flags, MODE_FORWARD, extra_disableflags, stream);
+}
+
+int b200mj_step_host(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, const double* ctrl_host,
+                     double* ctrl_dev, const double* obs_dev, double* obs_host, int nobs, void* stream) {
+  if (!M || !io || !ctrl_host || !ctrl_dev) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(ctrl_dev, ctrl_host, (size_t)batch * M->dm.nu * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) return -2;
+  b200mj_io io2 = *io; io2.ctrl = ctrl_dev;
+  int rc = launch(M, &io2, batch, nstep, flags, MODE_STEP, 0, stream);
+  if (rc) return rc;
+  if (obs_dev && obs_host && nobs > 0)
+    if (cudaMemcpyAsync(obs_host, obs_dev, (size_t)batch * nobs * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -2;
+  return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -5;
+}
+
+}  // extern "C"

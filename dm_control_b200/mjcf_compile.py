@@ -674,6 +674,15 @@ def _finish(c, root, nconmax, njmax):
   for l in range(nlevel):
     level_adr[l + 1] = level_adr[l] + int((depth == l).sum())
 
+  if nv > 64:
+    raise NotImplementedError('models with more than 64 dofs are outside the supported subset')
+  dofmask = np.zeros((nbody, 2), np.uint32)
+  for b in range(1, nbody):
+    p = body_parent[b]
+    dofmask[b] = dofmask[p]
+    for k in range(body_dofadr[b], body_dofadr[b] + body_dofnum[b]):
+      dofmask[b, k // 32] |= np.uint32(1 << (k % 32))
+  F['body_dofmask'] = dofmask.view(np.int32)
   F.update(body_parentid=body_parent, body_rootid=body_root, body_weldid=body_weld, body_jntnum=body_jntnum,
            body_jntadr=body_jntadr, body_dofnum=body_dofnum, body_dofadr=body_dofadr,
            body_geomnum=body_geomnum, body_geomadr=body_geomadr,

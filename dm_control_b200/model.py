@@ -146,3 +146,20 @@ class Model:
 
   def copy(self):
     return Model({k: v.copy() for k, v in self.fields.items()}, self.names, self.ordered_names)
+
+  # --- binary model I/O (stands where MJB save/load stands: wrapper/core.py:208-234,323-332) ---
+  def save(self, path):
+    import json
+    meta = json.dumps(dict(names=self.names, ordered_names=self.ordered_names, layout=[f for f, _ in FIELDS]))
+    np.savez_compressed(path, __meta__=np.frombuffer(meta.encode(), dtype=np.uint8), **self.fields)
+
+  @classmethod
+  def load(cls, path):
+    import json
+    with np.load(path) as z:
+      meta = json.loads(bytes(z['__meta__']).decode())
+      fields = {name: z[name] for name, _ in FIELDS if name in z}
+    missing = [name for name, _ in FIELDS if name not in fields]
+    if missing:
+      raise ValueError(f'{path}: model file predates the current blob layout (missing {missing}); regenerate it')
+    return cls(fields, meta['names'], meta['ordered_names'])

@@ -1,0 +1,321 @@
+"""`BatchedPhysics`: the drop-in for `dm_control.mujoco.Physics` on the forward-dynamics hot path.
+
+Mirrors the reference surface the `rl.control.Environment` loop and the suite tasks touch
+(dm_control/mujoco/engine.py:83-622 and the `control.Physics` ABC at dm_control/rl/control.py:206-267):
+`step`, `forward`, `reset`, `after_reset`, `reset_context`, `set_control`, `time`, `timestep`, `get_state`,
+`set_state`, `check_invalid_state`, `suppress_physics_errors`, `.model`, `.data`. The difference is the leading
+batch axis: every `data.<field>` is a `[B, ...]` float64 torch tensor resident in HBM, and one `step()` advances
+all B environments with a single launch of the hand-written sm_100a kernel through the C ABI (include/b200mj.h).
+
+There is no CPU path here. If libb200mj.so is missing, construction raises `lib.EngineError`.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+import types
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import mjcf_compile
+from . import model as _model
+
+_WARNING_NAMES = ('mjWARN_INERTIA', 'mjWARN_CONTACTFULL', 'mjWARN_CNSTRFULL', 'mjWARN_VGEOMFULL', 'mjWARN_BADQPOS',
+                  'mjWARN_BADQVEL', 'mjWARN_BADQACC', 'mjWARN_BADCTRL')
+DSBL_ACTUATION = 1 << 10
+
+_INVALID_PHYSICS_STATE = ('Physics state is invalid. Warning(s) raised: {warning_names}')
+
+
+class PhysicsError(RuntimeError):
+  """Raised if the state of the physics simulation becomes divergent (reference: rl/control.py:270)."""
+
+
+class _Data:
+  """Batched mjData slice: `[B, ...]` torch tensors, MuJoCo field names."""
+
+
+class BatchedPhysics:
+  """B copies of one compiled model stepped in lock-step on one GPU."""
+
+  legacy_step = True   # reference default: rl/control.py:209
+
+  # (name, per-env shape as a function of model, dtype)
+  _FIELDS = (
+      ('qpos', lambda m: (m.nq,)), ('qvel', lambda m: (m.nv,)), ('act', lambda m: (m.na,)),
+      ('qacc_warmstart', lambda m: (m.nv,)), ('time', lambda m: ()), ('ctrl', lambda m: (m.nu,)),
+      ('qfrc_applied', lambda m: (m.nv,)), ('xfrc_applied', lambda m: (m.nbody, 6)),
+      ('xpos', lambda m: (m.nbody, 3)), ('xquat', lambda m: (m.nbody, 4)), ('xmat', lambda m: (m.nbody, 9)),
+      ('xipos', lambda m: (m.nbody, 3)), ('geom_xpos', lambda m: (m.ngeom, 3)), ('geom_xmat', lambda m: (m.ngeom, 9)),
+      ('site_xpos', lambda m: (m.nsite, 3)), ('site_xmat', lambda m: (m.nsite, 9)),
+      ('subtree_com', lambda m: (m.nbody, 3)), ('subtree_linvel', lambda m: (m.nbody, 3)),
+      ('cvel', lambda m: (m.nbody, 6)), ('sensordata', lambda m: (m.nsensordata,)), ('qM', lambda m: (m.nv, m.nv)),
+      ('qfrc_bias', lambda m: (m.nv,)), ('qfrc_passive', lambda m: (m.nv,)), ('qacc', lambda m: (m.nv,)),
+      ('qfrc_actuator', lambda m: (m.nv,)), ('actuator_force', lambda m: (m.nu,)),
+      ('qfrc_constraint', lambda m: (m.nv,)), ('efc_force', lambda m: (m.njmax,)),
+      ('contact_dist', lambda m: (m.nconmax,)), ('contact_pos', lambda m: (m.nconmax, 3)),
+      ('contact_frame', lambda m: (m.nconmax, 9)))
+  _INT_FIELDS = (('ncon', lambda m: ()), ('contact_geom', lambda m: (m.nconmax, 2)),
+                 ('contact_efc_address', lambda m: (m.nconmax,)), ('nefc', lambda m: ()),
+                 ('solver_niter', lambda m: ()), ('warning', lambda m: (8,)))
+
+  def __init__(self, model, batch=1, device=None, outputs='all', sensors=True, full_final=True):
+    """Args:
+      model: `dm_control_b200.model.Model`.
+      batch: number of environments B.
+      device: torch CUDA device (default: current).
+      outputs: 'all' or an iterable of output field names to materialise in HBM each step (the rest stay in
+        shared memory only — the observation-contract idea of SURVEY.md Appendix B).
+      sensors: evaluate sensors (mj_sensorPos/Vel/Acc) inside the step.
+      full_final: the trailing step1 also runs collision + constraint assembly (needed for `data.ncon`/contacts).
+    """
+    if not torch.cuda.is_available():
+      raise _lib.EngineError('BatchedPhysics needs a CUDA device (B200); there is no CPU fallback.')
+    self._L = _lib.load()
+    self.model = model
+    self.batch = int(batch)
+    self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+    self._sensors = bool(sensors)
+    self._full_final = bool(full_final)
+    self._suppress = False
+    self._handle = ctypes.c_void_p()
+    self._upload_model()
+    m, B = model, self.batch
+    self.data = _Data()
+    state_names = ('qpos', 'qvel', 'act', 'qacc_warmstart', 'time', 'ctrl', 'qfrc_applied', 'xfrc_applied')
+    want = None if outputs == 'all' else set(outputs) | set(state_names) | {'warning'}
+    self._io = _lib.IO()
+    self._applied_dirty = False
+    for name, shp in self._FIELDS:
+      if want is not None and name not in want:
+        continue
+      t = torch.zeros((B,) + tuple(shp(m)), dtype=torch.float64, device=self.device)
+      setattr(self.data, name, t)
+    for name, shp in self._INT_FIELDS:
+      if want is not None and name not in want:
+        continue
+      t = torch.zeros((B,) + tuple(shp(m)), dtype=torch.int32, device=self.device)
+      setattr(self.data, name, t)
+    self._bind_io()
+    self._warn_seen = torch.zeros((B, 8), dtype=torch.int32, device=self.device)
+    self.reset()
+
+  # ---- construction helpers (reference: engine.py:451-503) -------------------------------------------
+  @classmethod
+  def from_xml_string(cls, xml_string, assets=None, **kw):
+    return cls(mjcf_compile.compile_xml(xml_string, assets=assets), **kw)
+
+  @classmethod
+  def from_xml_path(cls, path, **kw):
+    return cls(mjcf_compile.compile_file(path), **kw)
+
+  def _upload_model(self):
+    if self._handle:
+      self._L.b200mj_model_destroy(self._handle)
+      self._handle = ctypes.c_void_p()
+    with torch.cuda.device(self.device):
+      idata, rdata = self.model.pack()
+      self._blob = (idata, rdata)
+      _lib.check(self._L.b200mj_model_create(
+          idata.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), idata.size,
+          rdata.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), rdata.size, ctypes.byref(self._handle)))
+    self._model_version = self.model._version
+
+  def _bind_io(self):
+    for name, ctype in _lib.IO_FIELDS:
+      t = getattr(self.data, name, None)
+      if t is None or t.numel() == 0 or name in ('qfrc_applied', 'xfrc_applied'):
+        setattr(self._io, name, ctypes.cast(None, ctype))
+      else:
+        setattr(self._io, name, ctypes.cast(t.data_ptr(), ctype))
+
+  def enable_applied_forces(self, on=True):
+    """Route data.qfrc_applied / data.xfrc_applied into the step (off by default: saves two HBM reads per step)."""
+    for name, ctype in _lib.IO_FIELDS:
+      if name in ('qfrc_applied', 'xfrc_applied'):
+        t = getattr(self.data, name)
+        setattr(self._io, name, ctypes.cast(t.data_ptr() if on else None, ctype))
+
+  def free(self):
+    if getattr(self, '_handle', None):
+      self._L.b200mj_model_destroy(self._handle)
+      self._handle = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.free()
+    except Exception:
+      pass
+
+  # ---- engine calls -----------------------------------------------------------------------------------
+  def _stream(self):
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  def _flags(self):
+    f = 0
+    if self.legacy_step:
+      f |= _lib.STEP_LEGACY
+    if self._full_final:
+      f |= _lib.STEP_FULL_FINAL
+    if self._sensors:
+      f |= _lib.STEP_SENSORS
+    return f
+
+  def _sync_model(self):
+    if self.model._version != self._model_version:
+      self._upload_model()
+
+  def step(self, nstep=1):
+    """Advance all environments by `nstep` physics steps (reference: engine.py:164-176).
+
+    With `legacy_step` (default) the state is advanced `nstep` times and position/velocity dependent fields are
+    then refreshed for the new state (step2, (step1+step2)*(nstep-1), step1 — engine.py:147-162); acceleration
+    stage outputs are those of the last step2.
+    """
+    self._sync_model()
+    with self.check_invalid_state():
+      with torch.cuda.device(self.device):
+        _lib.check(self._L.b200mj_step(self._handle, ctypes.byref(self._io), self.batch, int(nstep), self._flags(),
+                                       self._stream()))
+
+  def forward(self, extra_disableflags=0):
+    """mj_forward on every environment (reference: engine.py:335-343)."""
+    self._sync_model()
+    with self.check_invalid_state():
+      with torch.cuda.device(self.device):
+        _lib.check(self._L.b200mj_forward(self._handle, ctypes.byref(self._io), self.batch, int(extra_disableflags),
+                                          _lib.STEP_SENSORS if self._sensors else 0, self._stream()))
+
+  def step_host(self, ctrl_host, obs_dev, obs_host, nstep=1):
+    """End-to-end step with HOST buffers: pinned numpy/torch ctrl in, packed observation tensor out."""
+    self._sync_model()
+    nobs = obs_dev.shape[1]
+    with torch.cuda.device(self.device):
+      _lib.check(self._L.b200mj_step_host(
+          self._handle, ctypes.byref(self._io), self.batch, int(nstep), self._flags(),
+          ctypes.c_void_p(ctrl_host.data_ptr()), ctypes.c_void_p(self.data.ctrl.data_ptr()),
+          ctypes.c_void_p(obs_dev.data_ptr()), ctypes.c_void_p(obs_host.data_ptr()), nobs, self._stream()))
+
+  # ---- reference Physics API ----------------------------------------------------------------------------
+  def set_control(self, control):
+    """Reference: engine.py:139-145 (`np.copyto(self.data.ctrl, control)`)."""
+    c = torch.as_tensor(control, dtype=torch.float64, device=self.device)
+    self.data.ctrl.copy_(c.expand_as(self.data.ctrl))
+
+  def reset(self, keyframe_id=None, env_mask=None):
+    """mj_resetData[Keyframe] + mj_forward with actuation disabled (reference: engine.py:306-327)."""
+    m, d = self.model, self.data
+    if keyframe_id is None:
+      q0 = torch.as_tensor(m.qpos0, device=self.device)
+    else:
+      if not 0 <= keyframe_id < m.nkey:
+        raise ValueError(f'`keyframe_id` must be between 0 and {m.nkey}, got: {keyframe_id}')
+      q0 = torch.as_tensor(m.key_qpos.reshape(m.nkey, m.nq)[keyframe_id], device=self.device)
+    if env_mask is None:
+      d.qpos.copy_(q0.expand_as(d.qpos))
+      for name in ('qvel', 'act', 'qacc_warmstart', 'time', 'ctrl', 'qfrc_applied', 'xfrc_applied', 'sensordata',
+                   'actuator_force', 'qacc'):
+        t = getattr(d, name, None)
+        if t is not None:
+          t.zero_()
+      if hasattr(d, 'warning'):
+        d.warning.zero_()
+        self._warn_seen.zero_()
+    else:
+      mask = torch.as_tensor(env_mask, dtype=torch.bool, device=self.device)
+      d.qpos[mask] = q0
+      for name in ('qvel', 'act', 'qacc_warmstart', 'time', 'ctrl'):
+        t = getattr(d, name)
+        t[mask] = 0
+    with self.suppress_physics_errors():   # reference swallows errors here too (control.py:248-251)
+      self.forward(extra_disableflags=DSBL_ACTUATION)
+
+  def after_reset(self):
+    """Reference: engine.py:329-333."""
+    self.forward(extra_disableflags=DSBL_ACTUATION)
+
+  @contextlib.contextmanager
+  def reset_context(self):
+    """Reference: rl/control.py:232-253."""
+    try:
+      self.reset()
+    except PhysicsError:
+      pass
+    yield self
+    self.after_reset()
+
+  def time(self):
+    return self.data.time
+
+  def timestep(self):
+    return self.model.opt.timestep
+
+  def control(self):
+    return self.data.ctrl
+
+  def position(self):
+    return self.data.qpos
+
+  def velocity(self):
+    return self.data.qvel
+
+  def activation(self):
+    return self.data.act
+
+  def get_state(self):
+    """[B, nq+nv+na] (reference: engine.py:235-250 / :567-585)."""
+    d = self.data
+    return torch.cat([d.qpos, d.qvel, d.act], dim=1)
+
+  def set_state(self, physics_state):
+    m, d = self.model, self.data
+    s = torch.as_tensor(physics_state, dtype=torch.float64, device=self.device)
+    if s.shape[-1] != m.nq + m.nv + m.na:
+      raise ValueError(f'Input physics state has shape {tuple(s.shape)}. Expected (..., {m.nq + m.nv + m.na}).')
+    s = s.expand(self.batch, -1)
+    d.qpos.copy_(s[:, :m.nq])
+    d.qvel.copy_(s[:, m.nq:m.nq + m.nv])
+    d.act.copy_(s[:, m.nq + m.nv:])
+
+  # ---- warnings -> PhysicsError (reference: engine.py:345-368) -----------------------------------------
+  @contextlib.contextmanager
+  def suppress_physics_errors(self):
+    prev = self._suppress
+    self._suppress = True
+    try:
+      yield
+    finally:
+      self._suppress = prev
+
+  check_errors = True   # set False on the throughput path: skips the device->host sync of the warning counters
+
+  @contextlib.contextmanager
+  def check_invalid_state(self):
+    yield
+    if not self.check_errors or not hasattr(self.data, 'warning'):
+      return
+    new = self.data.warning - self._warn_seen
+    if bool((new > 0).any()):
+      self._warn_seen.copy_(self.data.warning)
+      which = (new > 0).any(dim=0).cpu().numpy()
+      names = [n for n, w in zip(_WARNING_NAMES, which) if w]
+      message = _INVALID_PHYSICS_STATE.format(warning_names=', '.join(names))
+      if self._suppress:
+        return
+      raise PhysicsError(message)
+
+  def check_divergence(self):
+    """Reference: rl/control.py:255-267 (abstract) — raise if any state value is not finite."""
+    d = self.data
+    ok = torch.isfinite(d.qpos).all() & torch.isfinite(d.qvel).all() & torch.isfinite(d.qacc_warmstart).all()
+    if not bool(ok):
+      raise PhysicsError('Physics state has diverged (non-finite qpos/qvel).')
+
+  # ---- instrumentation ------------------------------------------------------------------------------------
+  def workspace_bytes(self):
+    return int(self._L.b200mj_workspace_bytes(self._handle))
+
+  def envs_per_block(self):
+    return int(self._L.b200mj_envs_per_block(self._handle))

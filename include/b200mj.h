@@ -1,0 +1,118 @@
+/* b200mj.h — C ABI of the B200-native batched forward-dynamics engine (libb200mj.so).
+ *
+ * The reference has no C-ABI plugin seam of its own: dm_control reaches the engine through pybind11
+ * calls on `mujoco.MjModel/MjData` handles. Each entry point below names the reference call it stands
+ * in for (paths relative to /root/reference/dm_control):
+ *
+ *   b200mj_model_create   <- mujoco.MjModel.from_xml_string result          mujoco/wrapper/core.py:179-182
+ *                            (the MJCF->tables compile itself is host Python, dm_control_b200/mjcf_compile.py)
+ *   b200mj_step           <- mujoco.mj_step2 / mj_step / mj_step1 sequence  mujoco/engine.py:147-176
+ *   b200mj_forward        <- mujoco.mj_forward (+ actuation-disabled form)  mujoco/engine.py:306-343
+ *   b200mj_step_host      <- the same step as seen by rl/control.py:99-127 with HOST action/observation
+ *                            buffers (host<->device copies inside the call)
+ *   b200mj_workspace_bytes / b200mj_launch_count / b200mj_last_kernel_ms : instrumentation
+ *
+ * Conventions: all `*_dev` pointers are device pointers on the current CUDA device; batched arrays are
+ * row-major [batch, n] (one environment's values contiguous: one warp owns one environment and reads its
+ * row with coalesced loads). Any output pointer may be NULL (that field is then not materialised).
+ * Return value: 0 ok; negative = configuration / launch error (see b200mj_error_string). Physics
+ * warnings (mjtWarning) are per-environment counters in `warning` [batch, 8].
+ * All calls are stream-ordered on `stream` (a cudaStream_t passed as void*), no host synchronisation
+ * except in b200mj_step_host.
+ */
+#ifndef B200MJ_H_
+#define B200MJ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200mj_model b200mj_model;
+
+/* Batched mjData slice crossing the ABI. State is read AND written; outputs are written. */
+typedef struct b200mj_io {
+  /* ---- physics state (in/out), [batch, n] ---- */
+  double* qpos;            /* nq  */
+  double* qvel;            /* nv  */
+  double* act;             /* na  (may be NULL when na == 0) */
+  double* qacc_warmstart;  /* nv  */
+  double* time;            /* 1   */
+  /* ---- inputs ---- */
+  const double* ctrl;          /* nu  */
+  const double* qfrc_applied;  /* nv, may be NULL */
+  const double* xfrc_applied;  /* nbody*6 (force, torque), may be NULL */
+  /* ---- position / velocity stage outputs (consistent with the NEW state) ---- */
+  double* xpos;            /* nbody*3 */
+  double* xquat;           /* nbody*4 */
+  double* xmat;            /* nbody*9 */
+  double* xipos;           /* nbody*3 */
+  double* geom_xpos;       /* ngeom*3 */
+  double* geom_xmat;       /* ngeom*9 */
+  double* site_xpos;       /* nsite*3 */
+  double* site_xmat;       /* nsite*9 */
+  double* subtree_com;     /* nbody*3 */
+  double* subtree_linvel;  /* nbody*3 (mj_subtreeVel) */
+  double* cvel;            /* nbody*6 */
+  double* sensordata;      /* nsensordata (pos/vel sensors from the new state, acc sensors from the last step2) */
+  double* qM;              /* nv*nv dense joint-space inertia */
+  double* qfrc_bias;       /* nv */
+  double* qfrc_passive;    /* nv */
+  /* ---- acceleration stage outputs (from the last step2 / forward) ---- */
+  double* qacc;            /* nv */
+  double* qfrc_actuator;   /* nv */
+  double* actuator_force;  /* nu */
+  double* qfrc_constraint; /* nv */
+  double* efc_force;       /* njmax */
+  /* ---- contacts of the new state ---- */
+  int32_t* ncon;           /* 1 */
+  int32_t* contact_geom;   /* nconmax*2 (geom1, geom2) */
+  int32_t* contact_efc_address; /* nconmax */
+  double* contact_dist;    /* nconmax */
+  double* contact_pos;     /* nconmax*3 */
+  double* contact_frame;   /* nconmax*9 */
+  int32_t* nefc;           /* 1 */
+  int32_t* solver_niter;   /* 1 */
+  /* ---- diagnostics ---- */
+  int32_t* warning;        /* 8 counters per env, accumulated */
+} b200mj_io;
+
+enum {
+  B200MJ_STEP_LEGACY = 1,      /* reference legacy ordering: step2,(step1+step2)*(n-1),step1 (engine.py:147-162) */
+  B200MJ_STEP_FULL_FINAL = 2,  /* final position stage also runs collision + constraint assembly (ncon, contacts) */
+  B200MJ_STEP_SENSORS = 4      /* evaluate sensors */
+};
+
+/* Upload a compiled model blob (layout: b200mj_model_fields.h). */
+int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int nr, b200mj_model** out);
+void b200mj_model_destroy(b200mj_model* m);
+/* Change opt.disableflags of an uploaded model (model.disable() context, wrapper/core.py:389-426). */
+int b200mj_model_set_disableflags(b200mj_model* m, int disableflags);
+/* Change per-env capacities (re-sizes the shared-memory workspace). */
+int b200mj_model_set_capacity(b200mj_model* m, int nconmax, int njmax);
+
+/* nstep physics steps for `batch` environments. flags: B200MJ_STEP_*. */
+int b200mj_step(const b200mj_model* m, const b200mj_io* io, int batch, int nstep, int flags, void* stream);
+/* mj_forward on the current state (no integration). extra_disableflags is OR-ed into opt.disableflags
+ * (the reference's reset()/after_reset() pass mjDSBL_ACTUATION, engine.py:325-333). */
+int b200mj_forward(const b200mj_model* m, const b200mj_io* io, int batch, int extra_disableflags, int flags,
+                   void* stream);
+
+/* End-to-end form with HOST buffers: copies ctrl_host [batch,nu] to the device, runs b200mj_step on the
+ * device-resident io, copies `nobs` packed doubles per env (obs_dev -> obs_host) back, synchronises. */
+int b200mj_step_host(const b200mj_model* m, const b200mj_io* io, int batch, int nstep, int flags,
+                     const double* ctrl_host, double* ctrl_dev, const double* obs_dev, double* obs_host, int nobs,
+                     void* stream);
+
+/* instrumentation */
+int64_t b200mj_workspace_bytes(const b200mj_model* m);   /* shared memory per environment (bytes) */
+int b200mj_envs_per_block(const b200mj_model* m);
+int64_t b200mj_launch_count(void);                        /* kernels launched by this library so far */
+const char* b200mj_error_string(int code);
+const char* b200mj_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MJ_H_ */

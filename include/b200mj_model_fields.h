@@ -29,6 +29,8 @@
   BMJ_R(body_subtreemass) BMJ_R(body_inertia) BMJ_R(body_invweight0)                             \
   /* tree levels: bodies sorted by depth; level_adr has nlevel+1 entries into level_body */      \
   BMJ_I(level_adr) BMJ_I(level_body)                                                             \
+  /* body_dofmask[2*b], [2*b+1]: bit i (lo word: dofs 0-31, hi word: 32-63) set iff dof i moves body b */ \
+  BMJ_I(body_dofmask)                                                             \
   /* ---- joints ---- */                                                                         \
   BMJ_I(jnt_type) BMJ_I(jnt_qposadr) BMJ_I(jnt_dofadr) BMJ_I(jnt_bodyid) BMJ_I(jnt_limited)      \
   BMJ_R(jnt_pos) BMJ_R(jnt_axis) BMJ_R(jnt_stiffness) BMJ_R(jnt_range) BMJ_R(jnt_margin)         \

@@ -248,7 +248,7 @@ static void chol_solve(real* x, const real* L, const real* b, int n) {
   }
   for (int i = n - 1; i >= 0; i--) {
     real s = x[i];
-    for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k];
+    for (int k = n - 1; k > i; k--) s -= L[k * n + i] * x[k];
     x[i] = s / L[i * n + i];
   }
 }
@@ -1555,7 +1555,8 @@ void bmjo_contact(void* dv, int i, double* out) {
   int k = 0;
   out[k++] = c->dist; for (int j = 0; j < 3; j++) out[k++] = c->pos[j]; for (int j = 0; j < 9; j++) out[k++] = c->frame[j];
   out[k++] = c->includemargin; for (int j = 0; j < 5; j++) out[k++] = c->friction[j];
-  for (int j = 0; j < 2; j++) out[k++] = c->solref[j]; for (int j = 0; j < 5; j++) out[k++] = c->solimp[j];
+  for (int j = 0; j < 2; j++) out[k++] = c->solref[j];
+  for (int j = 0; j < 5; j++) out[k++] = c->solimp[j];
   out[k++] = c->dim; out[k++] = c->geom1; out[k++] = c->geom2; out[k++] = c->efc_address;
 }
 

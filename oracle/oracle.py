@@ -27,8 +27,7 @@ def build(force=False):
 def lib():
   global _lib
   if _lib is None:
-    if not os.path.exists(_SO):
-      build()
+    build()   # make is a no-op when the .so is newer than its sources
     L = ctypes.CDLL(_SO)
     vp, ip, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
     L.bmjo_model_create.restype = vp
