@@ -1,0 +1,299 @@
+"""bench.py — env-steps/s of suite.humanoid:run, batch 8192 per GPU, random-action rollout (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference path, host cores
+
+One "step" = one `Environment.step` for the whole batch = n_sub_steps(5) physics steps + reward + observation
+(reference: rl/control.py:99-127, suite/humanoid.py:30). Prints ONE JSON line on rank 0. See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env-steps/sec suite.humanoid:run batch 8192 (per GPU) random-action rollout'
+UNIT = 'env-steps/s'
+BATCH = 8192
+NSUB = 5
+# compulsory fp64 bytes per humanoid env-step (5 fused substeps + observation-contract outputs)
+ALGO_BYTES_PER_ENV_STEP = 4068
+OBS_DIM = 67
+
+
+def _peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+  """nvidia-smi SM clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+  Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                    '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+      threading.Thread(target=self._read, daemon=True).start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(',')])
+
+  def stop(self):
+    if self.proc is not None:
+      self.proc.terminate()
+    time.sleep(0.05)
+    sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+    mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+    return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def time_cpu(seconds_budget, warmup_steps, timed_steps, nenv_per_thread=8, threads=None):
+  """Times `control_step(5)` (legacy ordering, engine.py:147-162) of the scalar oracle over all host cores.
+
+  Each thread owns `nenv_per_thread` environments (ctypes releases the GIL inside the C call). Returns
+  (env_steps_per_s, cores, sample description, ms per env-step-batch-of-sample).
+  """
+  import numpy as np
+  from concurrent.futures import ThreadPoolExecutor
+  from dm_control_b200 import testing_models as tm
+  from oracle import oracle as om
+  om.build()
+  threads = threads or os.cpu_count() or 1
+  model = tm.load('humanoid')
+  nenv = threads * nenv_per_thread
+  q0, v0 = tm.initial_states(model, 'humanoid', nenv, 0)
+  envs = []
+  for e in range(nenv):
+    o = om.OraclePhysics(model)
+    o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward()
+    envs.append(o)
+  rs = np.random.RandomState(1234)
+
+  def run_chunk(args):
+    t, nsteps, seed = args
+    r = np.random.RandomState(seed)
+    for _ in range(nsteps):
+      for o in envs[t * nenv_per_thread:(t + 1) * nenv_per_thread]:
+        o.ctrl[:] = r.uniform(-1, 1, model.nu)
+        o.control_step(NSUB)
+
+  with ThreadPoolExecutor(threads) as ex:
+    list(ex.map(run_chunk, [(t, warmup_steps, 100 + t) for t in range(threads)]))
+    t0 = time.perf_counter()
+    list(ex.map(run_chunk, [(t, timed_steps, 200 + t) for t in range(threads)]))
+    dt = time.perf_counter() - t0
+  del rs
+  value = nenv * timed_steps / dt
+  sample = f'{nenv} envs ({nenv_per_thread}/thread x {threads} threads) x {timed_steps} env-steps after {warmup_steps} warm-up, seeded humanoid:run states, uniform(-1,1) actions'
+  return value, threads, sample, dt * 1e3 / timed_steps
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  steps = max(1, args.steps)
+  value, cores, sample, ms = time_cpu(None, max(3, args.warmup), steps * 4)
+  line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+              ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+              config=dict(workload='suite.humanoid:run, 5 physics substeps per env-step, random actions',
+                          note='restated CPU oracle (oracle/mjoracle.cpp), NOT libmujoco: MuJoCo is absent from this image'),
+              cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample),
+              e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+  import torch
+  import torch.distributed as dist
+  from dm_control_b200 import lib as blib
+  from dm_control_b200 import suite
+  from dm_control_b200 import testing_models as tm
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  L = blib.load()
+
+  env = suite.load('humanoid', 'run', batch=BATCH, seed=1000 + rank, device=dev)
+  phys = env.physics
+  phys.check_errors = False          # no device->host sync inside the rollout; warnings are summed at the end
+  model = phys.model
+  # seeded, partly-in-contact start states (same family the parity tests use), then the task's own settle
+  q0, v0 = tm.initial_states(model, 'humanoid', BATCH, seed=rank)
+  phys.data.qpos.copy_(torch.as_tensor(q0, device=dev)); phys.data.qvel.copy_(torch.as_tensor(v0, device=dev))
+  phys.forward()
+  env._reset_next.zero_()
+  gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+  actions = torch.empty(BATCH, model.nu, dtype=torch.float64, device=dev)
+  packed = torch.empty(BATCH, OBS_DIM + 2, dtype=torch.float64, device=dev)
+  gathered = [torch.empty_like(packed) for _ in range(world)] if (world > 1 and rank == 0) else None
+  flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
+
+  def pack(ts):
+    o = ts.observation
+    packed[:, :21] = o['joint_angles']; packed[:, 21] = o['head_height']; packed[:, 22:34] = o['extremities']
+    packed[:, 34:37] = o['torso_vertical']; packed[:, 37:40] = o['com_velocity']; packed[:, 40:67] = o['velocity']
+    packed[:, 67] = ts.reward; packed[:, 68] = ts.discount
+    if world > 1:
+      dist.gather(packed, gathered, dst=0)     # NCCL over NVLink: observations/rewards to rank 0 (north_star)
+
+  def one_step():
+    flush.fill_(0.0)                                   # L2 flush between timed iterations (inside the timed region)
+    actions.uniform_(-1, 1, generator=gen)
+    pack(env.step(actions))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # settle to the steady-state contact load the metric is quoted on (20 warm-up env-steps minimum)
+  for _ in range(max(args.warmup, 3)):
+    one_step()
+  barrier()
+
+  # ---- device-resident arm -------------------------------------------------------------------------------
+  sampler = ClockSampler(local) if rank == 0 else None
+  if sampler:
+    sampler.start()
+  launches0 = L.b200mj_launch_count()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+  kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  barrier()
+  ev[0].record()
+  for i in range(args.steps):
+    flush.fill_(0.0)
+    actions.uniform_(-1, 1, generator=gen)
+    env._task.before_step(actions, phys)
+    kev[i][0].record()
+    phys.step(env.n_sub_steps)                         # the one launch of b200mj_step_kernel
+    kev[i][1].record()
+    env._task.after_step(phys)
+    reward = env._task.get_reward(phys)
+    obs = env._task.get_observation(phys)
+    pack(type('TS', (), dict(observation=obs, reward=reward, discount=torch.ones_like(reward))))
+  ev[1].record()
+  barrier()
+  ms_total = ev[0].elapsed_time(ev[1])
+  kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+  launches = L.b200mj_launch_count() - launches0
+  clocks = sampler.stop() if sampler else None
+  t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total, kernel_ms = float(t[0]), float(t[1])
+  value = BATCH * world * args.steps / (ms_total * 1e-3)
+
+  # ---- end-to-end arm: HOST action buffer in, HOST observation/reward buffer out, every step -----------------
+  act_host = torch.empty(BATCH, model.nu, dtype=torch.float64).pin_memory()
+  out_host = torch.empty((BATCH * world if rank == 0 else BATCH), OBS_DIM + 2, dtype=torch.float64).pin_memory()
+  cpu_gen = torch.Generator().manual_seed(77 + rank)
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(args.steps):
+    act_host.uniform_(-1, 1, generator=cpu_gen)
+    flush.fill_(0.0)
+    actions.copy_(act_host, non_blocking=True)                        # H2D
+    pack(env.step(actions))
+    if rank == 0 and world > 1:
+      out_host.copy_(torch.cat(gathered, 0), non_blocking=True)       # D2H of the gathered block
+    else:
+      out_host[:BATCH].copy_(packed, non_blocking=True)               # D2H
+    torch.cuda.current_stream().synchronize()                         # the user reads obs before the next action
+  e1.record()
+  barrier()
+  e2e_ms = e0.elapsed_time(e1)
+  t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_value = BATCH * world * args.steps / (float(t[0]) * 1e-3)
+  warn = phys.data.warning.sum(0)
+  if world > 1:
+    dist.all_reduce(warn)
+
+  if rank == 0:
+    peak, peak_src = _peaks()
+    achieved = ALGO_BYTES_PER_ENV_STEP * BATCH / (kernel_ms * 1e-3) / 1e9
+    prof = {}
+    pj = os.path.join(ROOT, 'profiles', 'summary.json')
+    if os.path.exists(pj):
+      prof = json.load(open(pj))
+    cpu = None
+    if world == 1 and not args.no_cpu:
+      v, cores, sample, _ = time_cpu(None, 3, 12)
+      cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample)
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+        data='synthetic',
+        config=dict(workload='suite.humanoid:run', batch_per_gpu=BATCH, global_batch=BATCH * world, n_sub_steps=NSUB,
+                    physics_steps_per_s=value * NSUB, parallelism=f'env-sharded x{world}',
+                    actions='uniform(-1,1) generated on device', l2='256 MB flush write between steps, inside the timed region',
+                    obs_gather='NCCL gather of [B,69] f64 to rank 0 each step' if world > 1 else 'n/a (1 GPU)',
+                    workspace_bytes_per_env=phys.workspace_bytes(), envs_per_block=phys.envs_per_block(),
+                    nconmax=model.nconmax, njmax=model.njmax),
+        e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * model.nu * 8,
+                 d2h_bytes_per_step=BATCH * (OBS_DIM + 2) * 8 * (world if world > 1 else 1)),
+        gpu_launches=int(launches),
+        roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                      traffic=prof.get('dram_bytes_per_launch'), peak_source=peak_src,
+                      kernel='b200mj_step_kernel', kernel_ms=kernel_ms, kernel_share_of_step=kernel_ms / (ms_total / args.steps),
+                      algorithmic_bytes_per_launch=ALGO_BYTES_PER_ENV_STEP * BATCH,
+                      note='latency/issue-bound fp64 kernel: compulsory traffic is ~4 kB per env-step, see DESIGN.md'),
+        clocks=clocks, warnings=[int(x) for x in warn.tolist()])
+    if cpu is not None:
+      line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_gpu(args)
+
+
+if __name__ == '__main__':
+  main()

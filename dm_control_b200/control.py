@@ -1,0 +1,88 @@
+"""`BatchedEnvironment`: B lock-stepped copies of `dm_control.rl.control.Environment` (rl/control.py:35-153).
+
+Same call order per step (`before_step` -> `physics.step(n_sub_steps)` -> `after_step` -> reward -> observation),
+same sub-step arithmetic (`compute_n_steps`, control.py:168-194), same time-limit rule, but every quantity has a
+leading batch axis and stays on the device. Episodes that hit the time limit (or whose physics diverged) are reset
+in place on the next `step`, per environment (the reference resets the single env on the next call, control.py:102).
+"""
+from __future__ import annotations
+
+import collections
+
+import torch
+
+
+def compute_n_steps(control_timestep, physics_timestep, tolerance=1e-8):
+  """Reference: rl/control.py:168-194 (same error text)."""
+  if control_timestep < physics_timestep:
+    raise ValueError('Control timestep ({}) cannot be smaller than physics timestep ({}).'.format(
+        control_timestep, physics_timestep))
+  if abs((control_timestep / physics_timestep - round(control_timestep / physics_timestep))) > tolerance:
+    raise ValueError('Control timestep ({}) must be an integer multiple of physics timestep ({})'.format(
+        control_timestep, physics_timestep))
+  return int(round(control_timestep / physics_timestep))
+
+
+TimeStep = collections.namedtuple('TimeStep', ['step_type', 'reward', 'discount', 'observation'])
+FIRST, MID, LAST = 0, 1, 2
+
+
+class BatchedEnvironment:
+
+  def __init__(self, physics, task, time_limit=float('inf'), control_timestep=None, n_sub_steps=None,
+               legacy_step=True, auto_reset=True):
+    self._physics, self._task = physics, task
+    physics.legacy_step = legacy_step
+    if n_sub_steps is not None and control_timestep is not None:
+      raise ValueError('Both n_sub_steps and control_timestep were supplied.')
+    if n_sub_steps is not None:
+      self._n_sub_steps = n_sub_steps
+    elif control_timestep is not None:
+      self._n_sub_steps = compute_n_steps(control_timestep, physics.timestep())
+    else:
+      self._n_sub_steps = 1
+    self._step_limit = float('inf') if time_limit == float('inf') else time_limit / (physics.timestep() * self._n_sub_steps)
+    self._step_count = torch.zeros(physics.batch, dtype=torch.int64, device=physics.device)
+    self._reset_next = torch.ones(physics.batch, dtype=torch.bool, device=physics.device)
+    self._auto_reset = auto_reset
+
+  @property
+  def physics(self):
+    return self._physics
+
+  @property
+  def task(self):
+    return self._task
+
+  @property
+  def n_sub_steps(self):
+    return self._n_sub_steps
+
+  def control_timestep(self):
+    return self._physics.timestep() * self._n_sub_steps
+
+  def reset(self):
+    self._task.initialize_episode(self._physics, None)
+    self._step_count.zero_()
+    self._reset_next.zero_()
+    obs = self._task.get_observation(self._physics)
+    B = self._physics.batch
+    return TimeStep(torch.full((B,), FIRST, device=self._physics.device), None, None, obs)
+
+  def step(self, action):
+    if self._auto_reset and bool(self._reset_next.any()):
+      mask = self._reset_next
+      self._task.initialize_episode(self._physics, mask)
+      self._step_count[mask] = 0
+      self._reset_next = torch.zeros_like(mask)
+    self._task.before_step(action, self._physics)
+    self._physics.step(self._n_sub_steps)
+    self._task.after_step(self._physics)
+    reward = self._task.get_reward(self._physics)
+    obs = self._task.get_observation(self._physics)
+    self._step_count += 1
+    last = self._step_count >= self._step_limit
+    self._reset_next = last
+    step_type = torch.where(last, LAST, MID)
+    discount = torch.ones_like(reward)
+    return TimeStep(step_type, reward, discount, obs)

@@ -1244,6 +1244,48 @@ __device__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, 
   tree_accumulate(c, cint, 6, true);
 }
 
+// ---- ray / convex zone test of the touch sensor (MuJoCo: mju_rayGeom(...) >= 0): does p + t v, t >= 0, meet the site? ----
+struct Interval { double lo, hi; bool ok; };
+__device__ __forceinline__ void iv_clip(Interval& a, double lo, double hi) {
+  if (lo > hi) { double t = lo; lo = hi; hi = t; }
+  a.lo = fmax(a.lo, lo); a.hi = fmin(a.hi, hi);
+  if (a.lo > a.hi) a.ok = false;
+}
+__device__ __forceinline__ void iv_quadric(Interval& r, double a, double b, double c) {   // a t^2 + 2 b t + c <= 0
+  if (a < BMJ_MINVAL) { if (c > 0) r.ok = false; return; }
+  double det = b * b - a * c;
+  if (det < 0) { r.ok = false; return; }
+  double sq = sqrt(det);
+  iv_clip(r, (-b - sq) / a, (-b + sq) / a);
+}
+__device__ __forceinline__ void iv_slab(Interval& r, double p, double v, double half) {
+  if (fabs(v) < BMJ_MINVAL) { if (fabs(p) > half) r.ok = false; return; }
+  iv_clip(r, (-half - p) / v, (half - p) / v);
+}
+__device__ bool ray_hits_zone(int type, const double* sz, const double* p, const double* v) {
+  Interval r; r.lo = -1e300; r.hi = 1e300; r.ok = true;
+  if (type == BMJ_GEOM_SPHERE) iv_quadric(r, dot3(v, v), dot3(p, v), dot3(p, p) - sz[0] * sz[0]);
+  else if (type == BMJ_GEOM_ELLIPSOID) {
+    double ps[3] = {p[0] / sz[0], p[1] / sz[1], p[2] / sz[2]}, vs[3] = {v[0] / sz[0], v[1] / sz[1], v[2] / sz[2]};
+    iv_quadric(r, dot3(vs, vs), dot3(ps, vs), dot3(ps, ps) - 1);
+  } else if (type == BMJ_GEOM_BOX) { for (int i = 0; i < 3; i++) iv_slab(r, p[i], v[i], sz[i]); }
+  else if (type == BMJ_GEOM_CYLINDER || type == BMJ_GEOM_CAPSULE) {
+    iv_quadric(r, v[0]*v[0] + v[1]*v[1], p[0]*v[0] + p[1]*v[1], p[0]*p[0] + p[1]*p[1] - sz[0]*sz[0]);
+    iv_slab(r, p[2], v[2], sz[1]);
+    if (type == BMJ_GEOM_CAPSULE) {
+      if (r.ok && r.hi >= 0) return true;
+      for (int s = -1; s <= 1; s += 2) {
+        Interval q; q.lo = -1e300; q.hi = 1e300; q.ok = true;
+        double pc[3] = {p[0], p[1], p[2] - s * sz[1]};
+        iv_quadric(q, dot3(v, v), dot3(pc, v), dot3(pc, pc) - sz[0] * sz[0]);
+        if (q.ok && q.hi >= 0) return true;
+      }
+      return false;
+    }
+  } else return false;
+  return r.ok && r.hi >= 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // sensors (stage 1 = position, 2 = velocity, 3 = acceleration); results staged in the workspace
 // ------------------------------------------------------------------------------------------------
@@ -1313,14 +1355,11 @@ __device__ void sensors(const Ctx& c, int stage, int ncon) {
         double nf = 0;
         if (ii[2] == 1) nf = W(force)[ii[3]]; else for (int k = 0; k < 4; k++) nf += W(force)[ii[3] + k];
         if (nf <= 0) continue;
-        double dif[3] = {rec[1] - sp[0], rec[2] - sp[1], rec[3] - sp[2]}, loc[3];
+        double dif[3] = {rec[1] - sp[0], rec[2] - sp[1], rec[3] - sp[2]}, loc[3], ray[3] = {rec[4], rec[5], rec[6]}, vloc[3];
         matT_vec(loc, sm, dif);
-        bool in = false;
-        if (stp == BMJ_GEOM_SPHERE) in = dot3(loc, loc) < sz[0] * sz[0];
-        else if (stp == BMJ_GEOM_CAPSULE) { double z = clampd(loc[2], -sz[1], sz[1]), dz = loc[2] - z; in = loc[0]*loc[0] + loc[1]*loc[1] + dz*dz < sz[0]*sz[0]; }
-        else if (stp == BMJ_GEOM_ELLIPSOID) in = (loc[0]/sz[0])*(loc[0]/sz[0]) + (loc[1]/sz[1])*(loc[1]/sz[1]) + (loc[2]/sz[2])*(loc[2]/sz[2]) < 1;
-        else if (stp == BMJ_GEOM_CYLINDER) in = fabs(loc[2]) < sz[1] && loc[0]*loc[0] + loc[1]*loc[1] < sz[0]*sz[0];
-        else if (stp == BMJ_GEOM_BOX) in = fabs(loc[0]) < sz[0] && fabs(loc[1]) < sz[1] && fabs(loc[2]) < sz[2];
+        if (m.geom_bodyid[ii[1]] == b) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
+        matT_vec(vloc, sm, ray);
+        bool in = ray_hits_zone(stp, sz, loc, vloc);
         if (in) total += nf;
       }
       out[0] = total;

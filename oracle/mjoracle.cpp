@@ -1025,6 +1025,53 @@ static void object_velocity_site(const OModel* m, const OData* d, int site, real
   mul_matT_vec3(res + 3, &d->site_xmat[9 * site], lin);
 }
 
+
+// ---- ray / convex zone test used by the touch sensor: does p + t v (t >= 0) meet the shape? ----------------
+struct Interval { real lo, hi; bool ok; };
+static inline Interval iv_all() { Interval r = {-1e300, 1e300, true}; return r; }
+static inline void iv_clip(Interval& a, real lo, real hi) { if (lo > hi) { real t = lo; lo = hi; hi = t; } a.lo = std::max(a.lo, lo); a.hi = std::min(a.hi, hi); if (a.lo > a.hi) a.ok = false; }
+// quadratic a t^2 + 2 b t + c <= 0
+static inline void iv_quadric(Interval& r, real a, real b, real c) {
+  if (a < BMJ_MINVAL) { if (c > 0) r.ok = false; return; }
+  real det = b * b - a * c;
+  if (det < 0) { r.ok = false; return; }
+  real sq = std::sqrt(det);
+  iv_clip(r, (-b - sq) / a, (-b + sq) / a);
+}
+static inline void iv_slab(Interval& r, real p, real v, real half) {
+  if (std::fabs(v) < BMJ_MINVAL) { if (std::fabs(p) > half) r.ok = false; return; }
+  iv_clip(r, (-half - p) / v, (half - p) / v);
+}
+static bool ray_hits_zone(int type, const real* sz, const real* p, const real* v) {
+  Interval r = iv_all();
+  switch (type) {
+    case BMJ_GEOM_SPHERE: iv_quadric(r, dot3(v, v), dot3(p, v), dot3(p, p) - sz[0] * sz[0]); break;
+    case BMJ_GEOM_ELLIPSOID: {
+      real ps[3] = {p[0] / sz[0], p[1] / sz[1], p[2] / sz[2]}, vs[3] = {v[0] / sz[0], v[1] / sz[1], v[2] / sz[2]};
+      iv_quadric(r, dot3(vs, vs), dot3(ps, vs), dot3(ps, ps) - 1);
+    } break;
+    case BMJ_GEOM_BOX: for (int i = 0; i < 3; i++) iv_slab(r, p[i], v[i], sz[i]); break;
+    case BMJ_GEOM_CYLINDER:
+      iv_quadric(r, v[0]*v[0] + v[1]*v[1], p[0]*v[0] + p[1]*v[1], p[0]*p[0] + p[1]*p[1] - sz[0]*sz[0]);
+      iv_slab(r, p[2], v[2], sz[1]);
+      break;
+    case BMJ_GEOM_CAPSULE: {
+      iv_quadric(r, v[0]*v[0] + v[1]*v[1], p[0]*v[0] + p[1]*v[1], p[0]*p[0] + p[1]*p[1] - sz[0]*sz[0]);
+      iv_slab(r, p[2], v[2], sz[1]);
+      if (r.ok && r.hi >= 0) return true;
+      for (int s = -1; s <= 1; s += 2) {
+        Interval q = iv_all();
+        real pc[3] = {p[0], p[1], p[2] - s * sz[1]};
+        iv_quadric(q, dot3(v, v), dot3(pc, v), dot3(pc, pc) - sz[0] * sz[0]);
+        if (q.ok && q.hi >= 0) return true;
+      }
+      return false;
+    }
+    default: return false;
+  }
+  return r.ok && r.hi >= 0;
+}
+
 static void sensors(const OModel* m, OData* d, int stage) {
   if (m->disableflags & BMJ_DSBL_SENSOR) return;
   bool did_subtree = false;
@@ -1094,23 +1141,14 @@ static void sensors(const OModel* m, OData* d, int stage) {
           if (c->dim == 1) nf = d->efc_force[c->efc_address];
           else for (int k = 0; k < 2 * (c->dim - 1); k++) nf += d->efc_force[c->efc_address + k];
           if (nf <= 0) continue;
-          // inside-site test in the site frame
+          // MuJoCo counts a contact when the ray from the contact point along the (body-oriented) normal meets
+          // the site volume (mju_rayGeom >= 0), which also admits points exactly on the zone boundary
           real dif[3] = {c->pos[0] - d->site_xpos[3 * id], c->pos[1] - d->site_xpos[3 * id + 1], c->pos[2] - d->site_xpos[3 * id + 2]};
           real loc[3]; mul_matT_vec3(loc, &d->site_xmat[9 * id], dif);
-          const real* sz = &m->site_size[3 * id];
-          bool in = false;
-          switch (m->site_type[id]) {
-            case BMJ_GEOM_SPHERE: in = dot3(loc, loc) < sz[0] * sz[0]; break;
-            case BMJ_GEOM_CAPSULE: {
-              real z = clampr(loc[2], -sz[1], sz[1]);
-              real dz = loc[2] - z;
-              in = loc[0]*loc[0] + loc[1]*loc[1] + dz*dz < sz[0] * sz[0];
-            } break;
-            case BMJ_GEOM_ELLIPSOID: in = (loc[0]/sz[0])*(loc[0]/sz[0]) + (loc[1]/sz[1])*(loc[1]/sz[1]) + (loc[2]/sz[2])*(loc[2]/sz[2]) < 1; break;
-            case BMJ_GEOM_CYLINDER: in = std::fabs(loc[2]) < sz[1] && loc[0]*loc[0] + loc[1]*loc[1] < sz[0]*sz[0]; break;
-            case BMJ_GEOM_BOX: in = std::fabs(loc[0]) < sz[0] && std::fabs(loc[1]) < sz[1] && std::fabs(loc[2]) < sz[2]; break;
-            default: break;
-          }
+          real ray[3] = {c->frame[0], c->frame[1], c->frame[2]};
+          if (b2 == b) for (int i = 0; i < 3; i++) ray[i] = -ray[i];
+          real vloc[3]; mul_matT_vec3(vloc, &d->site_xmat[9 * id], ray);
+          bool in = ray_hits_zone(m->site_type[id], &m->site_size[3 * id], loc, vloc);
           if (in) total += nf;
         }
         out[0] = total;

@@ -1,0 +1,129 @@
+"""-m gpu: engine semantics the reference's own engine tests pin, exercised on the CUDA path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+from dm_control_b200 import testing_models as tm   # noqa: E402
+from dm_control_b200 import mjcf_compile as mc    # noqa: E402
+
+
+def _phys(name, B, **kw):
+  from dm_control_b200.physics import BatchedPhysics
+  return BatchedPhysics(tm.load(name), batch=B, **kw)
+
+
+def _seed(phys, name, seed=0):
+  q0, v0 = tm.initial_states(phys.model, name, phys.batch, seed)
+  phys.data.qpos.copy_(torch.as_tensor(q0)); phys.data.qvel.copy_(torch.as_tensor(v0))
+  phys.forward()
+
+
+def test_readme_known_answer_on_gpu():
+  # dm_control/mujoco/README.md:25-50
+  phys = _phys('slide_box', 3)
+  with phys.reset_context():
+    phys.data.qpos[:, 0] = 0.5
+  np.testing.assert_allclose(phys.data.geom_xpos[0, 1].cpu().numpy(), [0, 0, 0.8], atol=1e-12)
+  while float(phys.time()[0]) < 1.0:
+    phys.step()
+  z = phys.data.geom_xpos[:, 1:3, 2].cpu().numpy()
+  assert np.all(np.abs(z - np.array([0.19996362, 0.39996362])) < 5e-9)
+
+
+def test_contact_force_equals_weight_on_gpu():
+  # dm_control/mujoco/wrapper/core_test.py:393-416: sum of contact normal forces == weight (7 places)
+  phys = _phys('free_box', 2)
+  phys.step(500)
+  d = phys.data
+  assert d.ncon.tolist() == [4, 4]
+  total = 0.0
+  for i in range(4):
+    a = int(d.contact_efc_address[0, i])
+    total += float(d.efc_force[0, a:a + 4].sum())   # pyramid: the normal force is the sum of the four edge forces
+  assert abs(total - 9.81 * phys.model.body_mass[1]) < 5e-8
+
+
+@pytest.mark.parametrize('name', ['cheetah', 'cartpole', 'humanoid'])
+def test_nstep_equals_repeated_step_bitwise(name):
+  # dm_control/mujoco/engine_test.py:627-663 (Euler for cheetah/humanoid, RK4 for cartpole)
+  a, b = _phys(name, 8), _phys(name, 8)
+  a.legacy_step = b.legacy_step = True
+  for p in (a, b):
+    _seed(p, name, 4)
+    p.set_control(torch.full((p.model.nu,), 0.25, dtype=torch.float64))
+  a.step(4)
+  for _ in range(4):
+    b.step()
+  assert torch.equal(a.get_state(), b.get_state())
+  assert torch.equal(a.data.qacc_warmstart, b.data.qacc_warmstart)
+
+
+def test_run_to_run_determinism_and_batch_invariance():
+  # suite/suite_test.py:169-185 (same seed + actions => identical trajectories), extended across batch sizes:
+  # env i of a B=4096 launch must equal env i of a B=64 launch bit for bit
+  big, small, again = _phys('humanoid', 4096), _phys('humanoid', 64), _phys('humanoid', 4096)
+  for p in (big, small, again):
+    _seed(p, 'humanoid', 9)
+  tape = torch.as_tensor(np.random.RandomState(3).uniform(-1, 1, (10, 4096, 21)), device='cuda')
+  for t in range(10):
+    big.set_control(tape[t]); again.set_control(tape[t]); small.set_control(tape[t, :64])
+    big.step(5); again.step(5); small.step(5)
+  assert torch.equal(big.get_state(), again.get_state())
+  assert torch.equal(big.get_state()[:64], small.get_state())
+  assert torch.equal(big.data.xpos[:64], small.data.xpos)
+  assert bool(torch.isfinite(big.get_state()).all())
+
+
+def test_actuation_disabled_in_after_reset():
+  # dm_control/mujoco/engine_test.py:599-604
+  phys = _phys('cartpole', 2)
+  phys.data.ctrl[:, 0] = 1.0
+  phys.after_reset()
+  assert float(phys.data.actuator_force.abs().max()) == 0.0
+  phys.forward()
+  assert phys.data.actuator_force[:, 0].tolist() == [1.0, 1.0]
+
+
+def test_bad_control_and_bad_state_raise_physics_error():
+  # dm_control/mujoco/engine_test.py:487-547
+  from dm_control_b200.physics import PhysicsError
+  phys = _phys('cartpole', 4)
+  phys.data.ctrl[2, 0] = float('nan')
+  with pytest.raises(PhysicsError, match='mjWARN_BADCTRL'):
+    phys.step()
+  phys.data.ctrl.zero_()
+  phys.step()                      # recovers
+  phys.data.qpos[1, 0] = float('inf')
+  with pytest.raises(PhysicsError, match='mjWARN_BADQPOS'):
+    phys.step()
+  assert bool(torch.isfinite(phys.data.qpos).all())   # offending env was reset in place
+  phys.data.qpos[0, 0] = 1e15
+  with phys.suppress_physics_errors():
+    phys.step()                    # suppressed: logged only
+
+
+def test_full_batch_properties_humanoid_8192():
+  """BASELINE.json size: properties that need no oracle (finite, bounded, contacts present, clock exact)."""
+  phys = _phys('humanoid', 8192, outputs=('xpos', 'subtree_com', 'sensordata', 'ncon'))
+  _seed(phys, 'humanoid', 1)
+  g = torch.Generator(device='cuda').manual_seed(0)
+  for _ in range(40):
+    phys.data.ctrl.uniform_(-1, 1, generator=g)
+    phys.step(5)
+  d = phys.data
+  assert bool(torch.isfinite(d.qpos).all()) and bool(torch.isfinite(d.qvel).all())
+  np.testing.assert_allclose(d.time.cpu().numpy(), 40 * 5 * 0.005, rtol=0, atol=1e-9)
+  quat = d.qpos[:, 3:7]
+  assert float((quat.norm(dim=1) - 1).abs().max()) < 1e-9         # free-joint quaternion stays unit
+  assert float(d.qpos[:, 2].min()) > -0.05                        # nobody tunnels through the floor
+  assert float(d.ncon.float().mean()) > 0.5                       # they are lying on it
+  assert int(d.warning.sum()) == 0
+
+
+def test_compile_and_step_inline_model():
+  phys = mc and __import__('dm_control_b200.physics', fromlist=['BatchedPhysics']).BatchedPhysics.from_xml_string(
+      tm.XML['pendulum_free'], batch=5)
+  phys.step(10)
+  assert bool(torch.isfinite(phys.data.qpos).all())
