@@ -17,12 +17,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/b200mj.h"
 #include "../../include/b200mj_model_fields.h"
 
 #define FULL 0xffffffffu
-#define FOR_LANES(i, n) for (int i = lane; i < (n); i += 32)
+#define FOR_LANES(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
 
 // ------------------------------------------------------------------------------------------------
 // device model view + workspace layout
@@ -46,8 +47,8 @@ struct Lay {
   int xpos, xquat, xmat, xipos, xanchor, xaxis, gxpos, gxmat, scom, slinvel;
   int cinert, crb, cdof, cdofdot, cvel, cacc, cfrc, cfrcext;
   int tenlen, tenJ, actforce;
-  int M, LM, H;
-  int J, efcD, efcSD, aref, jar, jv, force, eqflag;
+  int M, H, dinv;
+  int J, efcD, efcSD, aref, jar, jv, force, eqflag, actlist;
   int bias, passive, qfact, smooth, qaccs, qacc, qcon, Ma, grad, search, Mv, tmpv;
   int con;                               // contact records, 16 doubles each
   int rk;                                // RK4 scratch: X0q, X0v, X0a, accv, acca, accd
@@ -144,7 +145,7 @@ __device__ __forceinline__ void cross_force(double* r, const double* vel, const 
 __device__ __forceinline__ double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ bool bad_value(double x) { return isnan(x) || x > BMJ_MAXVAL || x < -BMJ_MAXVAL; }
 
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
@@ -172,41 +173,45 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------------
 // dense Cholesky in the workspace: A (n x n, row stride ld) -> lower factor Lm, same stride
 // ------------------------------------------------------------------------------------------------
-__device__ void chol_factor(const double* A, double* Lm, int n, int ld, int lane) {
-  for (int j = 0; j < n; j++) {
-    for (int i = lane; i < n; i += 32) {
-      if (i >= j) {
-        double t = A[i * ld + j];
-        const double* Li = Lm + i * ld; const double* Lj = Lm + j * ld;
-        for (int k = 0; k < j; k++) t -= Li[k] * Lj[k];
-        Lm[i * ld + j] = t;
-      }
+__device__ __noinline__ void chol_factor(const double* A, double* Lm, double* dinv, int n, int ld, int lane) {
+  // left-looking, one row (two when n > 32) per lane; the pivot travels by shuffle, so one sync per column.
+  // dinv[j] = 1 / L[j][j] is kept so that neither the factor nor the triangular solves divide.
+  _Pragma("unroll 1") for (int j = 0; j < n; j++) {
+    double t0 = 0, t1 = 0;
+    int i0 = lane, i1 = lane + 32;
+    const double* Lj = Lm + j * ld;
+    if (i0 >= j && i0 < n) {
+      t0 = A[i0 * ld + j];
+      const double* Li = Lm + i0 * ld;
+      for (int k = 0; k < j; k++) t0 -= Li[k] * Lj[k];
     }
-    __syncwarp();
-    double piv = Lm[j * ld + j];
+    if (i1 >= j && i1 < n) {
+      t1 = A[i1 * ld + j];
+      const double* Li = Lm + i1 * ld;
+      for (int k = 0; k < j; k++) t1 -= Li[k] * Lj[k];
+    }
+    double piv = __shfl_sync(FULL, j < 32 ? t0 : t1, j & 31);
     if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
-    double s = sqrt(piv);
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      if (i > j) Lm[i * ld + j] = Lm[i * ld + j] / s;
-      else if (i == j) Lm[i * ld + j] = s;
-    }
+    double inv = rsqrt(piv);
+    if (i0 == j || i1 == j) { Lm[j * ld + j] = piv * inv; dinv[j] = inv; }
+    if (i0 > j && i0 < n) Lm[i0 * ld + j] = t0 * inv;
+    if (i1 > j && i1 < n) Lm[i1 * ld + j] = t1 * inv;
     __syncwarp();
   }
 }
 
 // solve (L L^T) x = b; b, x are workspace vectors (may alias); n <= 64
-__device__ void chol_solve(const double* Lm, const double* b, double* x, int n, int ld, int lane) {
+__device__ __noinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int ld, int lane) {
   double x0 = lane < n ? b[lane] : 0.0, x1 = lane + 32 < n ? b[lane + 32] : 0.0;
-  for (int j = 0; j < n; j++) {
+  _Pragma("unroll 1") for (int j = 0; j < n; j++) {
     double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
-    double yj = v / Lm[j * ld + j];
+    double yj = v * dinv[j];
     if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= Lm[lane * ld + j] * yj; if (lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
     else { if (lane + 32 == j) x1 = yj; else if (lane + 32 > j && lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
   }
   for (int j = n - 1; j >= 0; j--) {
     double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
-    double yj = v / Lm[j * ld + j];
+    double yj = v * dinv[j];
     if (j < 32) { if (lane == j) x0 = yj; else if (lane < j) x0 -= Lm[j * ld + lane] * yj; }
     else { if (lane + 32 == j) x1 = yj; else if (lane + 32 < j) x1 -= Lm[j * ld + lane + 32] * yj; if (lane < n) x0 -= Lm[j * ld + lane] * yj; }
   }
@@ -216,26 +221,24 @@ __device__ void chol_solve(const double* Lm, const double* b, double* x, int n, 
   __syncwarp();
 }
 
-// bottom-up accumulation child -> parent for a [nbody, width] table; deterministic (parent gathers children)
-__device__ void tree_accumulate(const Ctx& c, double* tab, int width, bool into_world) {
-  const DevModel& m = c.m; int lane = c.lane;
-  for (int l = m.nlevel - 2; l >= (into_world ? 0 : 1); l--) {
-    int a0 = m.level_adr[l], a1 = m.level_adr[l + 1], a2 = m.level_adr[l + 2];
-    for (int k = a0 + lane; k < a1; k += 32) {
-      int p = m.level_body[k];
-      for (int q = a1; q < a2; q++) {
-        int ch = m.level_body[q];
-        if (m.body_parentid[ch] == p) for (int i = 0; i < width; i++) tab[p * width + i] += tab[ch * width + i];
-      }
+// bottom-up accumulation child -> parent for a [nbody, width] table. Bodies are numbered parents-first, so one
+// reverse sweep does it; lane i owns component i (width <= 10), which keeps the summation order fixed.
+__device__ __noinline__ void tree_accumulate_raw(const int* parentid, int nbody, double* tab, int width, bool into_world, int lane) {
+  if (lane < width) {
+    _Pragma("unroll 1") for (int b = nbody - 1; b > 0; b--) {
+      int p = parentid[b];
+      if (p > 0 || into_world) tab[p * width + lane] += tab[b * width + lane];
     }
-    __syncwarp();
   }
+  __syncwarp();
 }
+#define tree_accumulate(c, tab, width, into_world) \
+  tree_accumulate_raw((c).m.body_parentid, (c).m.nbody, tab, width, into_world, (c).lane)
 
 // ------------------------------------------------------------------------------------------------
 // position stage
 // ------------------------------------------------------------------------------------------------
-__device__ void kinematics(const Ctx& c) {
+__device__ __forceinline__ void kinematics(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane;
   double* qpos = W(qpos); double* xpos = W(xpos); double* xquat = W(xquat); double* xmat = W(xmat);
   if (lane == 0) {
@@ -248,9 +251,9 @@ __device__ void kinematics(const Ctx& c) {
     else if (t == BMJ_JNT_BALL) normalize4(qpos + m.jnt_qposadr[j]);
   }
   __syncwarp();
-  for (int l = 1; l < m.nlevel; l++) {
+  _Pragma("unroll 1") for (int l = 1; l < m.nlevel; l++) {
     int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
-    for (int k = a0 + lane; k < a1; k += 32) {
+    _Pragma("unroll 1") for (int k = a0 + lane; k < a1; k += 32) {
       int b = m.level_body[k], p = m.body_parentid[b];
       double pos[3], quat[4], tmp[3], bp[3] = {m.body_pos[3*b], m.body_pos[3*b+1], m.body_pos[3*b+2]};
       double bq[4] = {m.body_quat[4*b], m.body_quat[4*b+1], m.body_quat[4*b+2], m.body_quat[4*b+3]};
@@ -258,7 +261,7 @@ __device__ void kinematics(const Ctx& c) {
       for (int i = 0; i < 3; i++) pos[i] = xpos[3 * p + i] + tmp[i];
       mul_quat(quat, xquat + 4 * p, bq);
       int j0 = m.body_jntadr[b], jn = m.body_jntnum[b];
-      for (int j = j0; j < j0 + jn; j++) {
+      _Pragma("unroll 1") for (int j = j0; j < j0 + jn; j++) {
         int qa = m.jnt_qposadr[j], t = m.jnt_type[j];
         double* anchor = W(xanchor) + 3 * j; double* axis = W(xaxis) + 3 * j;
         double jax[3] = {m.jnt_axis[3*j], m.jnt_axis[3*j+1], m.jnt_axis[3*j+2]};
@@ -323,7 +326,18 @@ __device__ __forceinline__ void site_frame(const Ctx& c, int s, double* pos, dou
   quat2mat(mat, q);
 }
 
-__device__ void com_pos(const Ctx& c) {
+__device__ __forceinline__ void geom_frame(const Ctx& c, int g, double* pos, double* mat) {
+  const DevModel& m = c.m;
+  int b = m.geom_bodyid[g];
+  double tmp[3], q[4], gp[3] = {m.geom_pos[3*g], m.geom_pos[3*g+1], m.geom_pos[3*g+2]};
+  double gq[4] = {m.geom_quat[4*g], m.geom_quat[4*g+1], m.geom_quat[4*g+2], m.geom_quat[4*g+3]};
+  mat_vec(tmp, W(xmat) + 9 * b, gp);
+  for (int i = 0; i < 3; i++) pos[i] = W(xpos)[3 * b + i] + tmp[i];
+  mul_quat(q, W(xquat) + 4 * b, gq);
+  quat2mat(mat, q);
+}
+
+__device__ __forceinline__ void com_pos(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane;
   double* sc = W(scom); double* xipos = W(xipos);
   FOR_LANES(b, m.nbody) { double ms = m.body_mass[b]; for (int i = 0; i < 3; i++) sc[3 * b + i] = ms * xipos[3 * b + i]; }
@@ -383,9 +397,9 @@ __device__ void com_pos(const Ctx& c) {
   // fixed tendons: length and (dense) Jacobian row
   FOR_LANES(t, m.ntendon) {
     double* row = W(tenJ) + t * m.ldv;
-    for (int i = 0; i < m.nv; i++) row[i] = 0;
+    _Pragma("unroll 1") for (int i = 0; i < m.nv; i++) row[i] = 0;
     double len = 0;
-    for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) {
+    _Pragma("unroll 1") for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) {
       int j = m.wrap_objid[w];
       len += m.wrap_prm[w] * W(qpos)[m.jnt_qposadr[j]];
       row[m.jnt_dofadr[j]] += m.wrap_prm[w];
@@ -395,11 +409,11 @@ __device__ void com_pos(const Ctx& c) {
   __syncwarp();
 }
 
-__device__ void crb_and_factor(const Ctx& c) {
+__device__ __forceinline__ void crb_and_factor(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double* crb = W(crb); double* M = W(M);
-  for (int i = lane; i < 10 * m.nbody; i += 32) crb[i] = W(cinert)[i];
-  for (int i = lane; i < nv * ld; i += 32) M[i] = 0;
+  _Pragma("unroll 1") for (int i = lane; i < 10 * m.nbody; i += 32) crb[i] = W(cinert)[i];
+  _Pragma("unroll 1") for (int i = lane; i < nv * ld; i += 32) M[i] = 0;
   __syncwarp();
   tree_accumulate(c, crb, 10, false);
   FOR_LANES(i, nv) {
@@ -415,99 +429,111 @@ __device__ void crb_and_factor(const Ctx& c) {
     }
   }
   __syncwarp();
-  chol_factor(M, W(LM), nv, ld, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
 // collision (narrow phase per candidate pair; lanes = pairs; ordered compaction keeps pair order)
 // ------------------------------------------------------------------------------------------------
 #define MAXPC 4   // contacts one geom pair can emit
-struct PairCon { int n; double dist[MAXPC]; double pos[MAXPC][3]; double nrm[MAXPC][3]; double tan[3]; };
+// Raw contacts are staged in shared memory (lane-strided, inside the not-yet-used Jacobian buffer) rather than in
+// a per-thread array: dynamic indexing would push that array to local memory. Slot k, field f of this lane:
+//   stg[(k*7 + f)*32]   f = 0 dist, 1..3 pos, 4..6 normal ;  tangent hint: stg[(28 + f)*32]
+#define STG(k, f) stg[((k) * 7 + (f)) * 32]
+#define STG_TAN(f) stg[(28 + (f)) * 32]
+#define STAGE_DOUBLES (31 * 32)
 
-__device__ __forceinline__ int raw_plane_sphere(PairCon& pc, double margin, const double* ppos, const double* n, const double* spos, double radius) {
-  double dif[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
-  double cdist = dot3(dif, n);
-  if (cdist > margin + radius) return 0;
-  int k = pc.n++;
-  pc.dist[k] = cdist - radius;
-  for (int i = 0; i < 3; i++) { pc.nrm[k][i] = n[i]; pc.pos[k][i] = spos[i] - n[i] * (radius + 0.5 * pc.dist[k]); }
-  return 1;
+__device__ __forceinline__ void stage_contact(double* stg, int& n, double dist, const double* pos, const double* nrm) {
+  STG(n, 0) = dist;
+  for (int i = 0; i < 3; i++) { STG(n, 1 + i) = pos[i]; STG(n, 4 + i) = nrm[i]; }
+  n++;
 }
-__device__ __forceinline__ int raw_sphere_sphere(PairCon& pc, double margin, const double* p1, double r1, const double* p2, double r2) {
+__device__ __forceinline__ void raw_plane_sphere(double* stg, int& n, double margin, const double* ppos, const double* nrm, const double* spos, double radius) {
+  double dif[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
+  double cdist = dot3(dif, nrm);
+  if (cdist > margin + radius) return;
+  double dist = cdist - radius, pos[3];
+  for (int i = 0; i < 3; i++) pos[i] = spos[i] - nrm[i] * (radius + 0.5 * dist);
+  stage_contact(stg, n, dist, pos, nrm);
+}
+__device__ __forceinline__ void raw_sphere_sphere(double* stg, int& n, double margin, const double* p1, double r1, const double* p2, double r2) {
   double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
   double cdist = norm3(dif);
-  if (cdist > margin + r1 + r2) return 0;
-  int k = pc.n++;
-  pc.dist[k] = cdist - r1 - r2;
-  if (cdist < BMJ_MINVAL) { pc.nrm[k][0] = 1; pc.nrm[k][1] = pc.nrm[k][2] = 0; }
-  else for (int i = 0; i < 3; i++) pc.nrm[k][i] = dif[i] / cdist;
-  for (int i = 0; i < 3; i++) pc.pos[k][i] = p1[i] + pc.nrm[k][i] * (r1 + 0.5 * pc.dist[k]);
-  return 1;
+  if (cdist > margin + r1 + r2) return;
+  double dist = cdist - r1 - r2, nrm[3], pos[3];
+  if (cdist < BMJ_MINVAL) { nrm[0] = 1; nrm[1] = nrm[2] = 0; }
+  else for (int i = 0; i < 3; i++) nrm[i] = dif[i] / cdist;
+  for (int i = 0; i < 3; i++) pos[i] = p1[i] + nrm[i] * (r1 + 0.5 * dist);
+  stage_contact(stg, n, dist, pos, nrm);
 }
 
-__device__ void narrowphase(PairCon& pc, int t1, int t2, double margin, const double* p1, const double* m1, const double* s1,
-                            const double* p2, const double* m2, const double* s2) {
-  pc.n = 0; pc.tan[0] = pc.tan[1] = pc.tan[2] = 0;
+// returns the number of raw contacts staged for this lane's pair (normal points from geom1 to geom2)
+__device__ __noinline__ int narrowphase(double* stg, int t1, int t2, double margin, const double* p1, const double* m1, const double* s1,
+                                        const double* p2, const double* m2, const double* s2) {
+  int n = 0;
+  STG_TAN(0) = 0; STG_TAN(1) = 0; STG_TAN(2) = 0;
   if (t1 == BMJ_GEOM_PLANE) {
-    double n[3] = {m1[2], m1[5], m1[8]};
-    if (t2 == BMJ_GEOM_SPHERE) { raw_plane_sphere(pc, margin, p1, n, p2, s2[0]); return; }
+    double nr[3] = {m1[2], m1[5], m1[8]};
+    if (t2 == BMJ_GEOM_SPHERE) { raw_plane_sphere(stg, n, margin, p1, nr, p2, s2[0]); return n; }
     if (t2 == BMJ_GEOM_CAPSULE) {
       double ax[3] = {m2[2], m2[5], m2[8]}, e[3];
       for (int i = 0; i < 3; i++) e[i] = p2[i] + ax[i] * s2[1];
-      raw_plane_sphere(pc, margin, p1, n, e, s2[0]);
+      raw_plane_sphere(stg, n, margin, p1, nr, e, s2[0]);
       for (int i = 0; i < 3; i++) e[i] = p2[i] - ax[i] * s2[1];
-      raw_plane_sphere(pc, margin, p1, n, e, s2[0]);
-      if (pc.n) for (int i = 0; i < 3; i++) pc.tan[i] = ax[i];
-      return;
+      raw_plane_sphere(stg, n, margin, p1, nr, e, s2[0]);
+      if (n) for (int i = 0; i < 3; i++) STG_TAN(i) = ax[i];
+      return n;
     }
     if (t2 == BMJ_GEOM_ELLIPSOID) {
-      double nl[3]; matT_vec(nl, m2, n);
+      double nl[3]; matT_vec(nl, m2, nr);
       double sv[3] = {nl[0] * s2[0], nl[1] * s2[1], nl[2] * s2[2]};
       double len = norm3(sv);
-      if (len < BMJ_MINVAL) return;
+      if (len < BMJ_MINVAL) return 0;
       double loc[3] = {-s2[0] * sv[0] / len, -s2[1] * sv[1] / len, -s2[2] * sv[2] / len}, pt[3];
       mat_vec(pt, m2, loc);
       for (int i = 0; i < 3; i++) pt[i] += p2[i];
       double dif[3] = {pt[0] - p1[0], pt[1] - p1[1], pt[2] - p1[2]};
-      double dist = dot3(dif, n);
-      if (dist > margin) return;
-      pc.n = 1; pc.dist[0] = dist;
-      for (int i = 0; i < 3; i++) { pc.nrm[0][i] = n[i]; pc.pos[0][i] = pt[i] - n[i] * dist * 0.5; }
-      return;
+      double dist = dot3(dif, nr);
+      if (dist > margin) return 0;
+      double pos[3];
+      for (int i = 0; i < 3; i++) pos[i] = pt[i] - nr[i] * dist * 0.5;
+      stage_contact(stg, n, dist, pos, nr);
+      return n;
     }
     if (t2 == BMJ_GEOM_BOX) {
       double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-      double dist0 = dot3(dif, n);
-      for (int k = 0; k < 8 && pc.n < MAXPC; k++) {
+      double dist0 = dot3(dif, nr);
+      for (int k = 0; k < 8 && n < MAXPC; k++) {
         double loc[3] = {(k & 1 ? s2[0] : -s2[0]), (k & 2 ? s2[1] : -s2[1]), (k & 4 ? s2[2] : -s2[2])}, corner[3];
         mat_vec(corner, m2, loc);
-        double ldist = dot3(n, corner);
+        double ldist = dot3(nr, corner);
         if (dist0 + ldist > margin || ldist > 0) continue;
-        int q = pc.n++;
-        pc.dist[q] = dist0 + ldist;
-        for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + corner[i] - n[i] * pc.dist[q] * 0.5; }
+        double dist = dist0 + ldist, pos[3];
+        for (int i = 0; i < 3; i++) pos[i] = p2[i] + corner[i] - nr[i] * dist * 0.5;
+        stage_contact(stg, n, dist, pos, nr);
       }
-      return;
+      return n;
     }
     if (t2 == BMJ_GEOM_CYLINDER) {
       double ax[3] = {m2[2], m2[5], m2[8]};
       double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-      double dist0 = dot3(dif, n), prjaxis = dot3(n, ax);
+      double dist0 = dot3(dif, nr), prjaxis = dot3(nr, ax);
       if (prjaxis > 0) { for (int i = 0; i < 3; i++) ax[i] = -ax[i]; prjaxis = -prjaxis; }
       double vec[3], len_sq = 0;
-      for (int i = 0; i < 3; i++) { vec[i] = ax[i] * prjaxis - n[i]; len_sq += vec[i] * vec[i]; }
+      for (int i = 0; i < 3; i++) { vec[i] = ax[i] * prjaxis - nr[i]; len_sq += vec[i] * vec[i]; }
       double len = sqrt(len_sq);
       if (len < 1e-12) { vec[0] = m2[0] * s2[0]; vec[1] = m2[3] * s2[0]; vec[2] = m2[6] * s2[0]; }
       else for (int i = 0; i < 3; i++) vec[i] *= s2[0] / len;
-      double prjvec = dot3(vec, n), axl[3];
+      double prjvec = dot3(vec, nr), axl[3], pos[3];
       for (int i = 0; i < 3; i++) axl[i] = ax[i] * s2[1];
       double prjax = prjaxis * s2[1];
-      if (dist0 + prjax + prjvec > margin) return;
-      int q = pc.n++; pc.dist[q] = dist0 + prjax + prjvec;
-      for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + vec[i] + axl[i] - n[i] * pc.dist[q] * 0.5; }
+      if (dist0 + prjax + prjvec > margin) return 0;
+      double dist = dist0 + prjax + prjvec;
+      for (int i = 0; i < 3; i++) pos[i] = p2[i] + vec[i] + axl[i] - nr[i] * dist * 0.5;
+      stage_contact(stg, n, dist, pos, nr);
       if (dist0 - prjax + prjvec <= margin) {
-        q = pc.n++; pc.dist[q] = dist0 - prjax + prjvec;
-        for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + vec[i] - axl[i] - n[i] * pc.dist[q] * 0.5; }
+        dist = dist0 - prjax + prjvec;
+        for (int i = 0; i < 3; i++) pos[i] = p2[i] + vec[i] - axl[i] - nr[i] * dist * 0.5;
+        stage_contact(stg, n, dist, pos, nr);
       }
       double prjvec1 = -prjvec * 0.5;
       if (dist0 + prjax + prjvec1 <= margin) {
@@ -515,24 +541,25 @@ __device__ void narrowphase(PairCon& pc, int t1, int t2, double margin, const do
         double l1 = norm3(v1);
         if (l1 > BMJ_MINVAL) {
           for (int i = 0; i < 3; i++) v1[i] *= s2[0] * sqrt(3.0) * 0.5 / l1;
-          for (int sgn = -1; sgn <= 1 && pc.n < MAXPC; sgn += 2) {
-            q = pc.n++; pc.dist[q] = dist0 + prjax + prjvec1;
-            for (int i = 0; i < 3; i++) { pc.nrm[q][i] = n[i]; pc.pos[q][i] = p2[i] + sgn * v1[i] + axl[i] - vec[i] * 0.5 - n[i] * pc.dist[q] * 0.5; }
+          for (int sgn = -1; sgn <= 1 && n < MAXPC; sgn += 2) {
+            dist = dist0 + prjax + prjvec1;
+            for (int i = 0; i < 3; i++) pos[i] = p2[i] + sgn * v1[i] + axl[i] - vec[i] * 0.5 - nr[i] * dist * 0.5;
+            stage_contact(stg, n, dist, pos, nr);
           }
         }
       }
-      return;
+      return n;
     }
-    return;
+    return 0;
   }
   if (t1 == BMJ_GEOM_SPHERE) {
-    if (t2 == BMJ_GEOM_SPHERE) { raw_sphere_sphere(pc, margin, p1, s1[0], p2, s2[0]); return; }
+    if (t2 == BMJ_GEOM_SPHERE) { raw_sphere_sphere(stg, n, margin, p1, s1[0], p2, s2[0]); return n; }
     if (t2 == BMJ_GEOM_CAPSULE) {
       double ax[3] = {m2[2], m2[5], m2[8]}, w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
       double x = clampd(dot3(ax, w), -s2[1], s2[1]), nearp[3];
       for (int i = 0; i < 3; i++) nearp[i] = p2[i] + ax[i] * x;
-      raw_sphere_sphere(pc, margin, p1, s1[0], nearp, s2[0]);
-      return;
+      raw_sphere_sphere(stg, n, margin, p1, s1[0], nearp, s2[0]);
+      return n;
     }
     if (t2 == BMJ_GEOM_BOX) {
       double w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, loc[3], cl[3], nl[3], dist;
@@ -542,21 +569,23 @@ __device__ void narrowphase(PairCon& pc, int t1, int t2, double margin, const do
       if (!inside) {
         double dl[3] = {loc[0] - cl[0], loc[1] - cl[1], loc[2] - cl[2]};
         double dn = norm3(dl);
-        if (dn - s1[0] > margin) return;
+        if (dn - s1[0] > margin) return 0;
         dist = dn - s1[0];
         for (int i = 0; i < 3; i++) nl[i] = -dl[i] / dn;
       } else {
-        int best = 0; double bd = 1e300;
-        for (int i = 0; i < 3; i++) { double dd = s2[i] - fabs(loc[i]); if (dd < bd) { bd = dd; best = i; } }
-        nl[0] = nl[1] = nl[2] = 0; nl[best] = loc[best] > 0 ? -1 : 1;
+        double bd = s2[0] - fabs(loc[0]); int best = 0;
+        if (s2[1] - fabs(loc[1]) < bd) { bd = s2[1] - fabs(loc[1]); best = 1; }
+        if (s2[2] - fabs(loc[2]) < bd) { bd = s2[2] - fabs(loc[2]); best = 2; }
+        double sg0 = loc[0] > 0 ? -1 : 1, sg1 = loc[1] > 0 ? -1 : 1, sg2 = loc[2] > 0 ? -1 : 1;
+        nl[0] = best == 0 ? sg0 : 0; nl[1] = best == 1 ? sg1 : 0; nl[2] = best == 2 ? sg2 : 0;
         dist = -bd - s1[0];
       }
-      double nw[3]; mat_vec(nw, m2, nl);
-      pc.n = 1; pc.dist[0] = dist;
-      for (int i = 0; i < 3; i++) { pc.nrm[0][i] = nw[i]; pc.pos[0][i] = p1[i] + nw[i] * (s1[0] + 0.5 * dist); }
-      return;
+      double nw[3], pos[3]; mat_vec(nw, m2, nl);
+      for (int i = 0; i < 3; i++) pos[i] = p1[i] + nw[i] * (s1[0] + 0.5 * dist);
+      stage_contact(stg, n, dist, pos, nw);
+      return n;
     }
-    return;
+    return 0;
   }
   if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE) {
     double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
@@ -572,37 +601,38 @@ __device__ void narrowphase(PairCon& pc, int t1, int t2, double margin, const do
       else if (x2 < -len2) { x2 = -len2; x1 = clampd((u + mb * len2) / ma, -len1, len1); }
       double v1[3], v2[3];
       for (int i = 0; i < 3; i++) { v1[i] = p1[i] + a1[i] * x1; v2[i] = p2[i] + a2[i] * x2; }
-      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
-      return;
+      raw_sphere_sphere(stg, n, margin, v1, s1[0], v2, s2[0]);
+      return n;
     }
-    for (int e = 0; e < 2 && pc.n < 2; e++) {
+    for (int e = 0; e < 2 && n < 2; e++) {
       double x1 = e == 0 ? len1 : -len1, v1[3], v2[3];
       for (int i = 0; i < 3; i++) v1[i] = p1[i] + a1[i] * x1;
       double w[3] = {v1[0] - p2[0], v1[1] - p2[1], v1[2] - p2[2]};
       double x2 = dot3(w, a2);
       if (x2 < -len2 || x2 > len2) continue;
       for (int i = 0; i < 3; i++) v2[i] = p2[i] + a2[i] * x2;
-      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+      raw_sphere_sphere(stg, n, margin, v1, s1[0], v2, s2[0]);
     }
-    for (int e = 0; e < 2 && pc.n < 2; e++) {
+    for (int e = 0; e < 2 && n < 2; e++) {
       double x2 = e == 0 ? len2 : -len2, v1[3], v2[3];
       for (int i = 0; i < 3; i++) v2[i] = p2[i] + a2[i] * x2;
       double w[3] = {v2[0] - p1[0], v2[1] - p1[1], v2[2] - p1[2]};
       double x1 = dot3(w, a1);
       if (x1 <= -len1 || x1 >= len1) continue;
       for (int i = 0; i < 3; i++) v1[i] = p1[i] + a1[i] * x1;
-      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+      raw_sphere_sphere(stg, n, margin, v1, s1[0], v2, s2[0]);
     }
-    if (pc.n == 0) {
+    if (n == 0) {
       double x1 = clampd(u / ma, -len1, len1), v1[3], v2[3];
       for (int i = 0; i < 3; i++) v1[i] = p1[i] + a1[i] * x1;
       double w[3] = {v1[0] - p2[0], v1[1] - p2[1], v1[2] - p2[2]};
       double x2 = clampd(dot3(w, a2), -len2, len2);
       for (int i = 0; i < 3; i++) v2[i] = p2[i] + a2[i] * x2;
-      raw_sphere_sphere(pc, margin, v1, s1[0], v2, s2[0]);
+      raw_sphere_sphere(stg, n, margin, v1, s1[0], v2, s2[0]);
     }
-    return;
+    return n;
   }
+  return 0;
 }
 
 __device__ __forceinline__ void make_frame(double* frame, const double* normal, const double* tangent) {
@@ -624,14 +654,14 @@ __device__ __forceinline__ void make_frame(double* frame, const double* normal, 
 #define CON_STRIDE 16
 __device__ __forceinline__ int* con_ints(double* rec) { return reinterpret_cast<int*>(rec + 14); }
 
-__device__ int collision(const Ctx& c, int* warn_contactfull) {
+__device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
   const DevModel& m = c.m; int lane = c.lane;
   int ncon = 0;
   if (c.disableflags & (BMJ_DSBL_CONTACT | BMJ_DSBL_CONSTRAINT)) return 0;
-  for (int base = 0; base < m.npair; base += 32) {
+  double* stg = W(J) + lane;      // staging lives in the Jacobian buffer, which is written only after collision
+  _Pragma("unroll 1") for (int base = 0; base < m.npair; base += 32) {
     int p = base + lane;
-    PairCon pc; pc.n = 0;
-    int g1 = 0, g2 = 0;
+    int n = 0, g1 = 0, g2 = 0;
     if (p < m.npair) {
       g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
       int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
@@ -641,8 +671,8 @@ __device__ int collision(const Ctx& c, int* warn_contactfull) {
       bool keep;
       double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
       if (t1 == BMJ_GEOM_PLANE) {
-        double n[3] = {m1[2], m1[5], m1[8]};
-        keep = dot3(dif, n) <= m.geom_rbound[g2] + margin;
+        double nr[3] = {m1[2], m1[5], m1[8]};
+        keep = dot3(dif, nr) <= m.geom_rbound[g2] + margin;
       } else {
         double bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
         keep = dot3(dif, dif) <= bound * bound;
@@ -650,19 +680,20 @@ __device__ int collision(const Ctx& c, int* warn_contactfull) {
       if (keep) {
         double s1[3] = {m.geom_size[3*g1], m.geom_size[3*g1+1], m.geom_size[3*g1+2]};
         double s2[3] = {m.geom_size[3*g2], m.geom_size[3*g2+1], m.geom_size[3*g2+2]};
-        narrowphase(pc, t1, t2, margin, p1, m1, s1, p2, m2, s2);
+        n = narrowphase(stg, t1, t2, margin, p1, m1, s1, p2, m2, s2);
       }
     }
     int total;
-    int off = warp_excl_scan(pc.n, lane, &total);
+    int off = warp_excl_scan(n, lane, &total);
     if (total == 0) continue;
-    for (int k = 0; k < pc.n; k++) {
+    _Pragma("unroll 1") for (int k = 0; k < n; k++) {
       int idx = ncon + off + k;
       if (idx >= m.nconmax) continue;
       double* rec = W(con) + idx * CON_STRIDE;
-      rec[0] = pc.dist[k];
-      for (int i = 0; i < 3; i++) rec[1 + i] = pc.pos[k][i];
-      make_frame(rec + 4, pc.nrm[k], pc.tan);
+      rec[0] = STG(k, 0);
+      double nrm[3], tan[3];
+      for (int i = 0; i < 3; i++) { rec[1 + i] = STG(k, 1 + i); nrm[i] = STG(k, 4 + i); tan[i] = STG_TAN(i); }
+      make_frame(rec + 4, nrm, tan);
       int pr1 = m.geom_priority[g1], pr2 = m.geom_priority[g2];
       int condim; double mu;
       if (pr1 != pr2) { int gp = pr1 > pr2 ? g1 : g2; condim = m.geom_condim[gp]; mu = m.geom_friction[3 * gp]; }
@@ -681,43 +712,49 @@ __device__ int collision(const Ctx& c, int* warn_contactfull) {
 // ------------------------------------------------------------------------------------------------
 // constraint rows: Jacobian, regulariser D = 1/R and reference acceleration, fused
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double impedance_fn(const double* solimp, double pos, double margin) {
-  double d0 = clampd(solimp[0], BMJ_MINIMP, BMJ_MAXIMP), dmax = clampd(solimp[1], BMJ_MINIMP, BMJ_MAXIMP);
-  double width = fmax(BMJ_MINVAL, solimp[2]), mid = clampd(solimp[3], BMJ_MINIMP, BMJ_MAXIMP), power = fmax(1.0, solimp[4]);
-  double x = fabs(pos - margin) / width;
-  if (x >= 1) return dmax;
-  if (x <= 0) return d0;
-  double y;
-  if (power == 1) y = x;
-  else if (x <= mid) y = pow(x / mid, power) * mid;
-  else y = 1 - pow((1 - x) / (1 - mid), power) * (1 - mid);
-  return d0 + y * (dmax - d0);
-}
-// -> R (before the pyramid rescale) and aref for one row
-__device__ __forceinline__ void row_params(const Ctx& c, const double* solref, const double* solimp, double pos, double margin,
-                                           double diag, double vel, double* R, double* aref, double* imp_out) {
-  double imp = impedance_fn(solimp, pos, margin);
-  double dmax = clampd(solimp[1], BMJ_MINIMP, BMJ_MAXIMP);
+struct RowPrm { double R, aref; };
+// impedance d(r), stiffness/damping from solref, regulariser R and reference acceleration for one row
+__device__ __noinline__ RowPrm row_params_raw(double sr0, double sr1, double si0, double si1, double si2, double si3, double si4,
+                                              double pos, double margin, double diag, double vel, double timestep, int refsafe) {
+  double d0 = clampd(si0, BMJ_MINIMP, BMJ_MAXIMP), dmax = clampd(si1, BMJ_MINIMP, BMJ_MAXIMP);
+  double width = fmax(BMJ_MINVAL, si2), mid = clampd(si3, BMJ_MINIMP, BMJ_MAXIMP), power = fmax(1.0, si4);
+  double x = fabs(pos - margin) / width, imp;
+  if (x >= 1) imp = dmax;
+  else if (x <= 0) imp = d0;
+  else {
+    double y;
+    if (power == 1) y = x;
+    else if (x <= mid) y = pow(x / mid, power) * mid;
+    else y = 1 - pow((1 - x) / (1 - mid), power) * (1 - mid);
+    imp = d0 + y * (dmax - d0);
+  }
   double K, B;
-  if (solref[0] > 0) {
-    double tc = solref[0], dr = solref[1];
-    if (!(c.disableflags & BMJ_DSBL_REFSAFE)) tc = fmax(tc, 2 * c.m.timestep);
+  if (sr0 > 0) {
+    double tc = sr0, dr = sr1;
+    if (refsafe) tc = fmax(tc, 2 * timestep);
     K = 1 / fmax(BMJ_MINVAL, dmax * dmax * tc * tc * dr * dr);
     B = 2 / fmax(BMJ_MINVAL, dmax * tc);
-  } else { K = -solref[0] / fmax(BMJ_MINVAL, dmax * dmax); B = -solref[1] / fmax(BMJ_MINVAL, dmax); }
-  *R = fmax(BMJ_MINVAL, (1 - imp) * diag / imp);
-  *aref = -B * vel - K * imp * (pos - margin);
-  *imp_out = imp;
+  } else { K = -sr0 / fmax(BMJ_MINVAL, dmax * dmax); B = -sr1 / fmax(BMJ_MINVAL, dmax); }
+  RowPrm r;
+  r.R = fmax(BMJ_MINVAL, (1 - imp) * diag / imp);
+  r.aref = -B * vel - K * imp * (pos - margin);
+  return r;
+}
+__device__ __forceinline__ void row_params(const Ctx& c, const double* solref, const double* solimp, double pos, double margin,
+                                           double diag, double vel, double* R, double* aref, double* imp_out) {
+  RowPrm r = row_params_raw(solref[0], solref[1], solimp[0], solimp[1], solimp[2], solimp[3], solimp[4], pos, margin, diag, vel,
+                            c.m.timestep, !(c.disableflags & BMJ_DSBL_REFSAFE));
+  *R = r.R; *aref = r.aref; *imp_out = 0;
 }
 
-__device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
+__device__ __forceinline__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double* J = W(J); double* qvel = W(qvel);
   int nefc = 0;
   if (c.disableflags & BMJ_DSBL_CONSTRAINT) return 0;
   // ---- equality (all lanes build one row at a time) ----
   if (!(c.disableflags & BMJ_DSBL_EQUALITY)) {
-    for (int e = 0; e < m.neq; e++) {
+    _Pragma("unroll 1") for (int e = 0; e < m.neq; e++) {
       if (!m.eq_active0[e]) continue;
       if (nefc >= m.njmax) { *warn_cnstrfull = 1; return nefc; }
       const double* data = m.eq_data + 11 * e;
@@ -759,7 +796,7 @@ __device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
   __syncwarp();
   // ---- joint limits (one lane per joint; ordered compaction) ----
   if (!(c.disableflags & BMJ_DSBL_LIMIT)) {
-    for (int base = 0; base < m.njnt; base += 32) {
+    _Pragma("unroll 1") for (int base = 0; base < m.njnt; base += 32) {
       int j = base + lane;
       int cnt = 0; double dist[2]; int side[2];
       if (j < m.njnt && m.jnt_limited[j]) {
@@ -773,12 +810,12 @@ __device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
         }
       }
       int total, off = warp_excl_scan(cnt, lane, &total);
-      for (int k = 0; k < cnt; k++) {
+      _Pragma("unroll 1") for (int k = 0; k < cnt; k++) {
         int r = nefc + off + k;
         if (r >= m.njmax) continue;
         int da = m.jnt_dofadr[j];
         double* row = J + r * ld;
-        for (int i = 0; i < nv; i++) row[i] = 0;
+        _Pragma("unroll 1") for (int i = 0; i < nv; i++) row[i] = 0;
         row[da] = -side[k];
         double vel = -side[k] * qvel[da], R, aref, imp;
         row_params(c, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist[k], m.jnt_margin[j], m.dof_invweight0[da], vel, &R, &aref, &imp);
@@ -790,7 +827,7 @@ __device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
   }
   __syncwarp();
   // ---- contacts (lanes = dofs) ----
-  for (int ci = 0; ci < ncon; ci++) {
+  _Pragma("unroll 1") for (int ci = 0; ci < ncon; ci++) {
     double* rec = W(con) + ci * CON_STRIDE;
     int* ii = con_ints(rec);
     int g1 = ii[0], g2 = ii[1], dim = ii[2];
@@ -808,7 +845,7 @@ __device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
     int r1 = m.body_rootid[b1], r2 = m.body_rootid[b2];
     for (int i = 0; i < 3; i++) { off1[i] = pos[i] - W(scom)[3 * r1 + i]; off2[i] = pos[i] - W(scom)[3 * r2 + i]; }
     double pv[3] = {0, 0, 0};
-    for (int i = lane; i < nv; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
       unsigned w1 = (unsigned)m.body_dofmask[2 * b1 + (i >> 5)], w2 = (unsigned)m.body_dofmask[2 * b2 + (i >> 5)];
       bool in1 = (w1 >> (i & 31)) & 1, in2 = (w2 >> (i & 31)) & 1;
       double jd[3] = {0, 0, 0};
@@ -873,20 +910,20 @@ __device__ int make_constraint(const Ctx& c, int ncon, int* warn_cnstrfull) {
 // ------------------------------------------------------------------------------------------------
 // velocity stage: cvel, cdof_dot, passive forces, RNE bias
 // ------------------------------------------------------------------------------------------------
-__device__ void fwd_velocity(const Ctx& c) {
+__device__ __forceinline__ void fwd_velocity(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane;
   double* cvel = W(cvel); double* cacc = W(cacc); double* cfrc = W(cfrc); double* qvel = W(qvel);
   if (lane < 6) { cvel[lane] = 0; cfrc[lane] = 0; cacc[lane] = 0; }
   if (lane < 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) cacc[3 + lane] = -m.gravity[lane];
   __syncwarp();
-  for (int l = 1; l < m.nlevel; l++) {
+  _Pragma("unroll 1") for (int l = 1; l < m.nlevel; l++) {
     int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
-    for (int k = a0 + lane; k < a1; k += 32) {
+    _Pragma("unroll 1") for (int k = a0 + lane; k < a1; k += 32) {
       int b = m.level_body[k], p = m.body_parentid[b];
       double cv[6], ca[6];
       for (int i = 0; i < 6; i++) { cv[i] = cvel[6 * p + i]; ca[i] = cacc[6 * p + i]; }
       int j0 = m.body_jntadr[b], jn = m.body_jntnum[b];
-      for (int j = j0; j < j0 + jn; j++) {
+      _Pragma("unroll 1") for (int j = j0; j < j0 + jn; j++) {
         int da = m.jnt_dofadr[j], t = m.jnt_type[j];
         double* cdd = W(cdofdot); const double* cd = W(cdof);
         if (t == BMJ_JNT_FREE) {
@@ -903,7 +940,7 @@ __device__ void fwd_velocity(const Ctx& c) {
         }
       }
       int d0 = m.body_dofadr[b], dn = m.body_dofnum[b];
-      for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * qvel[q];
+      _Pragma("unroll 1") for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * qvel[q];
       double t1[6], t2[6], t3[6];
       mul_inert_vec(t1, W(cinert) + 10 * b, ca);
       mul_inert_vec(t2, W(cinert) + 10 * b, cv);
@@ -932,7 +969,7 @@ __device__ void fwd_velocity(const Ctx& c) {
   __syncwarp();
 }
 
-__device__ void subtree_vel(const Ctx& c) {
+__device__ __forceinline__ void subtree_vel(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane;
   double* sl = W(slinvel);
   FOR_LANES(b, m.nbody) {
@@ -951,7 +988,7 @@ __device__ void subtree_vel(const Ctx& c) {
 // ------------------------------------------------------------------------------------------------
 // acceleration stage
 // ------------------------------------------------------------------------------------------------
-__device__ void fwd_actuation(const Ctx& c) {
+__device__ __forceinline__ void fwd_actuation(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   bool off = c.disableflags & BMJ_DSBL_ACTUATION;
   FOR_LANES(a, m.nu) {
@@ -973,7 +1010,7 @@ __device__ void fwd_actuation(const Ctx& c) {
       } else {
         int t = m.actuator_trnid[a];
         length = gear * W(tenlen)[t];
-        double s = 0; for (int i = 0; i < nv; i++) s += gear * W(tenJ)[t * ld + i] * W(qvel)[i];
+        double s = 0; _Pragma("unroll 1") for (int i = 0; i < nv; i++) s += gear * W(tenJ)[t * ld + i] * W(qvel)[i];
         velocity = s;
       }
       const double* gp = m.actuator_gainprm + 3 * a; const double* bp = m.actuator_biasprm + 3 * a;
@@ -989,7 +1026,7 @@ __device__ void fwd_actuation(const Ctx& c) {
   __syncwarp();
   FOR_LANES(i, nv) {
     double s = 0;
-    for (int a = 0; a < m.nu; a++) {
+    _Pragma("unroll 1") for (int a = 0; a < m.nu; a++) {
       double gear = m.actuator_gear[a], mom;
       if (m.actuator_trntype[a] == BMJ_TRN_JOINT) mom = (m.jnt_dofadr[m.actuator_trnid[a]] == i) ? gear : 0.0;
       else mom = gear * W(tenJ)[m.actuator_trnid[a] * ld + i];
@@ -1000,7 +1037,7 @@ __device__ void fwd_actuation(const Ctx& c) {
   __syncwarp();
 }
 
-__device__ void fwd_acceleration(const Ctx& c, const b200mj_io& io, int env) {
+__device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& io, int env) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
   FOR_LANES(i, nv) {
     double s = W(passive)[i] - W(bias)[i] + W(qfact)[i];
@@ -1008,7 +1045,7 @@ __device__ void fwd_acceleration(const Ctx& c, const b200mj_io& io, int env) {
     W(smooth)[i] = s;
   }
   if (io.xfrc_applied) {
-    for (int b = 1; b < m.nbody; b++) {
+    _Pragma("unroll 1") for (int b = 1; b < m.nbody; b++) {
       const double* xf = io.xfrc_applied + ((size_t)env * m.nbody + b) * 6;
       double f[6]; bool any = false;
       for (int i = 0; i < 6; i++) { f[i] = xf[i]; any |= (f[i] != 0); }
@@ -1028,66 +1065,90 @@ __device__ void fwd_acceleration(const Ctx& c, const b200mj_io& io, int env) {
     }
   }
   __syncwarp();
-  chol_solve(W(LM), W(smooth), W(qaccs), nv, m.ldv, lane);
+  // factor M into the H buffer (free until the Newton solver assembles its Hessian there)
+  chol_factor(W(M), W(H), W(dinv), nv, m.ldv, lane);
+  chol_solve(W(H), W(dinv), W(smooth), W(qaccs), nv, m.ldv, lane);
 }
 
 // --- Newton solver ---------------------------------------------------------------------------------
-struct Primal { double cost, gauss; };
+struct Primal { double cost, gauss; int nact, changed; };
 
 // Ma = M qacc ; jar = J qacc - aref
-__device__ void compute_Ma_jar(const Ctx& c, int nefc) {
+__device__ __forceinline__ void compute_Ma_jar(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
-  FOR_LANES(i, nv) { double s = 0; const double* Mi = W(M) + i * ld; for (int j = 0; j < nv; j++) s += Mi[j] * W(qacc)[j]; W(Ma)[i] = s; }
-  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; for (int i = 0; i < nv; i++) s += Jr[i] * W(qacc)[i]; W(jar)[r] = s - W(aref)[r]; }
+  FOR_LANES(i, nv) { double s = 0; const double* Mi = W(M) + i * ld; _Pragma("unroll 1") for (int j = 0; j < nv; j++) s += Mi[j] * W(qacc)[j]; W(Ma)[i] = s; }
+  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; _Pragma("unroll 1") for (int i = 0; i < nv; i++) s += Jr[i] * W(qacc)[i]; W(jar)[r] = s - W(aref)[r]; }
   __syncwarp();
 }
 
-__device__ Primal constraint_update(const Ctx& c, int nefc) {
+__device__ __forceinline__ Primal constraint_update(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   const int* eqf = reinterpret_cast<const int*>(W(eqflag));
+  int* alist = reinterpret_cast<int*>(W(actlist));
   double cpart = 0;
-  FOR_LANES(r, nefc) {
-    double jar = W(jar)[r], D = W(efcD)[r];
-    bool act = eqf[r] || jar < 0;
-    W(efcSD)[r] = act ? D : 0.0;
-    W(force)[r] = act ? -D * jar : 0.0;
-    if (act) cpart += 0.5 * D * jar * jar;
+  int nact = 0, changed = 0;
+  _Pragma("unroll 1") for (int base = 0; base < nefc; base += 32) {
+    int r = base + lane;
+    bool act = false;
+    if (r < nefc) {
+      double jar = W(jar)[r], D = W(efcD)[r];
+      act = eqf[r] || jar < 0;
+      changed |= ((W(efcSD)[r] != 0.0) != act);
+      W(efcSD)[r] = act ? D : 0.0;
+      W(force)[r] = act ? -D * jar : 0.0;
+      if (act) cpart += 0.5 * D * jar * jar;
+    }
+    unsigned bal = __ballot_sync(FULL, act);
+    if (act) alist[nact + __popc(bal & ((1u << lane) - 1))] = r;
+    nact += __popc(bal);
   }
   __syncwarp();
   double gpart = 0;
   FOR_LANES(i, nv) {
     double s = 0;
-    for (int r = 0; r < nefc; r++) s += W(J)[r * ld + i] * W(force)[r];
+    _Pragma("unroll 1") for (int a = 0; a < nact; a++) { int r = alist[a]; s += W(J)[r * ld + i] * W(force)[r]; }
     W(qcon)[i] = s;
     gpart += (W(Ma)[i] - W(smooth)[i]) * (W(qacc)[i] - W(qaccs)[i]);
   }
   Primal p;
   p.gauss = 0.5 * warp_sum(gpart);
   p.cost = warp_sum(cpart) + p.gauss;
+  p.nact = nact;
+  p.changed = __any_sync(FULL, changed);
   __syncwarp();
   return p;
 }
 
-// grad, H = M + J^T diag(SD) J, factor, search = -H^-1 grad ; returns |grad|
-__device__ double newton_direction(const Ctx& c, int nefc) {
+// grad; (re)assemble H = M + J^T diag(SD) J and factor it only when the active set changed; search = -H^-1 grad.
+// Returns |grad|.
+__device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int nact, bool refactor) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double gpart = 0;
   FOR_LANES(i, nv) { double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; W(grad)[i] = g; gpart += g * g; }
   double gnorm = sqrt(warp_sum(gpart));
-  // lane j owns column j of H (and column j+32)
-  for (int j = lane; j < nv; j += 32) {
-    for (int i = 0; i < nv; i++) {
-      double acc = W(M)[i * ld + j];
-      for (int r = 0; r < nefc; r++) {
-        double sd = W(efcSD)[r];
-        acc += (sd * W(J)[r * ld + i]) * W(J)[r * ld + j];
+  if (refactor) {
+    const int* alist = reinterpret_cast<const int*>(W(actlist));
+    // lane j owns column j (and j+32) of the lower triangle; rows in register blocks of 8
+    _Pragma("unroll 1") for (int j = lane; j < nv; j += 32) {
+      _Pragma("unroll 1") for (int i0 = (j & ~7); i0 < nv; i0 += 8) {
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = (i0 + q < nv) ? W(M)[(i0 + q) * ld + j] : 0.0;
+        _Pragma("unroll 1") for (int a = 0; a < nact; a++) {
+          int r = alist[a];
+          const double* Jr = W(J) + r * ld;
+          double sj = W(efcSD)[r] * Jr[j];
+#pragma unroll
+          for (int q = 0; q < 8; q++) if (i0 + q < nv) acc[q] += Jr[i0 + q] * sj;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (i0 + q < nv) W(H)[(i0 + q) * ld + j] = acc[q];
       }
-      W(H)[i * ld + j] = acc;
     }
+    __syncwarp();
+    chol_factor(W(H), W(H), W(dinv), nv, ld, lane);   // in place: column j only reads columns < j and A[.][j]
   }
-  __syncwarp();
-  chol_factor(W(H), W(H), nv, ld, lane);   // in place: column j only reads columns < j and A[.][j]
-  chol_solve(W(H), W(grad), W(search), nv, ld, lane);
+  chol_solve(W(H), W(dinv), W(grad), W(search), nv, ld, lane);
   FOR_LANES(i, nv) W(search)[i] = -W(search)[i];
   __syncwarp();
   return gnorm;
@@ -1107,7 +1168,7 @@ __device__ __forceinline__ void ls_eval(const Ctx& c, int nefc, double alpha, co
   *d2 = 2 * q2;
 }
 
-__device__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
+__device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double sp = 0;
   FOR_LANES(i, nv) sp += W(search)[i] * W(search)[i];
@@ -1117,11 +1178,11 @@ __device__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
   double g1 = 0, g2 = 0;
   FOR_LANES(i, nv) {
     double s = 0; const double* Mi = W(M) + i * ld;
-    for (int j = 0; j < nv; j++) s += Mi[j] * W(search)[j];
+    _Pragma("unroll 1") for (int j = 0; j < nv; j++) s += Mi[j] * W(search)[j];
     W(Mv)[i] = s;
     g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
   }
-  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; for (int i = 0; i < nv; i++) s += Jr[i] * W(search)[i]; W(jv)[r] = s; }
+  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; _Pragma("unroll 1") for (int i = 0; i < nv; i++) s += Jr[i] * W(search)[i]; W(jv)[r] = s; }
   double qg[3] = {pr.gauss, warp_sum(g1), warp_sum(g2)};
   __syncwarp();
   double d1, d2;
@@ -1129,7 +1190,7 @@ __device__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
   if (d1 >= 0 || d2 <= 0) return 0;
   double lo = 0, dlo = d1, hi = 0, dhi = 0; bool have_hi = false;
   double alpha = -d1 / d2, best = 0;
-  for (int it = 0; it < m.ls_iterations; it++) {
+  _Pragma("unroll 1") for (int it = 0; it < m.ls_iterations; it++) {
     double e1, e2;
     ls_eval(c, nefc, alpha, qg, &e1, &e2);
     best = alpha;
@@ -1144,51 +1205,51 @@ __device__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
   return best;
 }
 
-__device__ int solve_newton(const Ctx& c, int nefc) {
+__device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
   Primal pr;
-  if (!(c.disableflags & BMJ_DSBL_WARMSTART)) {
-    FOR_LANES(i, nv) W(qacc)[i] = W(qaccws)[i];
+  // start point: the warm start if it has lower cost than the unconstrained acceleration.
+  // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart again (when it won)
+  bool warm = !(c.disableflags & BMJ_DSBL_WARMSTART);
+  double cost_warm = 0;
+  for (int cand = warm ? 0 : 1; cand < 3; cand++) {
+    if (cand == 2 && !(warm && cost_warm < pr.cost)) break;
+    const double* src = (cand == 1) ? W(qaccs) : W(qaccws);
+    FOR_LANES(i, nv) W(qacc)[i] = src[i];
     __syncwarp();
-    compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
-    double cost_warm = pr.cost;
-    FOR_LANES(i, nv) W(qacc)[i] = W(qaccs)[i];
-    __syncwarp();
-    compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
-    if (cost_warm < pr.cost) {
-      FOR_LANES(i, nv) W(qacc)[i] = W(qaccws)[i];
-      __syncwarp();
-      compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
-    }
-  } else {
-    FOR_LANES(i, nv) W(qacc)[i] = W(qaccs)[i];
-    __syncwarp();
-    compute_Ma_jar(c, nefc); pr = constraint_update(c, nefc);
+    compute_Ma_jar(c, nefc);
+    pr = constraint_update(c, nefc);
+    if (cand == 0) cost_warm = pr.cost;
   }
-  newton_direction(c, nefc);
   double scale = 1 / (m.meaninertia * max(1, nv));
   int iter = 0;
-  while (iter < m.iterations) {
+  bool refactor = true;
+  double oldcost = 0;
+  while (true) {
+    double gnorm = newton_direction(c, nefc, pr.nact, refactor);
+    if (iter > 0) {
+      double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
+      if (improvement < m.tolerance || gradient < m.tolerance) break;
+    }
+    if (iter >= m.iterations) break;
     double alpha = line_search(c, nefc, pr);
     if (alpha == 0) break;
     FOR_LANES(i, nv) { W(qacc)[i] += alpha * W(search)[i]; W(Ma)[i] += alpha * W(Mv)[i]; }
     FOR_LANES(r, nefc) W(jar)[r] += alpha * W(jv)[r];
     __syncwarp();
-    double oldcost = pr.cost;
+    oldcost = pr.cost;
     pr = constraint_update(c, nefc);
-    double gnorm = newton_direction(c, nefc);
+    refactor = pr.changed != 0;
     iter++;
-    double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
-    if (improvement < m.tolerance || gradient < m.tolerance) break;
   }
   return iter;
 }
 
 // cacc / cfrc_int with qacc + external contact forces (for accelerometer / force / torque sensors)
-__device__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, int ncon) {
+__device__ __forceinline__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, int ncon) {
   const DevModel& m = c.m; int lane = c.lane;
   double* cext = W(cfrcext); double* cacc = W(cacc); double* cint = W(cfrc);
-  for (int i = lane; i < 6 * m.nbody; i += 32) cext[i] = 0;
+  _Pragma("unroll 1") for (int i = lane; i < 6 * m.nbody; i += 32) cext[i] = 0;
   __syncwarp();
   if (io.xfrc_applied) {
     FOR_LANES(b, m.nbody) {
@@ -1204,7 +1265,7 @@ __device__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, 
   }
   // contacts: serial over contacts (lane 0) keeps the accumulation order fixed
   if (lane == 0) {
-    for (int ci = 0; ci < ncon; ci++) {
+    _Pragma("unroll 1") for (int ci = 0; ci < ncon; ci++) {
       double* rec = W(con) + ci * CON_STRIDE; int* ii = con_ints(rec);
       int adr = ii[3]; if (adr < 0) continue;
       double f[3] = {0, 0, 0}, mu = rec[13];
@@ -1225,14 +1286,14 @@ __device__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, 
   if (lane < 6) { cacc[lane] = 0; cint[lane] = 0; }
   if (lane < 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) cacc[3 + lane] = -m.gravity[lane];
   __syncwarp();
-  for (int l = 1; l < m.nlevel; l++) {
+  _Pragma("unroll 1") for (int l = 1; l < m.nlevel; l++) {
     int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
-    for (int k = a0 + lane; k < a1; k += 32) {
+    _Pragma("unroll 1") for (int k = a0 + lane; k < a1; k += 32) {
       int b = m.level_body[k], p = m.body_parentid[b];
       double ca[6];
       for (int i = 0; i < 6; i++) ca[i] = cacc[6 * p + i];
       int d0 = m.body_dofadr[b], dn = m.body_dofnum[b];
-      for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * W(qvel)[q] + W(cdof)[6 * q + i] * W(qacc)[q];
+      _Pragma("unroll 1") for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * W(qvel)[q] + W(cdof)[6 * q + i] * W(qacc)[q];
       double t1[6], t2[6], t3[6];
       mul_inert_vec(t1, W(cinert) + 10 * b, ca);
       mul_inert_vec(t2, W(cinert) + 10 * b, W(cvel) + 6 * b);
@@ -1262,7 +1323,7 @@ __device__ __forceinline__ void iv_slab(Interval& r, double p, double v, double 
   if (fabs(v) < BMJ_MINVAL) { if (fabs(p) > half) r.ok = false; return; }
   iv_clip(r, (-half - p) / v, (half - p) / v);
 }
-__device__ bool ray_hits_zone(int type, const double* sz, const double* p, const double* v) {
+__device__ __noinline__ bool ray_hits_zone(int type, const double* sz, const double* p, const double* v) {
   Interval r; r.lo = -1e300; r.hi = 1e300; r.ok = true;
   if (type == BMJ_GEOM_SPHERE) iv_quadric(r, dot3(v, v), dot3(p, v), dot3(p, p) - sz[0] * sz[0]);
   else if (type == BMJ_GEOM_ELLIPSOID) {
@@ -1289,11 +1350,11 @@ __device__ bool ray_hits_zone(int type, const double* sz, const double* p, const
 // ------------------------------------------------------------------------------------------------
 // sensors (stage 1 = position, 2 = velocity, 3 = acceleration); results staged in the workspace
 // ------------------------------------------------------------------------------------------------
-__device__ void sensors(const Ctx& c, int stage, int ncon) {
+__device__ __forceinline__ void sensors(const Ctx& c, int stage_mask, int ncon) {
   const DevModel& m = c.m; int lane = c.lane;
   if (c.disableflags & BMJ_DSBL_SENSOR) return;
   FOR_LANES(s, m.nsensor) {
-    if (m.sensor_needstage[s] != stage) continue;
+    if (!((stage_mask >> (m.sensor_needstage[s] - 1)) & 1)) continue;
     double* out = W(sens) + m.sensor_adr[s];
     int id = m.sensor_objid[s], st = m.sensor_type[s];
     if (st == BMJ_SENS_JOINTPOS) out[0] = W(qpos)[m.jnt_qposadr[id]];
@@ -1305,7 +1366,7 @@ __device__ void sensors(const Ctx& c, int stage, int ncon) {
       double p[3], pm[9];
       int ot = m.sensor_objtype[s];
       if (ot == BMJ_OBJ_SITE) site_frame(c, id, p, pm);
-      else if (ot == BMJ_OBJ_GEOM) for (int i = 0; i < 3; i++) p[i] = W(gxpos)[3 * id + i];
+      else if (ot == BMJ_OBJ_GEOM) geom_frame(c, id, p, pm);
       else if (ot == BMJ_OBJ_BODY) for (int i = 0; i < 3; i++) p[i] = W(xipos)[3 * id + i];
       else for (int i = 0; i < 3; i++) p[i] = W(xpos)[3 * id + i];
       int rid = m.sensor_refid[s];
@@ -1313,7 +1374,7 @@ __device__ void sensors(const Ctx& c, int stage, int ncon) {
       else {
         double rp[3], rm[9]; int rt = m.sensor_reftype[s];
         if (rt == BMJ_OBJ_SITE) site_frame(c, rid, rp, rm);
-        else if (rt == BMJ_OBJ_GEOM) { for (int i = 0; i < 3; i++) rp[i] = W(gxpos)[3 * rid + i]; for (int i = 0; i < 9; i++) rm[i] = W(gxmat)[9 * rid + i]; }
+        else if (rt == BMJ_OBJ_GEOM) geom_frame(c, rid, rp, rm);
         else if (rt == BMJ_OBJ_BODY) {
           for (int i = 0; i < 3; i++) rp[i] = W(xipos)[3 * rid + i];
           double q[4], iq[4] = {m.body_iquat[4*rid], m.body_iquat[4*rid+1], m.body_iquat[4*rid+2], m.body_iquat[4*rid+3]};
@@ -1348,7 +1409,7 @@ __device__ void sensors(const Ctx& c, int stage, int ncon) {
       double sp[3], sm[9]; site_frame(c, id, sp, sm);
       int b = m.site_bodyid[id]; double total = 0;
       double sz[3] = {m.site_size[3*id], m.site_size[3*id+1], m.site_size[3*id+2]}; int stp = m.site_type[id];
-      for (int ci = 0; ci < ncon; ci++) {
+      _Pragma("unroll 1") for (int ci = 0; ci < ncon; ci++) {
         double* rec = W(con) + ci * CON_STRIDE; int* ii = con_ints(rec);
         if (ii[3] < 0) continue;
         if (m.geom_bodyid[ii[0]] != b && m.geom_bodyid[ii[1]] != b) continue;
@@ -1372,7 +1433,7 @@ __device__ void sensors(const Ctx& c, int stage, int ncon) {
 // integration
 // ------------------------------------------------------------------------------------------------
 // qpos <- integrate(qpos, a*vel, h)
-__device__ void integrate_pos(const Ctx& c, double* qpos, const double* vel, double a, double h) {
+__device__ __forceinline__ void integrate_pos(const Ctx& c, double* qpos, const double* vel, double a, double h) {
   const DevModel& m = c.m; int lane = c.lane;
   FOR_LANES(j, m.njnt) {
     int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j], t = m.jnt_type[j];
@@ -1386,7 +1447,7 @@ __device__ void integrate_pos(const Ctx& c, double* qpos, const double* vel, dou
   __syncwarp();
 }
 
-__device__ void advance_act(const Ctx& c, double* act, const double* actdot, double scale, double h) {
+__device__ __forceinline__ void advance_act(const Ctx& c, double* act, const double* actdot, double scale, double h) {
   const DevModel& m = c.m; int lane = c.lane;
   FOR_LANES(a, m.nu) {
     int aa = m.actuator_actadr[a];
@@ -1400,15 +1461,13 @@ __device__ void advance_act(const Ctx& c, double* act, const double* actdot, dou
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-struct StepState { int ncon, nefc, niter; int warn[BMJ_NWARNING]; };
-
-__device__ bool check_bad(const Ctx& c, const double* v, int n) {
+__device__ __forceinline__ bool check_bad(const Ctx& c, const double* v, int n) {
   int lane = c.lane; int badf = 0;
   FOR_LANES(i, n) if (bad_value(v[i])) badf = 1;
   return __any_sync(FULL, badf);
 }
 
-__device__ void reset_state(const Ctx& c, double* time) {
+__device__ __forceinline__ void reset_state(const Ctx& c, double* time) {
   const DevModel& m = c.m; int lane = c.lane;
   FOR_LANES(i, m.nq) W(qpos)[i] = m.qpos0[i];
   FOR_LANES(i, m.nv) { W(qvel)[i] = 0; W(qaccws)[i] = 0; }
@@ -1417,44 +1476,15 @@ __device__ void reset_state(const Ctx& c, double* time) {
   __syncwarp();
 }
 
-// position + velocity stages on the workspace state
-__device__ void stage_posvel(const Ctx& c, StepState& st, bool with_constraints) {
-  kinematics(c);
-  com_pos(c);
-  crb_and_factor(c);
-  st.ncon = 0; st.nefc = 0;
-  if (with_constraints) {
-    int wfull = 0;
-    st.ncon = collision(c, &wfull);
-    if (wfull) st.warn[BMJ_WARN_CONTACTFULL]++;
-    int cfull = 0;
-    st.nefc = make_constraint(c, st.ncon, &cfull);
-    if (cfull) st.warn[BMJ_WARN_CNSTRFULL]++;
-  }
-  fwd_velocity(c);
-}
-
-// acceleration stage: qacc from the current pos/vel stage results
-__device__ void stage_acc(const Ctx& c, const b200mj_io& io, int env, StepState& st) {
-  const DevModel& m = c.m; int lane = c.lane;
-  fwd_actuation(c);
-  fwd_acceleration(c, io, env);
-  if (st.nefc == 0) {
-    FOR_LANES(i, m.nv) { W(qacc)[i] = W(qaccs)[i]; W(qcon)[i] = 0; }
-    st.niter = 0;
-    __syncwarp();
-  } else st.niter = solve_newton(c, st.nefc);
-}
-
-__device__ void euler_step(const Ctx& c, double* time) {
+__device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv; double h = m.timestep;
   advance_act(c, W(act), W(actdot), 1.0, h);
   if (m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
-    for (int j = lane; j < nv; j += 32) for (int i = 0; i < nv; i++) W(H)[i * ld + j] = W(M)[i * ld + j] + (i == j ? h * m.dof_damping[i] : 0.0);
+    _Pragma("unroll 1") for (int j = lane; j < nv; j += 32) _Pragma("unroll 1") for (int i = j; i < nv; i++) W(H)[i * ld + j] = W(M)[i * ld + j] + (i == j ? h * m.dof_damping[i] : 0.0);
     FOR_LANES(i, nv) W(tmpv)[i] = W(smooth)[i] + W(qcon)[i];
     __syncwarp();
-    chol_factor(W(H), W(H), nv, ld, lane);
-    chol_solve(W(H), W(tmpv), W(tmpv), nv, ld, lane);
+    chol_factor(W(H), W(H), W(dinv), nv, ld, lane);
+    chol_solve(W(H), W(dinv), W(tmpv), W(tmpv), nv, ld, lane);
     FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
   } else FOR_LANES(i, nv) W(qvel)[i] += h * W(qacc)[i];
   FOR_LANES(i, nv) W(qaccws)[i] = W(qacc)[i];
@@ -1463,15 +1493,23 @@ __device__ void euler_step(const Ctx& c, double* time) {
   *time += h;
 }
 
-__device__ void write_outputs(const Ctx& c, const b200mj_io& io, int env, const StepState& st, bool posvel, bool acc, bool want_sens) {
+__device__ __forceinline__ void write_outputs(const Ctx& c, const b200mj_io& io, int env, int ncon, int nefc, int niter,
+                                              bool posvel, bool acc, bool want_sens) {
   const DevModel& m = c.m; int lane = c.lane;
   size_t e = (size_t)env;
-#define OUT(ptr, src, n) if (io.ptr) { for (int i = lane; i < (n); i += 32) io.ptr[e * (n) + i] = (src)[i]; }
+#define OUT(ptr, src, n) if (io.ptr) { _Pragma("unroll 1") for (int i = lane; i < (n); i += 32) io.ptr[e * (n) + i] = (src)[i]; }
   if (posvel) {
     OUT(xpos, W(xpos), 3 * m.nbody) OUT(xquat, W(xquat), 4 * m.nbody) OUT(xmat, W(xmat), 9 * m.nbody)
-    OUT(xipos, W(xipos), 3 * m.nbody) OUT(geom_xpos, W(gxpos), 3 * m.ngeom) OUT(geom_xmat, W(gxmat), 9 * m.ngeom)
+    OUT(xipos, W(xipos), 3 * m.nbody)
     OUT(subtree_com, W(scom), 3 * m.nbody) OUT(subtree_linvel, W(slinvel), 3 * m.nbody) OUT(cvel, W(cvel), 6 * m.nbody)
     OUT(qfrc_bias, W(bias), m.nv) OUT(qfrc_passive, W(passive), m.nv)
+    if (io.geom_xpos || io.geom_xmat) {   // recomputed: the staged geom frames share storage with the Hessian
+      FOR_LANES(g, m.ngeom) {
+        double p[3], mm[9]; geom_frame(c, g, p, mm);
+        if (io.geom_xpos) for (int i = 0; i < 3; i++) io.geom_xpos[(e * m.ngeom + g) * 3 + i] = p[i];
+        if (io.geom_xmat) for (int i = 0; i < 9; i++) io.geom_xmat[(e * m.ngeom + g) * 9 + i] = mm[i];
+      }
+    }
     if (io.site_xpos || io.site_xmat) {
       FOR_LANES(s, m.nsite) {
         double p[3], mm[9]; site_frame(c, s, p, mm);
@@ -1479,10 +1517,10 @@ __device__ void write_outputs(const Ctx& c, const b200mj_io& io, int env, const 
         if (io.site_xmat) for (int i = 0; i < 9; i++) io.site_xmat[(e * m.nsite + s) * 9 + i] = mm[i];
       }
     }
-    if (io.qM) for (int i = lane; i < m.nv * m.nv; i += 32) io.qM[e * m.nv * m.nv + i] = W(M)[(i / m.nv) * m.ldv + (i % m.nv)];
-    if (io.ncon && lane == 0) io.ncon[e] = st.ncon;
-    if (io.nefc && lane == 0) io.nefc[e] = st.nefc;
-    FOR_LANES(k, st.ncon) {
+    if (io.qM) _Pragma("unroll 1") for (int i = lane; i < m.nv * m.nv; i += 32) io.qM[e * m.nv * m.nv + i] = W(M)[(i / m.nv) * m.ldv + (i % m.nv)];
+    if (io.ncon && lane == 0) io.ncon[e] = ncon;
+    if (io.nefc && lane == 0) io.nefc[e] = nefc;
+    FOR_LANES(k, ncon) {
       double* rec = W(con) + k * CON_STRIDE; int* ii = con_ints(rec);
       size_t o = e * m.nconmax + k;
       if (io.contact_geom) { io.contact_geom[2 * o] = ii[0]; io.contact_geom[2 * o + 1] = ii[1]; }
@@ -1495,8 +1533,8 @@ __device__ void write_outputs(const Ctx& c, const b200mj_io& io, int env, const 
   if (acc) {
     OUT(qacc, W(qacc), m.nv) OUT(qfrc_actuator, W(qfact), m.nv) OUT(actuator_force, W(actforce), m.nu)
     OUT(qfrc_constraint, W(qcon), m.nv)
-    if (io.efc_force) FOR_LANES(r, st.nefc) io.efc_force[e * m.njmax + r] = W(force)[r];
-    if (io.solver_niter && lane == 0) io.solver_niter[e] = st.niter;
+    if (io.efc_force) FOR_LANES(r, nefc) io.efc_force[e * m.njmax + r] = W(force)[r];
+    if (io.solver_niter && lane == 0) io.solver_niter[e] = niter;
   }
   if (want_sens) { OUT(sensordata, W(sens), m.nsensordata) }
 #undef OUT
@@ -1504,8 +1542,13 @@ __device__ void write_outputs(const Ctx& c, const b200mj_io& io, int env, const 
 
 enum { MODE_STEP = 0, MODE_FORWARD = 1 };
 
+// One launch = one warp per environment, `nstep` physics steps fused. Every stage function is inlined exactly
+// once into the single pass loop below (model / layout operands then come straight from the constant bank).
+//   pass kinds: [posvel + acc + integrate] x nstep  (RK4: 4 passes per step), then for the reference's legacy
+//   ordering one trailing [posvel] pass (= mj_step1 on the new state); MODE_FORWARD = one [posvel + acc] pass.
 extern "C" __global__ void __launch_bounds__(128)
-b200mj_step_kernel(DevModel m, Lay L, b200mj_io io, int batch, int nstep, int flags, int mode, int extra_disable) {
+b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ b200mj_io io,
+                   int batch, int nstep, int flags, int mode, int extra_disable) {
   extern __shared__ double smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -1519,88 +1562,103 @@ b200mj_step_kernel(DevModel m, Lay L, b200mj_io io, int batch, int nstep, int fl
   FOR_LANES(i, m.nu) W(ctrl)[i] = io.ctrl ? io.ctrl[e * m.nu + i] : 0.0;
   if (io.sensordata) FOR_LANES(i, m.nsensordata) W(sens)[i] = io.sensordata[e * m.nsensordata + i];
   double time = io.time ? io.time[e] : 0.0;
-  StepState st; st.ncon = st.nefc = st.niter = 0;
-  for (int i = 0; i < BMJ_NWARNING; i++) st.warn[i] = 0;
+  int w_contactfull = 0, w_cnstrfull = 0, w_badqpos = 0, w_badqvel = 0, w_badqacc = 0, w_badctrl = 0;
   __syncwarp();
-  bool want_sens = (flags & B200MJ_STEP_SENSORS) != 0;
-  bool has_acc_sens = m.acc_sensors != 0;
+  const bool want_sens = (flags & B200MJ_STEP_SENSORS) != 0;
+  const bool forward = mode == MODE_FORWARD;
+  const bool legacy = (flags & B200MJ_STEP_LEGACY) != 0;
+  const bool full_final = (flags & B200MJ_STEP_FULL_FINAL) != 0;
+  const bool rk4 = m.integrator == BMJ_INT_RK4;
   // ---- control check (mj_step / mj_step2 / mj_forward all start from a finite ctrl) ----
-  if (check_bad(c, W(ctrl), m.nu)) { st.warn[BMJ_WARN_BADCTRL]++; FOR_LANES(i, m.nu) W(ctrl)[i] = 0; __syncwarp(); }
+  if (check_bad(c, W(ctrl), m.nu)) { w_badctrl++; FOR_LANES(i, m.nu) W(ctrl)[i] = 0; __syncwarp(); }
 
-  if (mode == MODE_FORWARD) {
-    stage_posvel(c, st, true);
-    subtree_vel(c);
-    if (want_sens) { sensors(c, 1, st.ncon); sensors(c, 2, st.ncon); }
-    stage_acc(c, io, env, st);
-    if (want_sens) { if (has_acc_sens) rne_post_constraint(c, io, env, st.ncon); sensors(c, 3, st.ncon); }
-    write_outputs(c, io, env, st, true, true, want_sens);
+  int step_idx = 0, sub = 0;             // sub: Runge-Kutta stage 0..3 (always 0 for Euler)
+  int r_ncon = 0, r_nefc = 0, r_niter = 0;   // reported statistics (first evaluation of a step)
+  while (true) {
+    const bool final_pass = !forward && step_idx >= nstep;      // trailing mj_step1 of the legacy ordering
+    if (final_pass && !legacy) break;
+    const bool last = forward || step_idx == nstep - 1;
+    if (!forward && sub == 0) {
+      if (check_bad(c, W(qpos), m.nq)) { w_badqpos++; reset_state(c, &time); }
+      if (check_bad(c, W(qvel), m.nv)) { w_badqvel++; reset_state(c, &time); }
+    }
+    // ---------------- position + velocity stage ----------------
+    kinematics(c);
+    com_pos(c);
+    crb_and_factor(c);
+    int ncon = 0, nefc = 0, niter = 0;
+    if (!final_pass || full_final) {
+      int wfull = 0, cfull = 0;
+      ncon = collision(c, &wfull);
+      nefc = make_constraint(c, ncon, &cfull);
+      w_contactfull += wfull; w_cnstrfull += cfull;
+    }
+    fwd_velocity(c);
+    const bool out_posvel = final_pass || forward || (!legacy && last && sub == 0);
+    if (out_posvel) subtree_vel(c);
+    // ---------------- acceleration stage ----------------
+    if (!final_pass) {
+      fwd_actuation(c);
+      fwd_acceleration(c, io, env);
+      if (nefc == 0) {
+        FOR_LANES(i, m.nv) { W(qacc)[i] = W(qaccs)[i]; W(qcon)[i] = 0; }
+        __syncwarp();
+      } else niter = solve_newton(c, nefc);
+    }
+    if (sub == 0) { r_ncon = ncon; r_nefc = nefc; if (!final_pass) r_niter = niter; }
+    const bool out_acc = !final_pass && sub == 0 && last;
+    const int smask = want_sens ? ((out_posvel ? 3 : 0) | (out_acc ? 4 : 0)) : 0;
+    if ((smask & 4) && m.acc_sensors) rne_post_constraint(c, io, env, ncon);
+    if (smask) sensors(c, smask, ncon);
+    if (out_posvel || out_acc) write_outputs(c, io, env, r_ncon, r_nefc, r_niter, out_posvel, out_acc, want_sens && out_posvel);
+    if (final_pass || forward) break;
+    // ---------------- integration ----------------
+    if (sub == 0 && check_bad(c, W(qacc), m.nv)) { w_badqacc++; reset_state(c, &time); step_idx++; continue; }
+    if (!rk4) { euler_step(c, &time); step_idx++; }
+    else {
+      // classic RK4 over (qpos, qvel, act): stage `sub` has just produced F_sub = (qvel, qacc, act_dot)
+      const int nq = m.nq, nv = m.nv, na = m.na; const double h = m.timestep;
+      double* X0q = W(rk); double* X0v = X0q + nq; double* X0a = X0v + nv;
+      double* accv = X0a + na; double* acca = accv + nv; double* accd = acca + nv;
+      const double Bw = (sub == 0 || sub == 3) ? 1.0 / 6 : 1.0 / 3;
+      if (sub == 0) {
+        FOR_LANES(i, nq) X0q[i] = W(qpos)[i];
+        FOR_LANES(i, nv) { X0v[i] = W(qvel)[i]; accv[i] = 0; acca[i] = 0; }
+        FOR_LANES(i, na) { X0a[i] = W(act)[i]; accd[i] = 0; }
+      }
+      FOR_LANES(i, nv) { accv[i] += Bw * W(qvel)[i]; acca[i] += Bw * W(qacc)[i]; }
+      FOR_LANES(i, na) accd[i] += Bw * W(actdot)[i];
+      __syncwarp();
+      const bool fin = sub == 3;
+      const double a = fin ? 1.0 : (sub == 2 ? 1.0 : 0.5);
+      FOR_LANES(i, nq) W(qpos)[i] = X0q[i];
+      FOR_LANES(i, na) W(act)[i] = X0a[i];
+      __syncwarp();
+      integrate_pos(c, W(qpos), fin ? accv : W(qvel), a, h);      // stage velocity, or the weighted sum at the end
+      advance_act(c, W(act), fin ? accd : W(actdot), a, h);
+      FOR_LANES(i, nv) { W(qvel)[i] = X0v[i] + h * (a * (fin ? acca[i] : W(qacc)[i])); if (fin) W(qaccws)[i] = W(qacc)[i]; }
+      __syncwarp();
+      if (fin) { time += h; sub = 0; step_idx++; } else sub++;
+    }
+  }
+  if (forward) {
     FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];   // quaternions were normalised in place
   } else {
-    bool legacy = (flags & B200MJ_STEP_LEGACY) != 0;
-    for (int s = 0; s < nstep; s++) {
-      bool last = (s == nstep - 1);
-      if (check_bad(c, W(qpos), m.nq)) { st.warn[BMJ_WARN_BADQPOS]++; reset_state(c, &time); }
-      if (check_bad(c, W(qvel), m.nv)) { st.warn[BMJ_WARN_BADQVEL]++; reset_state(c, &time); }
-      stage_posvel(c, st, true);
-      bool sens_now = want_sens && last;
-      if (!legacy && sens_now) { subtree_vel(c); sensors(c, 1, st.ncon); sensors(c, 2, st.ncon); }
-      stage_acc(c, io, env, st);
-      if (sens_now) { if (has_acc_sens) rne_post_constraint(c, io, env, st.ncon); sensors(c, 3, st.ncon); }
-      if (last) write_outputs(c, io, env, st, !legacy, true, false);
-      if (check_bad(c, W(qacc), m.nv)) { st.warn[BMJ_WARN_BADQACC]++; reset_state(c, &time); continue; }
-      if (m.integrator == BMJ_INT_RK4) {
-        // classic RK4 over (qpos, qvel, act); F0 is the evaluation just made
-        int nq = m.nq, nv = m.nv, na = m.na; double h = m.timestep;
-        double* X0q = W(rk); double* X0v = X0q + nq; double* X0a = X0v + nv;
-        double* accv = X0a + na; double* acca = accv + nv; double* accd = acca + nv;
-        const double A[3] = {0.5, 0.5, 1.0}, B[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
-        FOR_LANES(i, nq) X0q[i] = W(qpos)[i];
-        FOR_LANES(i, nv) { X0v[i] = W(qvel)[i]; accv[i] = B[0] * W(qvel)[i]; acca[i] = B[0] * W(qacc)[i]; }
-        FOR_LANES(i, na) { X0a[i] = W(act)[i]; accd[i] = B[0] * W(actdot)[i]; }
-        __syncwarp();
-        StepState st2 = st;
-        for (int k = 1; k < 4; k++) {
-          double a = A[k - 1];
-          FOR_LANES(i, nq) W(qpos)[i] = X0q[i];
-          __syncwarp();
-          integrate_pos(c, W(qpos), W(qvel), a, h);            // uses stage k-1 velocity
-          FOR_LANES(i, nv) W(qvel)[i] = X0v[i] + h * (a * W(qacc)[i]);
-          FOR_LANES(i, na) W(act)[i] = X0a[i] + h * (a * W(actdot)[i]);
-          __syncwarp();
-          stage_posvel(c, st2, true);
-          stage_acc(c, io, env, st2);
-          FOR_LANES(i, nv) { accv[i] += B[k] * W(qvel)[i]; acca[i] += B[k] * W(qacc)[i]; }
-          FOR_LANES(i, na) accd[i] += B[k] * W(actdot)[i];
-          __syncwarp();
-        }
-        FOR_LANES(i, nq) W(qpos)[i] = X0q[i];
-        FOR_LANES(i, na) W(act)[i] = X0a[i];
-        __syncwarp();
-        advance_act(c, W(act), accd, 1.0, h);
-        FOR_LANES(i, nv) { W(qvel)[i] = X0v[i] + h * acca[i]; W(qaccws)[i] = W(qacc)[i]; }
-        __syncwarp();
-        integrate_pos(c, W(qpos), accv, 1.0, h);
-        time += h;
-      } else euler_step(c, &time);
-    }
-    if (legacy) {
-      // trailing mj_step1: position / velocity dependent fields of the NEW state
-      if (check_bad(c, W(qpos), m.nq)) { st.warn[BMJ_WARN_BADQPOS]++; reset_state(c, &time); }
-      if (check_bad(c, W(qvel), m.nv)) { st.warn[BMJ_WARN_BADQVEL]++; reset_state(c, &time); }
-      stage_posvel(c, st, (flags & B200MJ_STEP_FULL_FINAL) != 0);
-      subtree_vel(c);
-      if (want_sens) { sensors(c, 1, st.ncon); sensors(c, 2, st.ncon); }
-      write_outputs(c, io, env, st, true, false, want_sens);
-    } else if (want_sens) {
-      FOR_LANES(i, m.nsensordata) io.sensordata[e * m.nsensordata + i] = W(sens)[i];
-    }
-    // ---- store state ----
+    if (!legacy && want_sens) { FOR_LANES(i, m.nsensordata) if (io.sensordata) io.sensordata[e * m.nsensordata + i] = W(sens)[i]; }
     FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];
     FOR_LANES(i, m.nv) { io.qvel[e * m.nv + i] = W(qvel)[i]; if (io.qacc_warmstart) io.qacc_warmstart[e * m.nv + i] = W(qaccws)[i]; }
     FOR_LANES(i, m.na) io.act[e * m.na + i] = W(act)[i];
     if (io.time && lane == 0) io.time[e] = time;
   }
-  if (io.warning && lane == 0) for (int i = 0; i < BMJ_NWARNING; i++) if (st.warn[i]) io.warning[e * BMJ_NWARNING + i] += st.warn[i];
+  if (io.warning && lane == 0) {
+    int* w = io.warning + e * BMJ_NWARNING;
+    if (w_contactfull) w[BMJ_WARN_CONTACTFULL] += w_contactfull;
+    if (w_cnstrfull) w[BMJ_WARN_CNSTRFULL] += w_cnstrfull;
+    if (w_badqpos) w[BMJ_WARN_BADQPOS] += w_badqpos;
+    if (w_badqvel) w[BMJ_WARN_BADQVEL] += w_badqvel;
+    if (w_badqacc) w[BMJ_WARN_BADQACC] += w_badqacc;
+    if (w_badctrl) w[BMJ_WARN_BADCTRL] += w_badctrl;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1615,14 +1673,20 @@ static void build_layout(b200mj_model* M) {
   int nv = m.nv, nb = m.nbody, ld = m.ldv, nj = m.njmax;
   L.qpos = take(m.nq); L.qvel = take(nv); L.act = take(m.na); L.ctrl = take(m.nu); L.qaccws = take(nv); L.actdot = take(m.na);
   L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb); L.xipos = take(3 * nb);
-  L.xanchor = take(3 * m.njnt); L.xaxis = take(3 * m.njnt); L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom);
   L.scom = take(3 * nb); L.slinvel = take(3 * nb);
-  L.cinert = take(10 * nb); L.crb = take(10 * nb); L.cdof = take(6 * nv); L.cdofdot = take(6 * nv);
-  L.cvel = take(6 * nb); L.cacc = take(6 * nb); L.cfrc = take(6 * nb); L.cfrcext = take(m.acc_sensors ? 6 * nb : 0);
+  L.cinert = take(10 * nb); L.cdof = take(6 * nv); L.cdofdot = take(6 * nv);
+  L.cvel = take(6 * nb); L.cfrcext = take(m.acc_sensors ? 6 * nb : 0);
+  // Position/velocity-stage temporaries that are dead once the acceleration stage starts share their storage
+  // with the Newton Hessian / Cholesky buffer H (lifetimes: DESIGN.md "workspace").
+  int h0 = o;
+  L.crb = take(10 * nb); L.cacc = take(6 * nb); L.cfrc = take(6 * nb);
+  L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom); L.xanchor = take(3 * m.njnt); L.xaxis = take(3 * m.njnt);
+  if (o - h0 < nv * ld) take(nv * ld - (o - h0));
+  L.H = h0;
   L.tenlen = take(m.ntendon); L.tenJ = take(m.ntendon * ld); L.actforce = take(m.nu);
-  L.M = take(nv * ld); L.LM = take(nv * ld); L.H = take(nv * ld);
-  L.J = take(nj * ld); L.efcD = take(nj); L.efcSD = take(nj); L.aref = take(nj); L.jar = take(nj); L.jv = take(nj);
-  L.force = take(nj); L.eqflag = take((nj + 1) / 2);
+  L.M = take(nv * ld); L.dinv = take(nv);
+  L.J = take((m.npair > 0 && nj * ld < STAGE_DOUBLES) ? STAGE_DOUBLES : nj * ld); L.efcD = take(nj); L.efcSD = take(nj); L.aref = take(nj); L.jar = take(nj); L.jv = take(nj);
+  L.force = take(nj); L.eqflag = take((nj + 1) / 2); L.actlist = take((nj + 1) / 2);
   L.bias = take(nv); L.passive = take(nv); L.qfact = take(nv); L.smooth = take(nv); L.qaccs = take(nv); L.qacc = take(nv);
   L.qcon = take(nv); L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv); L.tmpv = take(nv);
   L.con = take(m.nconmax * CON_STRIDE);
@@ -1630,11 +1694,19 @@ static void build_layout(b200mj_model* M) {
   L.sens = take(m.nsensordata);
   L.total = o;
   M->smem_per_env = (size_t)o * sizeof(double);
-  size_t budget = 227 * 1024;
-  int epb = (int)(budget / (M->smem_per_env ? M->smem_per_env : 1));
-  if (epb > 4) epb = 4;
-  if (epb < 1) epb = 0;
-  M->envs_per_block = epb;
+  // environments (= warps) per CTA: maximise resident warps per SM given 228 KB/SM, 1 KB reserved per CTA,
+  // 227 KB max per CTA; prefer small CTAs (finer-grained refill when environments finish at different times)
+  int best = 0, best_warps = 0;
+  for (int epb = 1; epb <= 4; epb++) {
+    size_t per_cta = M->smem_per_env * epb;
+    if (per_cta > 227 * 1024) break;
+    int ctas = (int)((228 * 1024) / (per_cta + 1024));
+    if (ctas > 32) ctas = 32;
+    int warps = ctas * epb;
+    if (warps > 48) warps = 48;   // register file: 128 regs/thread -> 16 warps... (64K regs / (128*32)); capped below
+    if (warps > best_warps) { best_warps = warps; best = epb; }
+  }
+  M->envs_per_block = best;
 }
 
 extern "C" {
@@ -1734,6 +1806,7 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
   int epb = M->envs_per_block;
   int grid = (batch + epb - 1) / epb;
   size_t smem = M->smem_per_env * epb;
+  if (const char* pad = getenv("B200MJ_EXTRA_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
   b200mj_step_kernel<<<grid, 32 * epb, smem, (cudaStream_t)stream>>>(M->dm, M->lay, *io, batch, nstep, flags, mode, extra);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -5;

@@ -61,7 +61,8 @@ class BatchedPhysics:
                  ('contact_efc_address', lambda m: (m.nconmax,)), ('nefc', lambda m: ()),
                  ('solver_niter', lambda m: ()), ('warning', lambda m: (8,)))
 
-  def __init__(self, model, batch=1, device=None, outputs='all', sensors=True, full_final=True):
+  def __init__(self, model, batch=1, device=None, outputs='all', sensors=True, full_final=True, nconmax=None,
+               njmax=None):
     """Args:
       model: `dm_control_b200.model.Model`.
       batch: number of environments B.
@@ -70,10 +71,15 @@ class BatchedPhysics:
         shared memory only — the observation-contract idea of SURVEY.md Appendix B).
       sensors: evaluate sensors (mj_sensorPos/Vel/Acc) inside the step.
       full_final: the trailing step1 also runs collision + constraint assembly (needed for `data.ncon`/contacts).
+      nconmax, njmax: per-environment contact / constraint-row capacities (MJCF <size nconmax njmax>); they size
+        the shared-memory workspace, hence occupancy. Overflow raises mjWARN_CONTACTFULL / mjWARN_CNSTRFULL.
     """
     if not torch.cuda.is_available():
       raise _lib.EngineError('BatchedPhysics needs a CUDA device (B200); there is no CPU fallback.')
     self._L = _lib.load()
+    if nconmax is not None or njmax is not None:
+      model = model.copy()
+      model.set_capacity(nconmax, njmax)
     self.model = model
     self.batch = int(batch)
     self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')

@@ -52,10 +52,10 @@ def run(name, B, ncontrol, nsub, seed=0):
   print(f'{name}: B={B} steps={ncontrol}x{nsub} rel-err qpos {worst_q:.2e} qvel {worst_v:.2e}  ncon-mismatch {ncon_bad} pair-mismatch {pair_bad} first>1e-5 at {first_bad} warnings {warn.tolist()} ws_bytes {phys.workspace_bytes()} epb {phys.envs_per_block()}', flush=True)
   return max(worst_q, worst_v)
 
-def bench(name, B, nsub, iters=20):
+def bench(name, B, nsub, iters=20, **kw):
   model = tm.load(name)
   q0, v0 = tm.initial_states(model, name, B, 0)
-  phys = BatchedPhysics(model, batch=B, outputs=('xpos', 'xmat', 'subtree_com', 'sensordata'), full_final=False)
+  phys = BatchedPhysics(model, batch=B, outputs=('xpos', 'xmat', 'subtree_com', 'sensordata', 'ncon', 'nefc', 'solver_niter'), full_final=True, **kw)
   phys.check_errors = False
   phys.data.qpos.copy_(torch.as_tensor(q0)); phys.data.qvel.copy_(torch.as_tensor(v0)); phys.forward()
   g = torch.Generator(device='cuda').manual_seed(0)
@@ -67,6 +67,12 @@ def bench(name, B, nsub, iters=20):
     phys.data.ctrl.uniform_(-1, 1, generator=g); phys.step(nsub)
   e.record(); torch.cuda.synchronize()
   ms = s.elapsed_time(e) / iters
+  mx_con, mx_efc = 0, 0
+  nit = []
+  for _ in range(10):
+    phys.data.ctrl.uniform_(-1, 1, generator=g); phys.step(nsub)
+    mx_con = max(mx_con, int(phys.data.ncon.max())); mx_efc = max(mx_efc, int(phys.data.nefc.max())); nit.append(float(phys.data.solver_niter.float().mean()))
+  print(f'   stats {name} {kw}: max ncon {mx_con} max nefc {mx_efc} mean nefc {float(phys.data.nefc.float().mean()):.1f} mean niter {sum(nit)/len(nit):.2f}', flush=True)
   print(f'BENCH {name}: B={B} nsub={nsub} {ms:.3f} ms/env-step-batch -> {B / ms * 1e3:.0f} env-steps/s  ws {phys.workspace_bytes()} B epb {phys.envs_per_block()} warn {phys.data.warning.sum(0).tolist()}', flush=True)
 
 if __name__ == '__main__':
@@ -76,8 +82,8 @@ if __name__ == '__main__':
       run(name, B, nc, nsub)
     except Exception as ex:
       import traceback; traceback.print_exc()
-  for name, B, nsub in (('cheetah', 4096, 1), ('humanoid', 8192, 5)):
+  for name, B, nsub, kw in (('cheetah', 4096, 1, {}), ('humanoid', 8192, 5, {}), ('humanoid', 8192, 5, dict(nconmax=24, njmax=64)), ('humanoid', 8192, 5, dict(nconmax=16, njmax=48))):
     try:
-      bench(name, B, nsub)
+      bench(name, B, nsub, **kw)
     except Exception as ex:
       import traceback; traceback.print_exc()
