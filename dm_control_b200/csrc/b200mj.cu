@@ -165,31 +165,46 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
 }
 
 struct Ctx {
-  const DevModel& m; const Lay& L; double* ws; int lane; int disableflags;
-  __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df) {}
+  const DevModel& m; const Lay& L; double* ws; int lane; int disableflags; int sync_level;
+  __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df, int sl) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df), sync_level(sl) {}
 };
 #define W(name) (c.ws + c.L.name)
 
 // ------------------------------------------------------------------------------------------------
 // dense Cholesky in the workspace: A (n x n, row stride ld) -> lower factor Lm, same stride
 // ------------------------------------------------------------------------------------------------
+// dot product of two workspace rows with four independent accumulators (breaks the DFMA dependency chain)
+__device__ __forceinline__ double dot_rows(const double* a, const double* b, int n) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  int k = 0;
+  _Pragma("unroll 1") for (; k + 4 <= n; k += 4) { s0 += a[k] * b[k]; s1 += a[k + 1] * b[k + 1]; s2 += a[k + 2] * b[k + 2]; s3 += a[k + 3] * b[k + 3]; }
+  _Pragma("unroll 1") for (; k < n; k++) s0 += a[k] * b[k];
+  return (s0 + s1) + (s2 + s3);
+}
+
 __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* dinv, int n, int ld, int lane) {
   // left-looking, one row (two when n > 32) per lane; the pivot travels by shuffle, so one sync per column.
   // dinv[j] = 1 / L[j][j] is kept so that neither the factor nor the triangular solves divide.
+  if (n <= 32) {
+    const double* Li = Lm + lane * ld;
+    _Pragma("unroll 1") for (int j = 0; j < n; j++) {
+      double t = 0;
+      if (lane >= j && lane < n) t = A[lane * ld + j] - dot_rows(Li, Lm + j * ld, j);
+      double piv = __shfl_sync(FULL, t, j);
+      if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+      double inv = rsqrt(piv);
+      if (lane == j) { Lm[j * ld + j] = piv * inv; dinv[j] = inv; }
+      else if (lane > j && lane < n) Lm[lane * ld + j] = t * inv;
+      __syncwarp();
+    }
+    return;
+  }
   _Pragma("unroll 1") for (int j = 0; j < n; j++) {
     double t0 = 0, t1 = 0;
     int i0 = lane, i1 = lane + 32;
     const double* Lj = Lm + j * ld;
-    if (i0 >= j && i0 < n) {
-      t0 = A[i0 * ld + j];
-      const double* Li = Lm + i0 * ld;
-      for (int k = 0; k < j; k++) t0 -= Li[k] * Lj[k];
-    }
-    if (i1 >= j && i1 < n) {
-      t1 = A[i1 * ld + j];
-      const double* Li = Lm + i1 * ld;
-      for (int k = 0; k < j; k++) t1 -= Li[k] * Lj[k];
-    }
+    if (i0 >= j && i0 < n) t0 = A[i0 * ld + j] - dot_rows(Lm + i0 * ld, Lj, j);
+    if (i1 >= j && i1 < n) t1 = A[i1 * ld + j] - dot_rows(Lm + i1 * ld, Lj, j);
     double piv = __shfl_sync(FULL, j < 32 ? t0 : t1, j & 31);
     if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
     double inv = rsqrt(piv);
@@ -202,6 +217,22 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
 
 // solve (L L^T) x = b; b, x are workspace vectors (may alias); n <= 64
 __device__ __noinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int ld, int lane) {
+  if (n <= 32) {
+    double xi = lane < n ? b[lane] : 0.0;
+    const double* Li = Lm + lane * ld;
+    _Pragma("unroll 1") for (int j = 0; j < n; j++) {          // forward: L y = b
+      double yj = __shfl_sync(FULL, xi, j) * dinv[j];
+      if (lane == j) xi = yj; else if (lane > j && lane < n) xi -= Li[j] * yj;
+    }
+    _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {      // backward: L^T x = y
+      double yj = __shfl_sync(FULL, xi, j) * dinv[j];
+      if (lane == j) xi = yj; else if (lane < j) xi -= Lm[j * ld + lane] * yj;
+    }
+    __syncwarp();
+    if (lane < n) x[lane] = xi;
+    __syncwarp();
+    return;
+  }
   double x0 = lane < n ? b[lane] : 0.0, x1 = lane + 32 < n ? b[lane + 32] : 0.0;
   _Pragma("unroll 1") for (int j = 0; j < n; j++) {
     double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
@@ -209,7 +240,7 @@ __device__ __noinline__ void chol_solve(const double* Lm, const double* dinv, co
     if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= Lm[lane * ld + j] * yj; if (lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
     else { if (lane + 32 == j) x1 = yj; else if (lane + 32 > j && lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
   }
-  for (int j = n - 1; j >= 0; j--) {
+  _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {
     double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
     double yj = v * dinv[j];
     if (j < 32) { if (lane == j) x0 = yj; else if (lane < j) x0 -= Lm[j * ld + lane] * yj; }
@@ -1076,8 +1107,8 @@ struct Primal { double cost, gauss; int nact, changed; };
 // Ma = M qacc ; jar = J qacc - aref
 __device__ __forceinline__ void compute_Ma_jar(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
-  FOR_LANES(i, nv) { double s = 0; const double* Mi = W(M) + i * ld; _Pragma("unroll 1") for (int j = 0; j < nv; j++) s += Mi[j] * W(qacc)[j]; W(Ma)[i] = s; }
-  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; _Pragma("unroll 1") for (int i = 0; i < nv; i++) s += Jr[i] * W(qacc)[i]; W(jar)[r] = s - W(aref)[r]; }
+  FOR_LANES(i, nv) W(Ma)[i] = dot_rows(W(M) + i * ld, W(qacc), nv);
+  FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * ld, W(qacc), nv) - W(aref)[r];
   __syncwarp();
 }
 
@@ -1177,12 +1208,11 @@ __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Prim
   double gtol = m.tolerance * m.ls_tolerance * snorm * (m.meaninertia * max(1, nv));
   double g1 = 0, g2 = 0;
   FOR_LANES(i, nv) {
-    double s = 0; const double* Mi = W(M) + i * ld;
-    _Pragma("unroll 1") for (int j = 0; j < nv; j++) s += Mi[j] * W(search)[j];
+    double s = dot_rows(W(M) + i * ld, W(search), nv);
     W(Mv)[i] = s;
     g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
   }
-  FOR_LANES(r, nefc) { double s = 0; const double* Jr = W(J) + r * ld; _Pragma("unroll 1") for (int i = 0; i < nv; i++) s += Jr[i] * W(search)[i]; W(jv)[r] = s; }
+  FOR_LANES(r, nefc) W(jv)[r] = dot_rows(W(J) + r * ld, W(search), nv);
   double qg[3] = {pr.gauss, warp_sum(g1), warp_sum(g2)};
   __syncwarp();
   double d1, d2;
@@ -1205,42 +1235,61 @@ __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Prim
   return best;
 }
 
+// CTA-wide phase alignment: all warps of a CTA run the same code region at the same time so that instruction
+// lines are fetched from L2 once per CTA, not once per warp (the pass footprint is ~5x the 32 KB L1.5 I-cache).
+// level 1: coarse points (pass start, before / after the solver); 2: every stage boundary; 3: also every Newton trip
+#define PHASE_SYNC(level) do { if (c.sync_level >= (level)) __syncthreads(); } while (0)
+
 __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
-  Primal pr;
-  // start point: the warm start if it has lower cost than the unconstrained acceleration.
-  // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart again (when it won)
-  bool warm = !(c.disableflags & BMJ_DSBL_WARMSTART);
-  double cost_warm = 0;
-  for (int cand = warm ? 0 : 1; cand < 3; cand++) {
-    if (cand == 2 && !(warm && cost_warm < pr.cost)) break;
-    const double* src = (cand == 1) ? W(qaccs) : W(qaccws);
-    FOR_LANES(i, nv) W(qacc)[i] = src[i];
+  Primal pr; pr.cost = 0; pr.gauss = 0; pr.nact = 0; pr.changed = 1;
+  const bool active = nefc > 0;
+  if (active) {
+    // start point: the warm start if it has lower cost than the unconstrained acceleration.
+    // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart again (when it won)
+    bool warm = !(c.disableflags & BMJ_DSBL_WARMSTART);
+    double cost_warm = 0;
+    _Pragma("unroll 1") for (int cand = warm ? 0 : 1; cand < 3; cand++) {
+      if (cand == 2 && !(warm && cost_warm < pr.cost)) break;
+      const double* src = (cand == 1) ? W(qaccs) : W(qaccws);
+      FOR_LANES(i, nv) W(qacc)[i] = src[i];
+      __syncwarp();
+      compute_Ma_jar(c, nefc);
+      pr = constraint_update(c, nefc);
+      if (cand == 0) cost_warm = pr.cost;
+    }
+  } else {
+    FOR_LANES(i, nv) { W(qacc)[i] = W(qaccs)[i]; W(qcon)[i] = 0; }
     __syncwarp();
-    compute_Ma_jar(c, nefc);
-    pr = constraint_update(c, nefc);
-    if (cand == 0) cost_warm = pr.cost;
   }
   double scale = 1 / (m.meaninertia * max(1, nv));
   int iter = 0;
-  bool refactor = true;
+  bool refactor = true, done = !active;
   double oldcost = 0;
   while (true) {
-    double gnorm = newton_direction(c, nefc, pr.nact, refactor);
-    if (iter > 0) {
-      double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
-      if (improvement < m.tolerance || gradient < m.tolerance) break;
+    // every warp of the CTA takes the same number of trips: finished environments idle at the barrier
+    if (c.sync_level >= 3) { if (!__syncthreads_or(!done)) break; } else if (done) break;
+    if (!done) {
+      double gnorm = newton_direction(c, nefc, pr.nact, refactor);
+      bool stop = false;
+      if (iter > 0) {
+        double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
+        if (improvement < m.tolerance || gradient < m.tolerance) stop = true;
+      }
+      if (iter >= m.iterations) stop = true;
+      double alpha = 0;
+      if (!stop) { alpha = line_search(c, nefc, pr); if (alpha == 0) stop = true; }
+      if (stop) done = true;
+      else {
+        FOR_LANES(i, nv) { W(qacc)[i] += alpha * W(search)[i]; W(Ma)[i] += alpha * W(Mv)[i]; }
+        FOR_LANES(r, nefc) W(jar)[r] += alpha * W(jv)[r];
+        __syncwarp();
+        oldcost = pr.cost;
+        pr = constraint_update(c, nefc);
+        refactor = pr.changed != 0;
+        iter++;
+      }
     }
-    if (iter >= m.iterations) break;
-    double alpha = line_search(c, nefc, pr);
-    if (alpha == 0) break;
-    FOR_LANES(i, nv) { W(qacc)[i] += alpha * W(search)[i]; W(Ma)[i] += alpha * W(Mv)[i]; }
-    FOR_LANES(r, nefc) W(jar)[r] += alpha * W(jv)[r];
-    __syncwarp();
-    oldcost = pr.cost;
-    pr = constraint_update(c, nefc);
-    refactor = pr.changed != 0;
-    iter++;
   }
   return iter;
 }
@@ -1546,14 +1595,17 @@ enum { MODE_STEP = 0, MODE_FORWARD = 1 };
 // once into the single pass loop below (model / layout operands then come straight from the constant bank).
 //   pass kinds: [posvel + acc + integrate] x nstep  (RK4: 4 passes per step), then for the reference's legacy
 //   ordering one trailing [posvel] pass (= mj_step1 on the new state); MODE_FORWARD = one [posvel + acc] pass.
-extern "C" __global__ void __launch_bounds__(128)
+extern "C" __global__ void __launch_bounds__(256)
 b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ b200mj_io io,
-                   int batch, int nstep, int flags, int mode, int extra_disable) {
+                   int batch, int nstep, int flags, int mode, int extra_disable, int sync_level) {
   extern __shared__ double smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (env >= batch) return;
-  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable);
+  // warps past the end of the batch shadow the last environment (same control flow => same barrier count)
+  // and never store
+  const bool live = env < batch;
+  if (!live) env = batch - 1;
+  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, blockDim.x > 32 ? sync_level : 0);
   size_t e = (size_t)env;
   // ---- load state ----
   FOR_LANES(i, m.nq) W(qpos)[i] = io.qpos[e * m.nq + i];
@@ -1583,36 +1635,42 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
       if (check_bad(c, W(qvel), m.nv)) { w_badqvel++; reset_state(c, &time); }
     }
     // ---------------- position + velocity stage ----------------
+    PHASE_SYNC(1);
     kinematics(c);
+    PHASE_SYNC(2);
     com_pos(c);
     crb_and_factor(c);
     int ncon = 0, nefc = 0, niter = 0;
     if (!final_pass || full_final) {
       int wfull = 0, cfull = 0;
+      PHASE_SYNC(2);
       ncon = collision(c, &wfull);
+      PHASE_SYNC(2);
       nefc = make_constraint(c, ncon, &cfull);
       w_contactfull += wfull; w_cnstrfull += cfull;
     }
+    PHASE_SYNC(2);
     fwd_velocity(c);
     const bool out_posvel = final_pass || forward || (!legacy && last && sub == 0);
     if (out_posvel) subtree_vel(c);
     // ---------------- acceleration stage ----------------
     if (!final_pass) {
+      PHASE_SYNC(2);
       fwd_actuation(c);
       fwd_acceleration(c, io, env);
-      if (nefc == 0) {
-        FOR_LANES(i, m.nv) { W(qacc)[i] = W(qaccs)[i]; W(qcon)[i] = 0; }
-        __syncwarp();
-      } else niter = solve_newton(c, nefc);
+      PHASE_SYNC(1);
+      niter = solve_newton(c, nefc);
     }
     if (sub == 0) { r_ncon = ncon; r_nefc = nefc; if (!final_pass) r_niter = niter; }
     const bool out_acc = !final_pass && sub == 0 && last;
     const int smask = want_sens ? ((out_posvel ? 3 : 0) | (out_acc ? 4 : 0)) : 0;
+    PHASE_SYNC(1);
     if ((smask & 4) && m.acc_sensors) rne_post_constraint(c, io, env, ncon);
     if (smask) sensors(c, smask, ncon);
-    if (out_posvel || out_acc) write_outputs(c, io, env, r_ncon, r_nefc, r_niter, out_posvel, out_acc, want_sens && out_posvel);
+    if (live && (out_posvel || out_acc)) write_outputs(c, io, env, r_ncon, r_nefc, r_niter, out_posvel, out_acc, want_sens && out_posvel);
     if (final_pass || forward) break;
     // ---------------- integration ----------------
+    PHASE_SYNC(2);
     if (sub == 0 && check_bad(c, W(qacc), m.nv)) { w_badqacc++; reset_state(c, &time); step_idx++; continue; }
     if (!rk4) { euler_step(c, &time); step_idx++; }
     else {
@@ -1641,6 +1699,7 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
       if (fin) { time += h; sub = 0; step_idx++; } else sub++;
     }
   }
+  if (!live) return;
   if (forward) {
     FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];   // quaternions were normalised in place
   } else {
@@ -1694,18 +1753,11 @@ static void build_layout(b200mj_model* M) {
   L.sens = take(m.nsensordata);
   L.total = o;
   M->smem_per_env = (size_t)o * sizeof(double);
-  // environments (= warps) per CTA: maximise resident warps per SM given 228 KB/SM, 1 KB reserved per CTA,
-  // 227 KB max per CTA; prefer small CTAs (finer-grained refill when environments finish at different times)
-  int best = 0, best_warps = 0;
-  for (int epb = 1; epb <= 4; epb++) {
-    size_t per_cta = M->smem_per_env * epb;
-    if (per_cta > 227 * 1024) break;
-    int ctas = (int)((228 * 1024) / (per_cta + 1024));
-    if (ctas > 32) ctas = 32;
-    int warps = ctas * epb;
-    if (warps > 48) warps = 48;   // register file: 128 regs/thread -> 16 warps... (64K regs / (128*32)); capped below
-    if (warps > best_warps) { best_warps = warps; best = epb; }
-  }
+  // One CTA per SM holding as many environments (= warps) as the 227 KB of shared memory allow, at most 8: the
+  // warps of a CTA are phase-aligned with barriers and so share their instruction fetches.
+  int best = (int)((227 * 1024) / (M->smem_per_env ? M->smem_per_env : 1));
+  if (best > 8) best = 8;
+  if (const char* ev = getenv("B200MJ_ENVS_PER_BLOCK")) { int v = atoi(ev); if (v >= 1 && v <= best) best = v; }
   M->envs_per_block = best;
 }
 
@@ -1807,7 +1859,9 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
   int grid = (batch + epb - 1) / epb;
   size_t smem = M->smem_per_env * epb;
   if (const char* pad = getenv("B200MJ_EXTRA_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
-  b200mj_step_kernel<<<grid, 32 * epb, smem, (cudaStream_t)stream>>>(M->dm, M->lay, *io, batch, nstep, flags, mode, extra);
+  static int sync_level = -1;
+  if (sync_level < 0) { const char* sl = getenv("B200MJ_SYNC_LEVEL"); sync_level = sl ? atoi(sl) : 2; }
+  b200mj_step_kernel<<<grid, 32 * epb, smem, (cudaStream_t)stream>>>(M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

@@ -18,8 +18,8 @@ torch.cuda.synchronize(); s = torch.cuda.Event(enable_timing=True); e = torch.cu
 for _ in range(10):
   phys.data.ctrl.uniform_(-1, 1, generator=g); phys.step(5)
 e.record(); torch.cuda.synchronize()
-print('pad', os.environ.get('B200MJ_EXTRA_SMEM'), 'ws', phys.workspace_bytes(), 'ms', s.elapsed_time(e)/10)
+print('sync', os.environ.get('B200MJ_SYNC_LEVEL'), 'envs/block', os.environ.get('B200MJ_ENVS_PER_BLOCK'), phys.envs_per_block(), 'ws', phys.workspace_bytes(), 'ms', s.elapsed_time(e)/10)
 '''
-for pad in (0, 6000, 16000, 35000, 75000, 180000):
-  env = dict(os.environ, B200MJ_EXTRA_SMEM=str(pad))
+for pad, sl in ((5, 0), (5, 1), (5, 2), (5, 3), (4, 1), (4, 2), (3, 1), (2, 1)):
+  env = dict(os.environ, B200MJ_ENVS_PER_BLOCK=str(pad), B200MJ_SYNC_LEVEL=str(sl))
   print(subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True).stdout.strip(), flush=True)
