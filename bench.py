@@ -71,45 +71,51 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def time_cpu(seconds_budget, warmup_steps, timed_steps, nenv_per_thread=8, threads=None):
-  """Times `control_step(5)` (legacy ordering, engine.py:147-162) of the scalar oracle over all host cores.
-
-  Each thread owns `nenv_per_thread` environments (ctypes releases the GIL inside the C call). Returns
-  (env_steps_per_s, cores, sample description, ms per env-step-batch-of-sample).
-  """
+def _cpu_worker(args):
+  """One host process: builds its environments, waits at the shared start time, rolls them out in C."""
+  t, nenv, warmup_steps, timed_steps, start_at = args
   import numpy as np
-  from concurrent.futures import ThreadPoolExecutor
   from dm_control_b200 import testing_models as tm
   from oracle import oracle as om
-  om.build()
-  threads = threads or os.cpu_count() or 1
   model = tm.load('humanoid')
-  nenv = threads * nenv_per_thread
-  q0, v0 = tm.initial_states(model, 'humanoid', nenv, 0)
+  q0, v0 = tm.initial_states(model, 'humanoid', nenv, 7000 + t)
   envs = []
   for e in range(nenv):
     o = om.OraclePhysics(model)
     o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward()
     envs.append(o)
-  rs = np.random.RandomState(1234)
+  tape = np.random.RandomState(100 + t).uniform(-1, 1, (warmup_steps + timed_steps, nenv, model.nu))
+  for j, o in enumerate(envs):
+    o.rollout(tape[:warmup_steps, j], NSUB)
+  while time.time() < start_at:
+    time.sleep(0.001)
+  t0 = time.time()
+  for j, o in enumerate(envs):
+    o.rollout(tape[warmup_steps:, j], NSUB)
+  return t0, time.time()
 
-  def run_chunk(args):
-    t, nsteps, seed = args
-    r = np.random.RandomState(seed)
-    for _ in range(nsteps):
-      for o in envs[t * nenv_per_thread:(t + 1) * nenv_per_thread]:
-        o.ctrl[:] = r.uniform(-1, 1, model.nu)
-        o.control_step(NSUB)
 
-  with ThreadPoolExecutor(threads) as ex:
-    list(ex.map(run_chunk, [(t, warmup_steps, 100 + t) for t in range(threads)]))
-    t0 = time.perf_counter()
-    list(ex.map(run_chunk, [(t, timed_steps, 200 + t) for t in range(threads)]))
-    dt = time.perf_counter() - t0
-  del rs
+def time_cpu(warmup_steps=5, timed_steps=120, nenv_per_proc=4, procs=None):
+  """Times `control_step(5)` (legacy ordering, engine.py:147-162) of the scalar CPU oracle on all host cores.
+
+  One forked process per core, each owning `nenv_per_proc` environments and stepping them inside one C call;
+  all processes start their timed rollouts at the same wall-clock instant and the slowest sets the time.
+  Sized to ~10-30 s of CPU work in total. Returns (env_steps_per_s, cores, sample description, ms per env-step).
+  """
+  import multiprocessing as mp
+  from oracle import oracle as om
+  om.build()
+  procs = procs or os.cpu_count() or 1
+  ctx = mp.get_context('fork')
+  start_at = time.time() + 3.0 + 0.02 * procs          # leave time for every worker to build + warm up
+  with ctx.Pool(procs) as pool:
+    spans = pool.map(_cpu_worker, [(t, nenv_per_proc, warmup_steps, timed_steps, start_at) for t in range(procs)], chunksize=1)
+  dt = max(b for _, b in spans) - min(a for a, _ in spans)
+  nenv = procs * nenv_per_proc
   value = nenv * timed_steps / dt
-  sample = f'{nenv} envs ({nenv_per_thread}/thread x {threads} threads) x {timed_steps} env-steps after {warmup_steps} warm-up, seeded humanoid:run states, uniform(-1,1) actions'
-  return value, threads, sample, dt * 1e3 / timed_steps
+  sample = (f'{nenv} envs ({nenv_per_proc}/process x {procs} processes) x {timed_steps} env-steps after {warmup_steps} '
+            f'warm-up, seeded humanoid:run states, uniform(-1,1) actions')
+  return value, procs, sample, dt * 1e3 / timed_steps
 
 
 def run_reference(args):
@@ -117,7 +123,7 @@ def run_reference(args):
   if rank != 0:
     return
   steps = max(1, args.steps)
-  value, cores, sample, ms = time_cpu(None, max(3, args.warmup), steps * 4)
+  value, cores, sample, ms = time_cpu(max(3, min(args.warmup, 10)), max(40, steps * 6))
   line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
               ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
               config=dict(workload='suite.humanoid:run, 5 physics substeps per env-step, random actions',
@@ -253,7 +259,7 @@ def run_gpu(args):
       prof = json.load(open(pj))
     cpu = None
     if world == 1 and not args.no_cpu:
-      v, cores, sample, _ = time_cpu(None, 3, 12)
+      v, cores, sample, _ = time_cpu(5, 120)
       cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,

@@ -1245,16 +1245,29 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   Primal pr; pr.cost = 0; pr.gauss = 0; pr.nact = 0; pr.changed = 1;
   const bool active = nefc > 0;
   if (active) {
-    // start point: the warm start if it has lower cost than the unconstrained acceleration.
-    // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart again (when it won)
+    // start point: the warm start if it has lower cost than the unconstrained acceleration (MuJoCo's rule).
+    // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart restored (only when it won)
     bool warm = !(c.disableflags & BMJ_DSBL_WARMSTART);
     double cost_warm = 0;
     _Pragma("unroll 1") for (int cand = warm ? 0 : 1; cand < 3; cand++) {
-      if (cand == 2 && !(warm && cost_warm < pr.cost)) break;
-      const double* src = (cand == 1) ? W(qaccs) : W(qaccws);
-      FOR_LANES(i, nv) W(qacc)[i] = src[i];
-      __syncwarp();
-      compute_Ma_jar(c, nefc);
+      if (cand == 0) {
+        FOR_LANES(i, nv) W(qacc)[i] = W(qaccws)[i];
+        __syncwarp();
+        compute_Ma_jar(c, nefc);
+      } else if (cand == 1) {
+        // park the warm-start products (Mv / jv are free until the first line search); for the unconstrained
+        // candidate M qacc_smooth = qfrc_smooth by construction, so only J qacc_smooth is a product
+        FOR_LANES(i, nv) { W(Mv)[i] = W(Ma)[i]; W(qacc)[i] = W(qaccs)[i]; W(Ma)[i] = W(smooth)[i]; }
+        FOR_LANES(r, nefc) W(jv)[r] = W(jar)[r];
+        __syncwarp();
+        FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * m.ldv, W(qacc), nv) - W(aref)[r];
+        __syncwarp();
+      } else {
+        if (!(warm && cost_warm < pr.cost)) break;
+        FOR_LANES(i, nv) { W(qacc)[i] = W(qaccws)[i]; W(Ma)[i] = W(Mv)[i]; }
+        FOR_LANES(r, nefc) W(jar)[r] = W(jv)[r];
+        __syncwarp();
+      }
       pr = constraint_update(c, nefc);
       if (cand == 0) cost_warm = pr.cost;
     }
@@ -1860,7 +1873,7 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
   size_t smem = M->smem_per_env * epb;
   if (const char* pad = getenv("B200MJ_EXTRA_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
   static int sync_level = -1;
-  if (sync_level < 0) { const char* sl = getenv("B200MJ_SYNC_LEVEL"); sync_level = sl ? atoi(sl) : 2; }
+  if (sync_level < 0) { const char* sl = getenv("B200MJ_SYNC_LEVEL"); sync_level = sl ? atoi(sl) : 1; }
   b200mj_step_kernel<<<grid, 32 * epb, smem, (cudaStream_t)stream>>>(M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -5;

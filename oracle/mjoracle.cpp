@@ -840,7 +840,8 @@ static void make_constraint(const OModel* m, OData* d) {
     }
   }
   // ---- contacts -------------------------------------------------------------------------------
-  vec jp1(3 * nv), jp2(3 * nv), jr1(3 * nv), jr2(3 * nv), jf(6 * nv);
+  static thread_local vec jp1, jp2, jr1, jr2, jf;
+  jp1.resize(3 * nv); jp2.resize(3 * nv); jr1.resize(3 * nv); jr2.resize(3 * nv); jf.resize(6 * nv);
   for (int ci = 0; ci < d->ncon; ci++) {
     OContact* c = &d->contact[ci];
     c->efc_address = -1;
@@ -965,7 +966,8 @@ static void passive(const OModel* m, OData* d) {
 // recursive Newton-Euler: qfrc_bias (flg_acc=0) — gravity enters as base acceleration
 static void rne(const OModel* m, OData* d, real* result) {
   int nb = m->nbody, nv = m->nv;
-  vec loc_cacc(6 * nb, 0.0), loc_cfrc(6 * nb, 0.0);
+  static thread_local vec loc_cacc, loc_cfrc;
+  loc_cacc.assign(6 * nb, 0.0); loc_cfrc.assign(6 * nb, 0.0);
   if (!(m->disableflags & BMJ_DSBL_GRAVITY)) for (int i = 0; i < 3; i++) loc_cacc[3 + i] = -m->gravity[i];
   for (int b = 1; b < nb; b++) {
     int p = m->body_parentid[b];
@@ -1245,7 +1247,8 @@ static void fwd_acceleration(const OModel* m, OData* d) {
   int nv = m->nv;
   for (int i = 0; i < nv; i++) d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_applied[i] + d->qfrc_actuator[i];
   // Cartesian forces applied at body COMs
-  vec jp(3 * nv), jr(3 * nv);
+  static thread_local vec jp, jr;
+  jp.resize(3 * nv); jr.resize(3 * nv);
   for (int b = 1; b < m->nbody; b++) {
     const real* xf = &d->xfrc_applied[6 * b];
     bool any = false; for (int i = 0; i < 6; i++) if (xf[i] != 0) any = true;
@@ -1354,7 +1357,7 @@ static real line_search(PrimalCtx& c) {
 
 static void solve_newton(const OModel* m, OData* d) {
   int nv = m->nv, nefc = d->nefc;
-  PrimalCtx c; c.m = m; c.d = d; c.nv = nv; c.nefc = nefc;
+  static thread_local PrimalCtx c; c.m = m; c.d = d; c.nv = nv; c.nefc = nefc;
   c.jar.resize(nefc); c.Ma.resize(nv); c.grad.resize(nv); c.Mgrad.resize(nv); c.search.resize(nv); c.Mv.resize(nv);
   c.jv.resize(nefc); c.H.resize(nv * nv); c.LH.resize(nv * nv);
   auto compute_Ma_jar = [&]() {
@@ -1472,7 +1475,8 @@ static void euler(const OModel* m, OData* d) {
   bool damped = false;
   for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) damped = true;
   if (damped && !(m->disableflags & BMJ_DSBL_EULERDAMP)) {
-    vec A(d->M), rhs(nv), qacc(nv);
+    static thread_local vec A, rhs, qacc;
+    A = d->M; rhs.resize(nv); qacc.resize(nv);
     for (int i = 0; i < nv; i++) { A[i * nv + i] += h * m->dof_damping[i]; rhs[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i]; }
     chol_factor(d->Lh.data(), A.data(), nv);
     chol_solve(qacc.data(), d->Lh.data(), rhs.data(), nv);
@@ -1606,6 +1610,16 @@ void bmjo_control_step(void* mv, void* dv, int nstep) {
   if (m->integrator != BMJ_INT_RK4) { step2(m, d); for (int i = 1; i < nstep; i++) step(m, d); }
   else for (int i = 0; i < nstep; i++) step(m, d);
   step1(m, d);
+}
+
+// Rollout helper for the CPU baseline: `nsteps` control steps with a pre-generated action tape [nsteps, nu],
+// entirely in C so that Python threads only wait (ctypes drops the GIL for the whole call).
+void bmjo_rollout(void* mv, void* dv, const double* tape, int nsteps, int nsub) {
+  OModel* m = (OModel*)mv; OData* d = (OData*)dv;
+  for (int k = 0; k < nsteps; k++) {
+    for (int a = 0; a < m->nu; a++) d->ctrl[a] = tape[(size_t)k * m->nu + a];
+    bmjo_control_step(mv, dv, nsub);
+  }
 }
 
 }  // extern "C"

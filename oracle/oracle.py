@@ -41,6 +41,7 @@ def lib():
       getattr(L, f).argtypes = [vp, vp]
     L.bmjo_step.argtypes = [vp, vp, ctypes.c_int]
     L.bmjo_control_step.argtypes = [vp, vp, ctypes.c_int]
+    L.bmjo_rollout.argtypes = [vp, vp, dp, ctypes.c_int, ctypes.c_int]
     L.bmjo_set_disableflags.argtypes = [vp, ctypes.c_int]
     L.bmjo_get_disableflags.argtypes = [vp]
     L.bmjo_get_disableflags.restype = ctypes.c_int
@@ -182,6 +183,11 @@ class OraclePhysics:
   def control_step(self, nstep):
     """Reference legacy ordering: dm_control/mujoco/engine.py:147-162."""
     self._L.bmjo_control_step(self._m, self._d, nstep)
+
+  def rollout(self, tape, nsub):
+    """`len(tape)` control steps with actions tape[k] (C loop; the GIL is released for the whole call)."""
+    tape = np.ascontiguousarray(tape, dtype=np.float64)
+    self._L.bmjo_rollout(self._m, self._d, tape.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), tape.shape[0], nsub)
 
   def subtree_vel(self):
     self._L.bmjo_subtree_vel(self._m, self._d)
