@@ -164,7 +164,8 @@ def run_gpu(args):
   gen = torch.Generator(device=dev).manual_seed(1234 + rank)
   actions = torch.empty(BATCH, model.nu, dtype=torch.float64, device=dev)
   packed = torch.empty(BATCH, OBS_DIM + 2, dtype=torch.float64, device=dev)
-  gathered = [torch.empty_like(packed) for _ in range(world)] if (world > 1 and rank == 0) else None
+  from dm_control_b200 import sharding
+  gathered = torch.empty(BATCH * world, OBS_DIM + 2, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
   flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
 
   def pack(ts):
@@ -173,7 +174,8 @@ def run_gpu(args):
     packed[:, 34:37] = o['torso_vertical']; packed[:, 37:40] = o['com_velocity']; packed[:, 40:67] = o['velocity']
     packed[:, 67] = ts.reward; packed[:, 68] = ts.discount
     if world > 1:
-      dist.gather(packed, gathered, dst=0)     # NCCL over NVLink: observations/rewards to rank 0 (north_star)
+      # NCCL over NVLink: observations/rewards to rank 0, in environment order (north_star)
+      sharding.gather_to_rank0(packed, BATCH * world, out=gathered)
 
   def one_step():
     flush.fill_(0.0)                                   # L2 flush between timed iterations (inside the timed region)
@@ -235,7 +237,7 @@ def run_gpu(args):
     actions.copy_(act_host, non_blocking=True)                        # H2D
     pack(env.step(actions))
     if rank == 0 and world > 1:
-      out_host.copy_(torch.cat(gathered, 0), non_blocking=True)       # D2H of the gathered block
+      out_host.copy_(gathered, non_blocking=True)                     # D2H of the gathered block
     else:
       out_host[:BATCH].copy_(packed, non_blocking=True)               # D2H
     torch.cuda.current_stream().synchronize()                         # the user reads obs before the next action

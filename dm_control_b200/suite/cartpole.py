@@ -26,7 +26,7 @@ class Physics(BatchedPhysics):
     return self.data.xmat[:, 2:, 8]                       # xmat[2:, 'zz']
 
   def bounded_position(self):
-    poles = self.data.xmat[:, 2:, [8, 2]].reshape(self.batch, -1)   # xmat[2:, ['zz', 'xz']].ravel()
+    poles = torch.stack([self.data.xmat[:, 2:, 8], self.data.xmat[:, 2:, 2]], dim=2).reshape(self.batch, -1)   # xmat[2:, ['zz', 'xz']].ravel()
     return torch.cat([self.cart_position()[:, None], poles], dim=1)
 
 

@@ -24,8 +24,9 @@ class Physics(BatchedPhysics):
   def _ids(self):
     if not hasattr(self, '_hid'):
       n = self.model.names
+      limbs = [n['body'][s + l] for s in ('left_', 'right_') for l in ('hand', 'foot')]
       self._hid = dict(torso=n['body']['torso'], head=n['body']['head'],
-                       limbs=[n['body'][s + l] for s in ('left_', 'right_') for l in ('hand', 'foot')],
+                       limbs=torch.tensor(limbs, dtype=torch.int64, device=self.device),   # device-resident: no per-step H2D
                        linvel=int(self.model.sensor_adr[n['sensor']['torso_subtreelinvel']]))
     return self._hid
 
@@ -52,8 +53,8 @@ class Physics(BatchedPhysics):
     ids = self._ids()
     frame = self.data.xmat[:, ids['torso']].reshape(-1, 3, 3)
     torso_pos = self.data.xpos[:, ids['torso']]
-    rel = self.data.xpos[:, ids['limbs']] - torso_pos[:, None, :]          # [B, 4, 3]
-    return torch.einsum('bli,bij->blj', rel, frame).reshape(self.batch, 12)  # row-vector . frame (humanoid.py:120-129)
+    rel = self.data.xpos.index_select(1, ids['limbs']) - torso_pos[:, None, :]   # [B, 4, 3]
+    return torch.bmm(rel, frame).reshape(self.batch, 12)                   # row-vector . frame (humanoid.py:120-129)
 
 
 class Humanoid(base.Task):
@@ -96,10 +97,10 @@ class Humanoid(base.Task):
     small_control = rewards.tolerance(physics.control(), margin=1, value_at_margin=0, sigmoid='quadratic').mean(dim=1)
     small_control = (4 + small_control) / 5
     if self._move_speed == 0:
-      horizontal_velocity = physics.center_of_mass_velocity()[:, [0, 1]]
+      horizontal_velocity = physics.center_of_mass_velocity()[:, 0:2]
       dont_move = rewards.tolerance(horizontal_velocity, margin=2).mean(dim=1)
       return small_control * stand_reward * dont_move
-    com_velocity = physics.center_of_mass_velocity()[:, [0, 1]].norm(dim=1)
+    com_velocity = physics.center_of_mass_velocity()[:, 0:2].norm(dim=1)
     move = rewards.tolerance(com_velocity, bounds=(self._move_speed, float('inf')), margin=self._move_speed,
                              value_at_margin=0, sigmoid='linear')
     move = (5 * move + 1) / 6
