@@ -42,7 +42,7 @@ class ClockSampler:
        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
   def __init__(self, index):
-    self.index, self.rows, self.proc = index, [], None
+    self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
 
   def start(self):
     try:
@@ -54,16 +54,22 @@ class ClockSampler:
 
   def _read(self):
     for line in self.proc.stdout:
-      self.rows.append([x.strip() for x in line.split(',')])
+      self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+  def mark(self):
+    """Only samples that arrive after this instant are reported (the process is started before warm-up so that
+    its start-up cost — spawning nvidia-smi stalls the driver for tens of ms — stays out of the timed region)."""
+    self.t_mark = time.time()
 
   def stop(self):
     if self.proc is not None:
       self.proc.terminate()
     time.sleep(0.05)
-    sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-    mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+    rows = [r for t, r in self.rows if t >= self.t_mark] or [r for _, r in self.rows[-2:]]
+    sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
+    mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+    reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
     return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
                 samples=len(sm))
 
@@ -187,15 +193,17 @@ def run_gpu(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("B200_BENCH_NO_SAMPLER")) else None
+  if sampler:
+    sampler.start()
   # settle to the steady-state contact load the metric is quoted on (20 warm-up env-steps minimum)
   for _ in range(max(args.warmup, 3)):
     one_step()
   barrier()
 
   # ---- device-resident arm -------------------------------------------------------------------------------
-  sampler = ClockSampler(local) if rank == 0 else None
   if sampler:
-    sampler.start()
+    sampler.mark()
   launches0 = L.b200mj_launch_count()
   ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
   kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -292,7 +300,7 @@ def run_gpu(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
