@@ -63,7 +63,8 @@ def test_forward_fields_match_oracle(name, B, oracle_mod):
 
 
 @pytest.mark.parametrize('name,B,ncontrol,nsub', [('cartpole', 16, 60, 1), ('pendulum_free', 8, 50, 2),
-                                                   ('cheetah', 32, 100, 1), ('humanoid', 32, 20, 5)])
+                                                   ('cheetah', 32, 100, 1), ('humanoid', 32, 20, 5),
+                                                   ('quadruped', 16, 15, 4)])
 def test_rollout_matches_oracle(name, B, ncontrol, nsub, oracle_mod):
   """Fixed recorded action tape, legacy step ordering; compare every control step."""
   model, phys, oracles = _setup(name, B, 0, oracle_mod)

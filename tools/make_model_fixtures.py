@@ -43,7 +43,7 @@ def quadruped_walk_xml():
 def main():
   os.makedirs(OUT, exist_ok=True)
   caps = dict(cartpole=dict(nconmax=0, njmax=4), cheetah=dict(nconmax=16, njmax=80),
-              humanoid=dict(nconmax=24, njmax=64), quadruped=dict(nconmax=24, njmax=96))
+              humanoid=dict(nconmax=32, njmax=96), quadruped=dict(nconmax=24, njmax=96))
   for name in ('cartpole', 'cheetah', 'humanoid'):
     m = mc.compile_file(os.path.join(REF, name + '.xml'), **caps[name])
     m.save(os.path.join(OUT, name + '.npz'))
