@@ -37,41 +37,56 @@ def _peaks():
 
 
 class ClockSampler:
-  """nvidia-smi SM clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-  Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+  """SM clock + clocks-event (throttle) reasons sampled DURING the timed region.
 
-  def __init__(self, index):
-    self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
+  Samples are taken inline from the benchmark thread through NVML every few steps (0.15 ms per sample). A polling
+  child process (`nvidia-smi -lms 200`) or a polling thread was measured to cost this workload 15-40 %: the step
+  issues ~17 launches plus cross-stream events, and concurrent driver queries stall them. nvidia-smi is the fallback
+  (one query per sample) when pynvml is unavailable.
+  """
+  BITS = dict(sw_power_cap=0x4, hw_slowdown=0x8, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40)
 
-  def start(self):
+  def __init__(self, index, uuid=None):
+    self.index, self.rows, self.mode = index, [], None
     try:
-      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                    '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
-      threading.Thread(target=self._read, daemon=True).start()
+      import pynvml
+      pynvml.nvmlInit()
+      h = None
+      if uuid:
+        for cand in (f'GPU-{uuid}', str(uuid)):
+          try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+            break
+          except Exception:
+            h = None
+      self._h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+      self._nv = pynvml
+      self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+      self._reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+      self.mode = 'nvml-inline'
     except Exception:
-      self.proc = None
+      self.mode = 'nvidia-smi-inline'
 
-  def _read(self):
-    for line in self.proc.stdout:
-      self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+  def sample(self):
+    try:
+      if self.mode == 'nvml-inline':
+        sm = self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)
+        bits = int(self._reasons(self._h))
+        self.rows.append((float(sm), float(self._max), [n for n, b in self.BITS.items() if bits & b]))
+      else:
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm,'
+                              'clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,'
+                              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown',
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=10).stdout
+        f = [x.strip() for x in out.strip().split(',')]
+        self.rows.append((float(f[0]), float(f[1]), [n for n, v in zip(self.BITS, f[2:6]) if v.lower().startswith('active')]))
+    except Exception:
+      pass
 
-  def mark(self):
-    """Only samples that arrive after this instant are reported (the process is started before warm-up so that
-    its start-up cost — spawning nvidia-smi stalls the driver for tens of ms — stays out of the timed region)."""
-    self.t_mark = time.time()
-
-  def stop(self):
-    if self.proc is not None:
-      self.proc.terminate()
-    time.sleep(0.05)
-    rows = [r for t, r in self.rows if t >= self.t_mark] or [r for _, r in self.rows[-2:]]
-    sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
-    mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
-    return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                samples=len(sm))
+  def summary(self):
+    sm = [r[0] for r in self.rows]
+    return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max((r[1] for r in self.rows), default=None),
+                reasons=sorted({n for r in self.rows for n in r[2]}), samples=len(sm), source=self.mode)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -193,23 +208,22 @@ def run_gpu(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("B200_BENCH_NO_SAMPLER")) else None
-  if sampler:
-    sampler.start()
+  sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if (rank == 0 and not os.environ.get("B200_BENCH_NO_SAMPLER")) else None
   # settle to the steady-state contact load the metric is quoted on (20 warm-up env-steps minimum)
   for _ in range(max(args.warmup, 3)):
     one_step()
   barrier()
 
   # ---- device-resident arm -------------------------------------------------------------------------------
-  if sampler:
-    sampler.mark()
   launches0 = L.b200mj_launch_count()
   ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
   kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
   barrier()
   ev[0].record()
+  every = max(1, args.steps // 8)
   for i in range(args.steps):
+    if sampler and i % every == every // 2:
+      sampler.sample()                                 # clocks / throttle reasons while the region is running
     flush.fill_(0.0)
     actions.uniform_(-1, 1, generator=gen)
     env._task.before_step(actions, phys)
@@ -225,7 +239,7 @@ def run_gpu(args):
   ms_total = ev[0].elapsed_time(ev[1])
   kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
   launches = L.b200mj_launch_count() - launches0
-  clocks = sampler.stop() if sampler else None
+  clocks = sampler.summary() if sampler else None
   t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
