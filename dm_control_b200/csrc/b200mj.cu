@@ -966,8 +966,10 @@ __device__ __forceinline__ int make_constraint(const Ctx& c, int ncon, int* warn
 __device__ __forceinline__ void fwd_velocity(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane;
   double* cvel = W(cvel); double* cacc = W(cacc); double* cfrc = W(cfrc); double* qvel = W(qvel);
-  if (lane < 6) { cvel[lane] = 0; cfrc[lane] = 0; cacc[lane] = 0; }
-  if (lane < 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) cacc[3 + lane] = -m.gravity[lane];
+  if (lane < 6) {   // world body: zero velocity / force; gravity enters as a base acceleration (one writer per element)
+    cvel[lane] = 0; cfrc[lane] = 0;
+    cacc[lane] = (lane >= 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) ? -m.gravity[lane - 3] : 0.0;
+  }
   __syncwarp();
   _Pragma("unroll 1") for (int l = 1; l < m.nlevel; l++) {
     int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
@@ -1367,8 +1369,10 @@ __device__ __forceinline__ void rne_post_constraint(const Ctx& c, const b200mj_i
       }
     }
   }
-  if (lane < 6) { cacc[lane] = 0; cint[lane] = 0; }
-  if (lane < 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) cacc[3 + lane] = -m.gravity[lane];
+  if (lane < 6) {
+    cint[lane] = 0;
+    cacc[lane] = (lane >= 3 && !(c.disableflags & BMJ_DSBL_GRAVITY)) ? -m.gravity[lane - 3] : 0.0;
+  }
   __syncwarp();
   _Pragma("unroll 1") for (int l = 1; l < m.nlevel; l++) {
     int a0 = m.level_adr[l], a1 = m.level_adr[l + 1];
