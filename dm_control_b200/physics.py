@@ -108,6 +108,14 @@ class BatchedPhysics:
     self._warn_seen = torch.zeros((B, 8), dtype=torch.int32, device=self.device)
     self.reset()
 
+  @property
+  def named(self):
+    """Named indexing (`physics.named.data.xpos['torso', 'z']`), batched: see dm_control_b200/index.py."""
+    if getattr(self, '_named', None) is None:
+      from . import index
+      self._named = index.NamedIndexStructs(self)
+    return self._named
+
   # ---- construction helpers (reference: engine.py:451-503) -------------------------------------------
   @classmethod
   def from_xml_string(cls, xml_string, assets=None, **kw):
