@@ -1,0 +1,66 @@
+"""-m gpu: the batched suite tasks behave like the reference's conformance tests demand (suite/suite_test.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+@pytest.mark.parametrize('domain,task,nu,obs_dim', [('cartpole', 'swingup', 1, 5), ('cheetah', 'run', 6, 17),
+                                                     ('humanoid', 'run', 21, 67), ('quadruped', 'walk', 12, 78)])
+def test_task_conformance(domain, task, nu, obs_dim):
+  from dm_control_b200 import suite
+  B = 64
+  env = suite.load(domain, task, batch=B, seed=3)
+  ts = env.reset()
+  assert ts.reward is None and int(ts.step_type[0]) == 0
+  g = torch.Generator(device='cuda').manual_seed(0)
+  dims, seen = None, []
+  for t in range(12):
+    a = torch.rand(B, nu, generator=g, device='cuda', dtype=torch.float64) * 2 - 1     # suite_test.py:32-45 policy
+    ts = env.step(a)
+    flat = torch.cat([v.reshape(B, -1) for v in ts.observation.values()], dim=1)
+    assert flat.shape == (B, obs_dim), flat.shape                                       # SURVEY §8a observation sizes
+    assert bool(torch.isfinite(flat).all())                                              # suite_test.py:148-167
+    assert float(ts.reward.min()) >= 0.0 and float(ts.reward.max()) <= 1.0
+    seen.append(flat)
+  assert float((seen[-1] - seen[0]).abs().max()) > 1e-6                                  # observations are not constant
+  assert float(seen[0].std(dim=0).max()) > 1e-6                                          # initial states are randomised across envs
+
+
+def test_same_seed_same_trajectory():
+  # suite/suite_test.py:169-185
+  from dm_control_b200 import suite
+  outs = []
+  for _ in range(2):
+    env = suite.load('cheetah', 'run', batch=16, seed=11)
+    env.reset()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for _ in range(5):
+      ts = env.step(torch.rand(16, 6, generator=g, device='cuda', dtype=torch.float64) * 2 - 1)
+    outs.append(torch.cat([v.reshape(16, -1) for v in ts.observation.values()], dim=1))
+  assert torch.equal(outs[0], outs[1])
+
+
+def test_humanoid_reward_matches_numpy_formula():
+  """The torch reward equals the reference formula (suite/humanoid.py:183-207) evaluated in numpy on the same fields."""
+  from dm_control_b200 import suite
+  env = suite.load('humanoid', 'run', batch=32, seed=1)
+  env.reset()
+  g = torch.Generator(device='cuda').manual_seed(2)
+  for _ in range(8):
+    ts = env.step(torch.rand(32, 21, generator=g, device='cuda', dtype=torch.float64) * 2 - 1)
+  p = env.physics
+  head = p.head_height().cpu().numpy(); up = p.torso_upright().cpu().numpy(); ctrl = p.control().cpu().numpy()
+  com = p.center_of_mass_velocity().cpu().numpy()
+  def tol(x, lo, hi, margin, sig, vam):
+    x = np.asarray(x); inb = (lo <= x) & (x <= hi); d = np.where(x < lo, lo - x, x - hi) / margin
+    if sig == 'gaussian': s = np.exp(-0.5 * (d * np.sqrt(-2 * np.log(vam))) ** 2)
+    elif sig == 'linear': sx = d * (1 - vam); s = np.where(abs(sx) < 1, 1 - sx, 0.0)
+    else: sx = d * np.sqrt(1 - vam); s = np.where(abs(sx) < 1, 1 - sx ** 2, 0.0)
+    return np.where(inb, 1.0, s)
+  standing = tol(head, 1.4, np.inf, 0.35, 'gaussian', 0.1)
+  upright = tol(up, 0.9, np.inf, 1.9, 'linear', 0)
+  small = (4 + tol(ctrl, 0, 0, 1, 'quadratic', 0).mean(1)) / 5
+  move = (5 * tol(np.linalg.norm(com[:, :2], axis=1), 10, np.inf, 10, 'linear', 0) + 1) / 6
+  np.testing.assert_allclose(ts.reward.cpu().numpy(), small * standing * upright * move, rtol=1e-12, atol=1e-14)
