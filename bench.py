@@ -116,7 +116,7 @@ def _cpu_worker(args):
   return t0, time.time()
 
 
-def time_cpu(warmup_steps=5, timed_steps=120, nenv_per_proc=4, procs=None):
+def time_cpu(warmup_steps=5, timed_steps=150, nenv_per_proc=8, procs=None):
   """Times `control_step(5)` (legacy ordering, engine.py:147-162) of the scalar CPU oracle on all host cores.
 
   One forked process per core, each owning `nenv_per_proc` environments and stepping them inside one C call;
@@ -144,7 +144,7 @@ def run_reference(args):
   if rank != 0:
     return
   steps = max(1, args.steps)
-  value, cores, sample, ms = time_cpu(max(3, min(args.warmup, 10)), max(40, steps * 6))
+  value, cores, sample, ms = time_cpu(max(3, min(args.warmup, 10)), max(60, min(steps * 6, 300)))
   line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
               ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
               config=dict(workload='suite.humanoid:run, 5 physics substeps per env-step, random actions',
@@ -283,7 +283,7 @@ def run_gpu(args):
       prof = json.load(open(pj))
     cpu = None
     if world == 1 and not args.no_cpu:
-      v, cores, sample, _ = time_cpu(5, 120)
+      v, cores, sample, _ = time_cpu(5, 150)
       cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -299,8 +299,10 @@ def run_gpu(args):
                  d2h_bytes_per_step=BATCH * (OBS_DIM + 2) * 8 * (world if world > 1 else 1)),
         gpu_launches=int(launches),
         roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                      traffic=prof.get('dram_bytes_per_launch'), peak_source=peak_src,
-                      kernel='b200mj_step_kernel', kernel_ms=kernel_ms, kernel_share_of_step=kernel_ms / (ms_total / args.steps),
+                      traffic=prof.get('dram_bytes_per_step', prof.get('dram_bytes_per_launch')), peak_source=peak_src,
+                      kernel='b200mj step group: (pos_kernel + acc_kernel x row-buckets) x (n_sub_steps-1) + fused step_kernel',
+                      dominant_kernel=prof.get('dominant_kernel', 'b200mj_acc_kernel'),
+                      kernel_ms=kernel_ms, kernel_share_of_step=kernel_ms / (ms_total / args.steps),
                       algorithmic_bytes_per_launch=ALGO_BYTES_PER_ENV_STEP * BATCH,
                       note='latency/issue-bound fp64 kernel: compulsory traffic is ~4 kB per env-step, see DESIGN.md'),
         clocks=clocks, warnings=[int(x) for x in warn.tolist()])

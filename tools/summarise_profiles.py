@@ -54,6 +54,27 @@ if os.path.exists(rep):
   by = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_by_function.py'), os.path.join(G, 'bench_src_cs.csv'), '40',
                        os.path.join(G, 'bench_src_c.csv')], capture_output=True, text=True).stdout
   open(os.path.join(P, f'{tag}_step_kernel_by_function.txt'), 'w').write(by)
+# ---- DRAM traffic of the whole step group --------------------------------------------------------------------
+dc = os.path.join(G, 'step_dram.csv')
+if os.path.exists(dc):
+  rows = [r for r in csv.reader(open(dc)) if r]
+  hdr = next(r for r in rows if r and r[0] == 'ID')
+  ik, im, iu, iv = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Unit'), hdr.index('Metric Value')
+  tot = 0.0; fused = 0; per_kernel = {}
+  for r in rows[rows.index(hdr) + 1:]:
+    if 'dram__bytes' in r[im]:
+      v = float(r[iv].replace(',', '')) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(r[iu], 1)
+      tot += v; per_kernel[r[ik][:24]] = per_kernel.get(r[ik][:24], 0) + v
+    if r[im] == 'gpu__time_duration.sum' and 'b200mj_step_kernel' in r[ik]: fused += 1
+  if fused:
+    summary['dram_bytes_per_step'] = tot / fused
+    summary['dram_bytes_per_step_by_kernel'] = {k: v / fused for k, v in per_kernel.items()}
+    summary['dram_steps_in_capture'] = fused
+lc2 = os.path.join(P, f'{tag}_launches_summary.csv')
+if os.path.exists(lc2):
+  rows = list(csv.reader(open(lc2)))[1:]
+  mine = [r for r in rows if r and 'b200mj' in r[0]]
+  if mine: summary['dominant_kernel'] = max(mine, key=lambda r: float(r[2]))[0]
 summary['source'] = f'profiles/{tag}_*: ncu captures of `python bench.py --steps 2..3 --warmup 3 --no-cpu` (tools/profile_bench.sh)'
 json.dump(summary, open(os.path.join(P, 'summary.json'), 'w'), indent=1)
 print(json.dumps(summary, indent=1))
