@@ -52,7 +52,8 @@ def test_model_sizes_match_survey_table():
   exp = dict(cartpole=dict(nbody=3, njnt=2, nq=2, nv=2, nu=1, na=0, ngeom=5, nsensordata=0),
              cheetah=dict(nbody=8, njnt=9, nq=9, nv=9, nu=6, na=0, ngeom=9, nsensordata=3),
              humanoid=dict(nbody=17, njnt=22, nq=28, nv=27, nu=21, na=0, ngeom=20, nsensordata=66),
-             quadruped=dict(nbody=18, njnt=17, nq=23, nv=22, nu=12, na=12, ngeom=20, nsensordata=36, ntendon=12, neq=4))
+             quadruped=dict(nbody=18, njnt=17, nq=23, nv=22, nu=12, na=12, ngeom=20, nsensordata=36, ntendon=12, neq=4),
+             cmu_humanoid=dict(nq=63, nv=62, nu=56, na=0, njnt=57, nsensordata=25))
   for name, sizes in exp.items():
     m = tm.load(name)
     for k, v in sizes.items():

@@ -40,7 +40,7 @@ def _setup(name, B, seed, oracle_mod):
 
 
 @pytest.mark.parametrize('name,B', [('cartpole', 8), ('pendulum_free', 8), ('cheetah', 16), ('humanoid', 16),
-                                    ('slide_box', 4), ('free_box', 4)])
+                                    ('slide_box', 4), ('free_box', 4), ('cmu_humanoid', 4)])
 def test_forward_fields_match_oracle(name, B, oracle_mod):
   model, phys, oracles = _setup(name, B, 11, oracle_mod)
   for f in ('xpos', 'xquat', 'xmat', 'xipos', 'geom_xpos', 'geom_xmat', 'site_xpos', 'site_xmat', 'subtree_com',
@@ -64,7 +64,7 @@ def test_forward_fields_match_oracle(name, B, oracle_mod):
 
 @pytest.mark.parametrize('name,B,ncontrol,nsub', [('cartpole', 16, 60, 1), ('pendulum_free', 8, 50, 2),
                                                    ('cheetah', 32, 100, 1), ('humanoid', 32, 20, 5),
-                                                   ('quadruped', 16, 15, 4)])
+                                                   ('quadruped', 16, 15, 4), ('cmu_humanoid', 6, 6, 6)])
 def test_rollout_matches_oracle(name, B, ncontrol, nsub, oracle_mod):
   """Fixed recorded action tape, legacy step ordering; compare every control step."""
   model, phys, oracles = _setup(name, B, 0, oracle_mod)

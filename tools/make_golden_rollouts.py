@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dm_control_b200 import testing_models as tm
 from oracle import oracle as om
 
-CASES = (('cartpole', 1, 40), ('cheetah', 1, 60), ('humanoid', 5, 16), ('quadruped', 4, 12), ('pendulum_free', 2, 30))
+CASES = (('cartpole', 1, 40), ('cheetah', 1, 60), ('humanoid', 5, 16), ('quadruped', 4, 12), ('pendulum_free', 2, 30), ('cmu_humanoid', 6, 5))
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'oracle_rollouts.npz')
 
 

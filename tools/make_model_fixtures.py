@@ -7,6 +7,7 @@ MJCF compiler from the reference XML:
   cartpole   dm_control/suite/cartpole.xml                         (suite.cartpole:swingup)
   cheetah    dm_control/suite/cheetah.xml                          (suite.cheetah:run)
   humanoid   dm_control/suite/humanoid.xml                         (suite.humanoid:run)
+  cmu_humanoid  locomotion/walkers/assets/humanoid_CMU_V2019.xml + the position actuators cmu_humanoid.py builds, on a plane
   quadruped  dm_control/suite/quadruped.xml, stripped exactly as suite/quadruped.py:55-93 `make_model` does for
              `walk` (walls, ball, target site, terrain hfield and rangefinder sensors removed; floor resized)
 
@@ -40,6 +41,40 @@ def quadruped_walk_xml():
   return ET.tostring(root)
 
 
+def cmu_humanoid_flat_xml():
+  """CMU humanoid V2019 as `CMUHumanoidPositionControlled` builds it (locomotion/walkers/cmu_humanoid.py:360-394,
+  scaled_actuators.py:37-82), standing on a plane, under the composer root compiler settings
+  (composer/arena.xml:2: angle=radian, boundmass=1e-5, boundinertia=1e-11) and the example's 5 ms physics step
+  (locomotion/examples/basic_cmu_2019.py:57-58). Corridor walls and the egocentric camera are NOT part of this fixture."""
+  import re
+  walkers = '/root/reference/dm_control/locomotion/walkers'
+  root = ET.parse(os.path.join(walkers, 'assets', 'humanoid_CMU_V2019.xml')).getroot()
+  src = open(os.path.join(walkers, 'cmu_humanoid.py')).read()
+  table = src.split('_POSITION_ACTUATORS = [')[1].split(']\n')[0]
+  params = re.findall(r"PositionActuatorParams\('(\w+)',\s*\[\s*(-?[\d.]+),\s*(-?[\d.]+)\s*\],\s*([\d.]+)\s*\)", table)
+  assert len(params) == 56, len(params)
+  root.insert(0, ET.Element('compiler', angle='radian', boundmass='1e-5', boundinertia='1e-11'))
+  root.insert(1, ET.Element('option', timestep='0.005'))
+  world = root.find('worldbody')
+  world.insert(0, ET.Element('geom', name='groundplane', type='plane', size='1 1 1', condim='3', friction='1 0.005 0.0001',
+                             solref='0.02 1', solimp='0.9 0.95 0.001 0.5 2', contype='1', conaffinity='1'))
+  body = [b for b in world.findall('body') if b.get('name') == 'root'][0]
+  body.set('pos', '0 0 0.94'); body.set('quat', '0.859 1.0 1.0 0.859')          # cmu_humanoid.py:174-176 upright pose
+  body.insert(0, ET.Element('freejoint', name='root'))
+  joints = {j.get('name'): j for j in root.iter('joint')}
+  # joint ranges: explicit on the element, else inherited from defaults (all CMU joints carry their own range)
+  act = root.find('actuator')
+  for m in list(act):
+    act.remove(m)
+  for name, f_lo, f_hi, kp in params:
+    lo, hi = [float(x) for x in joints[name].get('range').split()]
+    kp = float(kp); slope = (hi - lo) / 2.0
+    ET.SubElement(act, 'general', name=name, joint=name, biastype='affine', gainprm=repr(kp * slope),
+                  biasprm=f'{kp * (lo - slope * -1.0)!r} {-kp!r} 0', ctrllimited='true', ctrlrange='-1 1',
+                  forcelimited='true', forcerange=f'{f_lo} {f_hi}')
+  return ET.tostring(root)
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   caps = dict(cartpole=dict(nconmax=0, njmax=4), cheetah=dict(nconmax=16, njmax=80),
@@ -54,6 +89,10 @@ def main():
     print('quadruped', 'nq', m.nq, 'nv', m.nv, 'nu', m.nu, 'na', m.na, 'nbody', m.nbody, 'ngeom', m.ngeom, 'npair', m.npair)
   except Exception as ex:
     print('quadruped: not compiled yet:', repr(ex))
+  m = mc.compile_xml(cmu_humanoid_flat_xml(), nconmax=40, njmax=112)
+  m.save(os.path.join(OUT, 'cmu_humanoid.npz'))
+  print('cmu_humanoid', 'nq', m.nq, 'nv', m.nv, 'nu', m.nu, 'nbody', m.nbody, 'ngeom', m.ngeom, 'npair', m.npair, 'nsensordata', m.nsensordata,
+        'mass %.2f' % m.body_mass.sum())
 
 
 if __name__ == '__main__':
