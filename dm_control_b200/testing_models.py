@@ -99,4 +99,16 @@ def initial_states(model, name, batch, seed=0):
         v[e, da:da + 6] = rs.uniform(-0.5, 0.5, 6)
   if name == 'cartpole':
     q[:, 0] = np.clip(q[:, 0], -1.0, 1.0)
+  if name == 'cmu_humanoid':
+    # 56 joints drawn over their whole range fold the walker into itself (hundreds of constraint rows): start
+    # from the upright pose with small joint offsets and a slightly lowered root instead
+    for e in range(batch):
+      rs = np.random.RandomState(seed * 100003 + e + 77)
+      q[e] = model.qpos0
+      q[e, 2] = model.qpos0[2] * rs.uniform(0.93, 1.0)
+      for j in range(model.njnt):
+        if model.jnt_type[j] == 3:
+          lo, hi = model.jnt_range[j]
+          qa = model.jnt_qposadr[j]
+          q[e, qa] = np.clip(model.qpos0[qa] + rs.uniform(-0.15, 0.15), lo + 0.02, hi - 0.02)
   return q, v
