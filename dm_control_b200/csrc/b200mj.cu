@@ -2005,10 +2005,16 @@ static void build_layout(b200mj_model* M) {
     };
     M->smem_acc = acc_layout(M->lay_acc, nj, false);
     // row-count buckets: most environments carry far fewer rows than njmax (humanoid: mean 10, max 43 of 64)
-    int caps[3] = {8, 20, nj};
-    if (const char* ev = getenv("B200MJ_BUCKETS")) { int a1 = 0, a2 = 0; if (sscanf(ev, "%d,%d", &a1, &a2) == 2) { caps[0] = a1; caps[1] = a2; } }
+    int caps[4] = {10, 24, nj, nj};
+    int ncap = 3;
+    if (const char* ev = getenv("B200MJ_BUCKETS")) {
+      int a1 = 0, a2 = 0, a3 = 0;
+      int got = sscanf(ev, "%d,%d,%d", &a1, &a2, &a3);
+      if (got == 2) { caps[0] = a1; caps[1] = a2; caps[2] = nj; ncap = 3; }
+      else if (got == 3) { caps[0] = a1; caps[1] = a2; caps[2] = a3; caps[3] = nj; ncap = 4; }
+    }
     M->nbucket = 0;
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < ncap; k++) {
       int cap = caps[k] < nj ? caps[k] : nj;
       if (M->nbucket > 0 && cap <= M->rows_cap[M->nbucket - 1]) continue;
       int bi = M->nbucket++;
@@ -2151,7 +2157,7 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
 
 static int split_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("B200MJ_SPLIT"); v = e ? atoi(e) : 1; }
+  if (v < 0) { const char* e = getenv("B200MJ_SPLIT"); v = e ? atoi(e) : 2; }
   return v;
 }
 
@@ -2175,9 +2181,9 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   cudaStream_t st = (cudaStream_t)stream;
   const int gp = (batch + M->epb_pos - 1) / M->epb_pos;
   const bool want_sens = (flags & B200MJ_STEP_SENSORS) != 0;
-  // split_enabled() == 1 (default): split kernels for the first nstep-1 physics steps, the fused kernel for the last
-  // one (acceleration-stage sensors, outputs, trailing mj_step1): measured faster than splitting that one too.
-  // == 2: every physics step split (acclast / posfinal variants), kept for experiments.
+  // split_enabled() == 2 (default): every physics step split; the last one uses the sensor-carrying acceleration
+  // kernel and the trailing mj_step1 is the `posfinal` kernel (12 % faster than == 1 with concurrent bucket streams).
+  // == 1: split kernels for the first nstep-1 physics steps, the fused kernel for the last one. == 0: fused only.
   const bool all_split = split_enabled() >= 2;
   const int nsplit = all_split ? nstep : nstep - 1;
   for (int s = 0; s < nsplit; s++) {
