@@ -2224,7 +2224,7 @@ int b200mj_step_host(const b200mj_model* M, const b200mj_io* io, int batch, int 
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemcpyAsync(ctrl_dev, ctrl_host, (size_t)batch * M->dm.nu * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) return -2;
   b200mj_io io2 = *io; io2.ctrl = ctrl_dev;
-  int rc = launch(M, &io2, batch, nstep, flags, MODE_STEP, 0, stream);
+  int rc = b200mj_step(M, &io2, batch, nstep, flags, stream);
   if (rc) return rc;
   if (obs_dev && obs_host && nobs > 0)
     if (cudaMemcpyAsync(obs_host, obs_dev, (size_t)batch * nobs * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -2;

@@ -127,3 +127,37 @@ def test_compile_and_step_inline_model():
       tm.XML['pendulum_free'], batch=5)
   phys.step(10)
   assert bool(torch.isfinite(phys.data.qpos).all())
+
+
+def test_step_host_equals_step():
+  """The HOST-buffer entry point (b200mj_step_host) gives the same state as set_control + step on device tensors."""
+  a, b = _phys('cheetah', 16), _phys('cheetah', 16)
+  for p in (a, b):
+    _seed(p, 'cheetah', 2)
+  ctrl = torch.rand(16, 6, dtype=torch.float64).mul_(2).sub_(1).pin_memory()
+  obs_host = torch.empty(16, 3, dtype=torch.float64).pin_memory()
+  for _ in range(5):
+    a.set_control(ctrl.cuda()); a.step(3)
+    b.step_host(ctrl, b.data.sensordata, obs_host, nstep=3)
+  assert torch.equal(a.get_state(), b.get_state())
+  assert torch.equal(obs_host, a.data.sensordata.cpu())
+
+
+def test_fused_and_split_paths_agree_bitwise(monkeypatch):
+  """B200MJ_SPLIT=0 (one fused kernel) and the default split path are the same arithmetic."""
+  import subprocess, sys, os, json
+  code = ("import sys, json, torch; sys.path.insert(0, %r);"
+          "from dm_control_b200 import testing_models as tm; from dm_control_b200.physics import BatchedPhysics;"
+          "m = tm.load('humanoid'); q, v = tm.initial_states(m, 'humanoid', 32, 5); p = BatchedPhysics(m, batch=32);"
+          "p.data.qpos.copy_(torch.as_tensor(q)); p.data.qvel.copy_(torch.as_tensor(v)); p.forward();"
+          "g = torch.Generator(device='cuda').manual_seed(0);"
+          "[ (p.data.ctrl.uniform_(-1, 1, generator=g), p.step(5)) for _ in range(6) ];"
+          "print(json.dumps(dict(q=p.data.qpos.cpu().tolist(), s=p.data.sensordata.cpu().tolist(), n=p.data.ncon.cpu().tolist())))"
+          ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  outs = []
+  for split in ('0', '1', '2'):
+    env = dict(os.environ, B200MJ_SPLIT=split)
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+  assert outs[0] == outs[1] == outs[2]
