@@ -182,6 +182,8 @@ def run_gpu(args):
   phys.data.qpos.copy_(torch.as_tensor(q0, device=dev)); phys.data.qvel.copy_(torch.as_tensor(v0, device=dev))
   phys.forward()
   env._reset_next.zero_()
+  # the task's ~80 tiny reward/observation launches replay as one CUDA graph (falls back to eager if capture fails)
+  env._graph_task_ops = not os.environ.get('B200_BENCH_NO_GRAPH')
   gen = torch.Generator(device=dev).manual_seed(1234 + rank)
   actions = torch.empty(BATCH, model.nu, dtype=torch.float64, device=dev)
   packed = torch.empty(BATCH, OBS_DIM + 2, dtype=torch.float64, device=dev)
@@ -210,6 +212,15 @@ def run_gpu(args):
 
   sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if (rank == 0 and not os.environ.get("B200_BENCH_NO_SAMPLER")) else None
   # settle to the steady-state contact load the metric is quoted on (20 warm-up env-steps minimum)
+  try:
+    one_step()
+  except Exception as ex:           # graph capture unsupported for some op: eager task ops
+    if not env._graph_task_ops:
+      raise
+    sys.stderr.write(f'task-op graph capture failed ({ex!r}); running the task ops eagerly\n')
+    env._graph_task_ops = False; env._graph = None
+    torch.cuda.synchronize()
+    one_step()
   for _ in range(max(args.warmup, 3)):
     one_step()
   barrier()
@@ -231,8 +242,7 @@ def run_gpu(args):
     phys.step(env.n_sub_steps)                         # the one launch of b200mj_step_kernel
     kev[i][1].record()
     env._task.after_step(phys)
-    reward = env._task.get_reward(phys)
-    obs = env._task.get_observation(phys)
+    reward, obs = env._reward_and_observation()
     pack(type('TS', (), dict(observation=obs, reward=reward, discount=torch.ones_like(reward))))
   ev[1].record()
   barrier()
@@ -292,6 +302,7 @@ def run_gpu(args):
         config=dict(workload='suite.humanoid:run', batch_per_gpu=BATCH, global_batch=BATCH * world, n_sub_steps=NSUB,
                     physics_steps_per_s=value * NSUB, parallelism=f'env-sharded x{world}',
                     actions='uniform(-1,1) generated on device', l2='256 MB flush write between steps, inside the timed region',
+                    task_ops='one CUDA-graph replay' if env._graph_task_ops else 'eager torch ops',
                     obs_gather='NCCL gather of [B,69] f64 to rank 0 each step' if world > 1 else 'n/a (1 GPU)',
                     workspace_bytes_per_env=phys.workspace_bytes(), envs_per_block=phys.envs_per_block(),
                     nconmax=model.nconmax, njmax=model.njmax),

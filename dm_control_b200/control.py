@@ -30,7 +30,7 @@ FIRST, MID, LAST = 0, 1, 2
 class BatchedEnvironment:
 
   def __init__(self, physics, task, time_limit=float('inf'), control_timestep=None, n_sub_steps=None,
-               legacy_step=True, auto_reset=True):
+               legacy_step=True, auto_reset=True, graph_task_ops=False):
     self._physics, self._task = physics, task
     physics.legacy_step = legacy_step
     if n_sub_steps is not None and control_timestep is not None:
@@ -45,6 +45,11 @@ class BatchedEnvironment:
     self._step_count = torch.zeros(physics.batch, dtype=torch.int64, device=physics.device)
     self._reset_next = torch.ones(physics.batch, dtype=torch.bool, device=physics.device)
     self._auto_reset = auto_reset
+    # Optional: replay the task's reward/observation torch ops (~80 tiny launches) as one CUDA graph. The returned
+    # reward / observation tensors are then static buffers that the next step overwrites.
+    self._graph_task_ops = graph_task_ops
+    self._graph = None
+    self._graph_out = None
 
   @property
   def physics(self):
@@ -69,6 +74,24 @@ class BatchedEnvironment:
     B = self._physics.batch
     return TimeStep(torch.full((B,), FIRST, device=self._physics.device), None, None, obs)
 
+  def _reward_and_observation(self):
+    if not self._graph_task_ops:
+      return self._task.get_reward(self._physics), self._task.get_observation(self._physics)
+    if self._graph is None:
+      # warm up eagerly on a side stream (allocator + lazy module loads), then capture once
+      s = torch.cuda.Stream(device=self._physics.device)
+      s.wait_stream(torch.cuda.current_stream(self._physics.device))
+      with torch.cuda.stream(s):
+        for _ in range(2):
+          self._task.get_reward(self._physics); self._task.get_observation(self._physics)
+      torch.cuda.current_stream(self._physics.device).wait_stream(s)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        out = (self._task.get_reward(self._physics), self._task.get_observation(self._physics))
+      self._graph, self._graph_out = g, out
+    self._graph.replay()
+    return self._graph_out
+
   def step(self, action):
     if self._auto_reset and bool(self._reset_next.any()):
       mask = self._reset_next
@@ -78,8 +101,7 @@ class BatchedEnvironment:
     self._task.before_step(action, self._physics)
     self._physics.step(self._n_sub_steps)
     self._task.after_step(self._physics)
-    reward = self._task.get_reward(self._physics)
-    obs = self._task.get_observation(self._physics)
+    reward, obs = self._reward_and_observation()
     self._step_count += 1
     last = self._step_count >= self._step_limit
     self._reset_next = last
