@@ -195,6 +195,20 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------------
 // dense Cholesky in the workspace: A (n x n, row stride ld) -> lower factor Lm, same stride
 // ------------------------------------------------------------------------------------------------
+// coalesced copy between a handover row in global memory and the workspace: 16-byte accesses, four in flight per
+// lane (a rolled 8-byte loop would serialise one L2/DRAM latency per element). Regions are 16-byte aligned and padded
+// to an even number of doubles by the layout builder.
+__device__ __forceinline__ void copy_row(double* dst, const double* src, int n, int lane) {
+  const int n2 = (n + 1) >> 1;
+  double2* d2 = reinterpret_cast<double2*>(dst); const double2* s2 = reinterpret_cast<const double2*>(src);
+  int i = lane;
+  _Pragma("unroll 1") for (; i + 96 < n2; i += 128) {
+    double2 a = s2[i], b = s2[i + 32], c = s2[i + 64], d = s2[i + 96];
+    d2[i] = a; d2[i + 32] = b; d2[i + 64] = c; d2[i + 96] = d;
+  }
+  _Pragma("unroll 1") for (; i < n2; i += 32) d2[i] = s2[i];
+}
+
 // dot product of two workspace rows with four independent accumulators (breaks the DFMA dependency chain)
 __device__ __forceinline__ double dot_rows(const double* a, const double* b, int n) {
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -1811,11 +1825,11 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   } else {
     // hand over the small tables the actuation stage needs and the row counts
     FOR_LANES(t, m.ntendon) hrow[H.tenlen + t] = W(tenlen)[t];
-    _Pragma("unroll 1") for (int i = lane; i < m.ntendon * m.ldv; i += 32) hrow[H.tenJ + i] = W(tenJ)[i];
+    copy_row(hrow + H.tenJ, W(tenJ), m.ntendon * m.ldv, lane);
     if (lane == 0) { int* cnt = reinterpret_cast<int*>(hrow + H.counts); cnt[0] = ncon; cnt[1] = nefc; }
     if (dump) {
       double* d2 = hand2 + e * H2.total;
-#define DUMP(dst, src, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32) d2[H2.dst + i] = W(src)[i];
+#define DUMP(dst, src, n) copy_row(d2 + H2.dst, W(src), (n), lane);
       DUMP(xpos, xpos, 3 * m.nbody) DUMP(xquat, xquat, 4 * m.nbody) DUMP(xmat, xmat, 9 * m.nbody) DUMP(xipos, xipos, 3 * m.nbody)
       DUMP(scom, scom, 3 * m.nbody) DUMP(cinert, cinert, 10 * m.nbody) DUMP(cdof, cdof, 6 * m.nv) DUMP(cdofdot, cdofdot, 6 * m.nv)
       DUMP(cvel, cvel, 6 * m.nbody) DUMP(con, con, ncon * CON_STRIDE)
@@ -1869,16 +1883,16 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
                      W(bias)[i] = hrow[H.bias + i]; W(passive)[i] = hrow[H.passive + i]; }
   FOR_LANES(i, m.na) W(act)[i] = io.act[e * m.na + i];
   FOR_LANES(i, m.nu) W(ctrl)[i] = io.ctrl ? io.ctrl[e * m.nu + i] : 0.0;
-  _Pragma("unroll 1") for (int i = lane; i < nv * ld; i += 32) W(M)[i] = hrow[H.M + i];
-  _Pragma("unroll 1") for (int i = lane; i < nefc * ld; i += 32) W(J)[i] = hrow[H.J + i];
+  copy_row(W(M), hrow + H.M, nv * ld, lane);
+  copy_row(W(J), hrow + H.J, nefc * ld, lane);
   FOR_LANES(r, nefc) { W(efcD)[r] = hrow[H.efcD + r]; W(aref)[r] = hrow[H.aref + r];
                        reinterpret_cast<int*>(W(eqflag))[r] = reinterpret_cast<const int*>(hrow + H.eqflag)[r]; W(efcSD)[r] = 0; }
   FOR_LANES(t, m.ntendon) W(tenlen)[t] = hrow[H.tenlen + t];
-  _Pragma("unroll 1") for (int i = lane; i < m.ntendon * ld; i += 32) W(tenJ)[i] = hrow[H.tenJ + i];
+  copy_row(W(tenJ), hrow + H.tenJ, m.ntendon * ld, lane);
   const bool want_sens = LAST && (flags & B200MJ_STEP_SENSORS) != 0;
   if (want_sens) {
     const double* d2 = hand2 + e * H2.total;
-#define UNDUMP(dst, src, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32) W(dst)[i] = d2[H2.src + i];
+#define UNDUMP(dst, src, n) copy_row(W(dst), d2 + H2.src, (n), lane);
     UNDUMP(xpos, xpos, 3 * m.nbody) UNDUMP(xquat, xquat, 4 * m.nbody) UNDUMP(xmat, xmat, 9 * m.nbody) UNDUMP(xipos, xipos, 3 * m.nbody)
     UNDUMP(scom, scom, 3 * m.nbody) UNDUMP(cinert, cinert, 10 * m.nbody) UNDUMP(cdof, cdof, 6 * m.nv) UNDUMP(cdofdot, cdofdot, 6 * m.nv)
     UNDUMP(cvel, cvel, 6 * m.nbody) UNDUMP(con, con, ncon * CON_STRIDE)

@@ -64,3 +64,26 @@ def test_humanoid_reward_matches_numpy_formula():
   small = (4 + tol(ctrl, 0, 0, 1, 'quadratic', 0).mean(1)) / 5
   move = (5 * tol(np.linalg.norm(com[:, :2], axis=1), 10, np.inf, 10, 'linear', 0) + 1) / 6
   np.testing.assert_allclose(ts.reward.cpu().numpy(), small * standing * upright * move, rtol=1e-12, atol=1e-14)
+
+
+def test_time_limit_and_auto_reset():
+  """rl/control.py:99-127 semantics, batched: the step that reaches the limit is LAST; the next call re-initialises."""
+  from dm_control_b200 import suite, control
+  env = suite.load('cartpole', 'swingup', batch=8, seed=0, time_limit=0.05)   # 5 control steps of 0.01 s
+  env.reset()
+  a = torch.zeros(8, 1, dtype=torch.float64, device='cuda')
+  types = []
+  for _ in range(7):
+    ts = env.step(a)
+    types.append(int(ts.step_type[0]))
+  assert types == [control.MID] * 4 + [control.LAST] + [control.MID] * 2
+  assert float(env.physics.data.time.max()) == pytest.approx(0.02)          # two steps into the second episode
+  # masked reset keeps the other environments untouched
+  env2 = suite.load('cheetah', 'run', batch=6, seed=2)
+  env2.reset()
+  before = env2.physics.get_state().clone()
+  mask = torch.tensor([True, False, False, True, False, False], device='cuda')
+  env2.task.initialize_episode(env2.physics, mask)
+  after = env2.physics.get_state()
+  assert torch.equal(after[~mask], before[~mask])
+  assert not torch.equal(after[mask], before[mask])

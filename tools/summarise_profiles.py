@@ -65,7 +65,7 @@ if os.path.exists(dc):
     if 'dram__bytes' in r[im]:
       v = float(r[iv].replace(',', '')) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(r[iu], 1)
       tot += v; per_kernel[r[ik][:24]] = per_kernel.get(r[ik][:24], 0) + v
-    if r[im] == 'gpu__time_duration.sum' and 'b200mj_step_kernel' in r[ik]: fused += 1
+    if r[im] == 'gpu__time_duration.sum' and 'b200mj_posfinal_kernel' in r[ik]: fused += 1
   if fused:
     summary['dram_bytes_per_step'] = tot / fused
     summary['dram_bytes_per_step_by_kernel'] = {k: v / fused for k, v in per_kernel.items()}
