@@ -311,7 +311,7 @@ def run_gpu(args):
         gpu_launches=int(launches),
         roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                       traffic=prof.get('dram_bytes_per_step', prof.get('dram_bytes_per_launch')), peak_source=peak_src,
-                      kernel='b200mj step group: (pos_kernel + acc_kernel x row-buckets) x (n_sub_steps-1) + fused step_kernel',
+                      kernel='b200mj step group: [pos_kernel, acc_kernel x row-buckets] x (n_sub_steps-1), [pos_kernel, acclast_kernel x row-buckets], posfinal_kernel',
                       dominant_kernel=prof.get('dominant_kernel', 'b200mj_acc_kernel'),
                       kernel_ms=kernel_ms, kernel_share_of_step=kernel_ms / (ms_total / args.steps),
                       algorithmic_bytes_per_launch=ALGO_BYTES_PER_ENV_STEP * BATCH,
