@@ -116,6 +116,38 @@ class Model:
     kind = _OBJ_ALIASES[str(object_type).replace('mjOBJ_', '').lower()]
     return self.ordered_names[kind][object_id]
 
+  _DISABLE_NAMES = dict(constraint=1 << 0, equality=1 << 1, frictionloss=1 << 2, limit=1 << 3, contact=1 << 4,
+                        passive=1 << 5, gravity=1 << 6, clampctrl=1 << 7, warmstart=1 << 8, filterparent=1 << 9,
+                        actuation=1 << 10, refsafe=1 << 11, sensor=1 << 12, midphase=1 << 13, eulerdamp=1 << 14)
+
+  def disable(self, *flags):
+    """Context manager that sets `opt.disableflags` bits for its body (reference: wrapper/core.py:389-426).
+
+    `flags` are names ('contact', 'gravity', ...) or `mjtDisableBit` integers; anything else raises ValueError.
+    """
+    import contextlib
+    bits = 0
+    for f in flags:
+      if isinstance(f, str):
+        if f not in self._DISABLE_NAMES:
+          raise ValueError(f'{f!r} is not a valid flag name. Valid names: {", ".join(sorted(self._DISABLE_NAMES))}')
+        bits |= self._DISABLE_NAMES[f]
+      else:
+        f = int(f)
+        if f <= 0 or f not in self._DISABLE_NAMES.values():
+          raise ValueError(f'{f!r} is not a value in `mjtDisableBit`.')
+        bits |= f
+
+    @contextlib.contextmanager
+    def ctx():
+      old = self.opt.disableflags
+      self.opt.disableflags = old | bits
+      try:
+        yield
+      finally:
+        self.opt.disableflags = old
+    return ctx()
+
   def set_capacity(self, nconmax=None, njmax=None):
     if nconmax is not None:
       self.fields['sizes'][SIZE['NCONMAX']] = nconmax

@@ -33,6 +33,15 @@ class PhysicsError(RuntimeError):
   """Raised if the state of the physics simulation becomes divergent (reference: rl/control.py:270)."""
 
 
+def action_spec(physics):
+  """(minimum, maximum) float64 arrays of shape [nu]; unlimited controls get -/+ mjMAXVAL (engine.py:1093-1103)."""
+  m = physics.model
+  limited = m.actuator_ctrllimited.astype(bool)
+  lo = np.where(limited, m.actuator_ctrlrange[:, 0], -1e10)
+  hi = np.where(limited, m.actuator_ctrlrange[:, 1], 1e10)
+  return lo.astype(np.float64), hi.astype(np.float64)
+
+
 class _Data:
   """Batched mjData slice: `[B, ...]` torch tensors, MuJoCo field names."""
 
@@ -180,6 +189,16 @@ class BatchedPhysics:
   def _sync_model(self):
     if self.model._version != self._model_version:
       self._upload_model()
+
+  def copy(self, share_model=False):
+    """A new BatchedPhysics with the same model and a copy of the batched state (reference: engine.py:287-304)."""
+    other = type(self)(self.model if share_model else self.model.copy(), batch=self.batch, device=self.device,
+                       sensors=self._sensors, full_final=self._full_final)
+    for name in ('qpos', 'qvel', 'act', 'qacc_warmstart', 'time', 'ctrl'):
+      getattr(other.data, name).copy_(getattr(self.data, name))
+    other.legacy_step = self.legacy_step
+    other.forward()
+    return other
 
   def step(self, nstep=1):
     """Advance all environments by `nstep` physics steps (reference: engine.py:164-176).

@@ -94,3 +94,31 @@ def test_no_cpu_fallback():
   from dm_control_b200.physics import BatchedPhysics
   with pytest.raises(blib.EngineError):
     BatchedPhysics(tm.load('cartpole'), batch=2)
+
+
+def test_model_disable_context_and_errors():
+  # dm_control/mujoco/wrapper/core_test.py:291-338 (flag plumbing; the physics effect is tested on the GPU)
+  m = tm.load('cartpole').copy()
+  base = m.opt.disableflags
+  with m.disable('contact', 'gravity'):
+    assert m.opt.disableflags == base | (1 << 4) | (1 << 6)
+    with m.disable(1 << 10):
+      assert m.opt.disableflags & (1 << 10)
+  assert m.opt.disableflags == base
+  with pytest.raises(ValueError):
+    with m.disable('invalid_flag_name'):
+      pass
+  with pytest.raises(ValueError):
+    with m.disable(-99):
+      pass
+
+
+def test_action_spec():
+  # dm_control/mujoco/engine_test.py:606-625
+  import types
+  from dm_control_b200 import mjcf_compile as mc, physics as ph
+  xml = '''<mujoco><worldbody><body><geom type="sphere" size="0.1"/><joint type="hinge" name="hinge"/></body></worldbody>
+  <actuator><motor joint="hinge" ctrllimited="false"/><motor joint="hinge" ctrllimited="true" ctrlrange="-1 2"/></actuator></mujoco>'''
+  lo, hi = ph.action_spec(types.SimpleNamespace(model=mc.compile_xml(xml)))
+  np.testing.assert_array_equal(lo, [-1e10, -1.0])
+  np.testing.assert_array_equal(hi, [1e10, 2.0])

@@ -161,3 +161,40 @@ def test_fused_and_split_paths_agree_bitwise(monkeypatch):
     assert r.returncode == 0, r.stderr[-2000:]
     outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
   assert outs[0] == outs[1] == outs[2]
+
+
+SLIDING_CUBE = """
+<mujoco><option gravity="0 0 -9.81"/><worldbody>
+  <geom name="floor" type="plane" pos="0 0 0" size="10 10 0.1"/>
+  <body name="cube" pos="0 0 0.1"><geom type="box" size="0.1 0.1 0.1" mass="1"/>
+    <site name="cube_site" type="box" size="0.1 0.1 0.1"/><joint type="slide"/></body>
+</worldbody><sensor><touch name="touch_sensor" site="cube_site"/></sensor></mujoco>"""
+
+
+def test_disable_flags_on_gpu():
+  # dm_control/mujoco/wrapper/core_test.py:291-330 through model.disable(...) on the CUDA path
+  from dm_control_b200.physics import BatchedPhysics
+  phys = BatchedPhysics.from_xml_string(SLIDING_CUBE, batch=2)
+  phys.step(100)
+  assert float(phys.data.qvel.abs().max()) < 5e-5
+  assert float((phys.data.sensordata[:, 0] - 9.81).abs().max()) < 5e-3
+  with phys.model.disable('contact', 'gravity'):
+    phys.step()
+  assert float(phys.data.qvel.abs().max()) < 5e-5
+  assert float(phys.data.sensordata.abs().max()) == 0.0
+  with phys.model.disable(1 << 4):
+    phys.step(10)
+  assert float(phys.data.qvel.max()) < -0.1
+
+
+def test_copy_then_lockstep():
+  # dm_control/mujoco/engine_test.py:549-572: a copy stepped in lock-step stays bit-equal
+  a = _phys('cheetah', 8)
+  _seed(a, 'cheetah', 6)
+  a.set_control(torch.full((6,), 0.3, dtype=torch.float64)); a.step(10)
+  b = a.copy()
+  for p in (a, b):
+    p.set_control(torch.full((6,), -0.2, dtype=torch.float64))
+  a.step(10); b.step(10)
+  assert torch.equal(a.get_state(), b.get_state())
+  a.free(); a.free()       # idempotent (engine_test.py:203-205)
