@@ -73,7 +73,10 @@ class _Opt:
       m.fields['opt_int'][OPTI[key]] = value
     else:
       raise AttributeError(name)
-    m._version += 1
+    if key == 'DISABLEFLAGS':
+      m._flags_version += 1      # cheap path: the uploaded model only needs its flag word refreshed
+    else:
+      m._version += 1
 
 
 class Model:
@@ -88,6 +91,7 @@ class Model:
     self.ordered_names = ordered_names
     self.opt = _Opt(self)
     self._version = 0
+    self._flags_version = 0
 
   # --- sizes ---------------------------------------------------------------------------------
   def __getattr__(self, name):

@@ -145,6 +145,7 @@ class BatchedPhysics:
           idata.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), idata.size,
           rdata.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), rdata.size, ctypes.byref(self._handle)))
     self._model_version = self.model._version
+    self._model_flags_version = self.model._flags_version
 
   def _bind_io(self):
     for name, ctype in _lib.IO_FIELDS:
@@ -189,6 +190,9 @@ class BatchedPhysics:
   def _sync_model(self):
     if self.model._version != self._model_version:
       self._upload_model()
+    elif self.model._flags_version != self._model_flags_version:
+      _lib.check(self._L.b200mj_model_set_disableflags(self._handle, int(self.model.opt.disableflags)))
+      self._model_flags_version = self.model._flags_version
 
   def copy(self, share_model=False):
     """A new BatchedPhysics with the same model and a copy of the batched state (reference: engine.py:287-304)."""
