@@ -304,7 +304,7 @@ def run_gpu(args):
                     actions='uniform(-1,1) generated on device', l2='256 MB flush write between steps, inside the timed region',
                     task_ops='one CUDA-graph replay' if env._graph_task_ops else 'eager torch ops',
                     obs_gather='NCCL gather of [B,69] f64 to rank 0 each step' if world > 1 else 'n/a (1 GPU)',
-                    workspace_bytes_per_env=phys.workspace_bytes(), envs_per_block=phys.envs_per_block(),
+                    kernels=phys.describe(),
                     nconmax=model.nconmax, njmax=model.njmax),
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * model.nu * 8,
                  d2h_bytes_per_step=BATCH * (OBS_DIM + 2) * 8 * (world if world > 1 else 1)),

@@ -2089,6 +2089,18 @@ int64_t b200mj_launch_count(void) { return g_launches; }
 int64_t b200mj_workspace_bytes(const b200mj_model* m) { return m ? (int64_t)m->smem_per_env : -1; }
 int b200mj_envs_per_block(const b200mj_model* m) { return m ? m->envs_per_block : -1; }
 
+int b200mj_describe(const b200mj_model* M, char* buf, int n) {
+  if (!M || !buf || n <= 0) return -1;
+  int w = snprintf(buf, n, "{\"fused_workspace_bytes\": %zu, \"fused_envs_per_cta\": %d, \"pos_workspace_bytes\": %zu, \"pos_envs_per_cta\": %d, "
+                   "\"handover_bytes_per_env\": %zu, \"acc_buckets\": [", M->smem_per_env, M->envs_per_block, M->smem_pos, M->epb_pos,
+                   (size_t)(M->hand.total + M->hand2.total) * sizeof(double));
+  for (int b = 0; b < M->nbucket && w < n; b++)
+    w += snprintf(buf + w, n - w, "%s{\"rows\": %d, \"workspace_bytes\": %zu, \"last_step_workspace_bytes\": %zu}", b ? ", " : "",
+                  M->rows_cap[b], M->smem_acc_b[b], M->smem_accs_b[b]);
+  if (w < n) w += snprintf(buf + w, n - w, "]}");
+  return w < n ? 0 : -1;
+}
+
 int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int nr, b200mj_model** out) {
   if (!idata || !rdata || !out || ni <= 0 || nr <= 0) return -1;
   b200mj_model* M = new b200mj_model();

@@ -36,7 +36,7 @@ STEP_LEGACY, STEP_FULL_FINAL, STEP_SENSORS = 1, 2, 4
 
 # every symbol include/b200mj.h declares
 SYMBOLS = ('b200mj_model_create', 'b200mj_model_destroy', 'b200mj_model_set_disableflags', 'b200mj_model_set_capacity',
-           'b200mj_step', 'b200mj_forward', 'b200mj_step_host', 'b200mj_workspace_bytes', 'b200mj_envs_per_block',
+           'b200mj_step', 'b200mj_forward', 'b200mj_step_host', 'b200mj_workspace_bytes', 'b200mj_envs_per_block', 'b200mj_describe',
            'b200mj_launch_count', 'b200mj_error_string', 'b200mj_version')
 
 _lib = None
@@ -72,6 +72,8 @@ def load():
   L.b200mj_workspace_bytes.argtypes = [vp]
   L.b200mj_workspace_bytes.restype = ctypes.c_int64
   L.b200mj_envs_per_block.argtypes = [vp]
+  L.b200mj_describe.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+  L.b200mj_describe.restype = ctypes.c_int
   L.b200mj_launch_count.restype = ctypes.c_int64
   L.b200mj_error_string.argtypes = [ctypes.c_int]
   L.b200mj_error_string.restype = ctypes.c_char_p

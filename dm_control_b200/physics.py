@@ -354,5 +354,12 @@ class BatchedPhysics:
   def workspace_bytes(self):
     return int(self._L.b200mj_workspace_bytes(self._handle))
 
+  def describe(self):
+    """Kernel workspaces of this model (fused / position / acceleration row-buckets), as a dict."""
+    import json
+    buf = ctypes.create_string_buffer(2048)
+    _lib.check(self._L.b200mj_describe(self._handle, buf, 2048))
+    return json.loads(buf.value.decode())
+
   def envs_per_block(self):
     return int(self._L.b200mj_envs_per_block(self._handle))

@@ -10,7 +10,7 @@
  *   b200mj_forward        <- mujoco.mj_forward (+ actuation-disabled form)  mujoco/engine.py:306-343
  *   b200mj_step_host      <- the same step as seen by rl/control.py:99-127 with HOST action/observation
  *                            buffers (host<->device copies inside the call)
- *   b200mj_workspace_bytes / b200mj_launch_count / b200mj_last_kernel_ms : instrumentation
+ *   b200mj_workspace_bytes / b200mj_envs_per_block / b200mj_describe / b200mj_launch_count : instrumentation
  *
  * Conventions: all `*_dev` pointers are device pointers on the current CUDA device; batched arrays are
  * row-major [batch, n] (one environment's values contiguous: one warp owns one environment and reads its
@@ -108,6 +108,8 @@ int b200mj_step_host(const b200mj_model* m, const b200mj_io* io, int batch, int 
 /* instrumentation */
 int64_t b200mj_workspace_bytes(const b200mj_model* m);   /* shared memory per environment (bytes) */
 int b200mj_envs_per_block(const b200mj_model* m);
+/* JSON description of the kernel workspaces (fused, position, acceleration row-buckets) into buf[n]; 0 ok. */
+int b200mj_describe(const b200mj_model* m, char* buf, int n);
 int64_t b200mj_launch_count(void);                        /* kernels launched by this library so far */
 const char* b200mj_error_string(int code);
 const char* b200mj_version(void);
