@@ -219,73 +219,110 @@ __device__ __forceinline__ double dot_rows(const double* a, const double* b, int
   return (s0 + s1) + (s2 + s3);
 }
 
-__device__ __noinline__ void chol_factor(const double* A, double* Lm, double* dinv, int n, int ld, int lane) {
+// Symmetric nv x nv matrices (M, the Newton Hessian, their Cholesky factors) are stored as PACKED lower triangles:
+// element (i, j <= i) at tri(i) + j. Rows stay contiguous (what the left-looking factorisation and the triangular
+// solves walk), lane-strided row starts tri(lane) hit distinct banks (triangular numbers are a permutation mod 2^k),
+// and two packed triangles cost 0.52 of one dense matrix: the acceleration kernels hold 16 instead of 11
+// environments per SM.
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// row i of (symmetric S) * v from the packed lower triangle; accumulation order identical to dot_rows
+__device__ __forceinline__ double symv_row(const double* Sp, const double* v, int n, int i) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const double* Si = Sp + tri(i);        // row i, columns <= i
+  const double* Sc = Sp + i;             // column i below the diagonal: Sc[tri(k)], k > i
+  int k = 0, tk = 0;
+  _Pragma("unroll 1") for (; k + 4 <= n; k += 4) {
+    const int t1 = tk + k + 1, t2 = t1 + k + 2, t3 = t2 + k + 3;
+    s0 += (k <= i ? Si[k] : Sc[tk]) * v[k];
+    s1 += (k + 1 <= i ? Si[k + 1] : Sc[t1]) * v[k + 1];
+    s2 += (k + 2 <= i ? Si[k + 2] : Sc[t2]) * v[k + 2];
+    s3 += (k + 3 <= i ? Si[k + 3] : Sc[t3]) * v[k + 3];
+    tk = t3 + k + 4;
+  }
+  _Pragma("unroll 1") for (; k < n; k++) { s0 += (k <= i ? Si[k] : Sc[tk]) * v[k]; tk += k + 1; }
+  return (s0 + s1) + (s2 + s3);
+}
+
+__device__ __noinline__ void chol_factor(const double* A, double* Lm, double* dinv, int n, int lane) {
   // left-looking, one row (two when n > 32) per lane; the pivot travels by shuffle, so one sync per column.
   // dinv[j] = 1 / L[j][j] is kept so that neither the factor nor the triangular solves divide.
+  // A and Lm are packed lower triangles and may alias (column j only reads columns < j and A[.][j]).
   if (n <= 32) {
-    const double* Li = Lm + lane * ld;
+    const int ti = tri(lane);
+    const double* Li = Lm + ti;
+    int tj = 0;
     _Pragma("unroll 1") for (int j = 0; j < n; j++) {
       double t = 0;
-      if (lane >= j && lane < n) t = A[lane * ld + j] - dot_rows(Li, Lm + j * ld, j);
+      if (lane >= j && lane < n) t = A[ti + j] - dot_rows(Li, Lm + tj, j);
       double piv = __shfl_sync(FULL, t, j);
       if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
       double inv = rsqrt(piv);
-      if (lane == j) { Lm[j * ld + j] = piv * inv; dinv[j] = inv; }
-      else if (lane > j && lane < n) Lm[lane * ld + j] = t * inv;
+      if (lane == j) { Lm[tj + j] = piv * inv; dinv[j] = inv; }
+      else if (lane > j && lane < n) Lm[ti + j] = t * inv;
       __syncwarp();
+      tj += j + 1;
     }
     return;
   }
+  const int i0 = lane, i1 = lane + 32, ti0 = tri(i0), ti1 = tri(i1);
+  int tj = 0;
   _Pragma("unroll 1") for (int j = 0; j < n; j++) {
     double t0 = 0, t1 = 0;
-    int i0 = lane, i1 = lane + 32;
-    const double* Lj = Lm + j * ld;
-    if (i0 >= j && i0 < n) t0 = A[i0 * ld + j] - dot_rows(Lm + i0 * ld, Lj, j);
-    if (i1 >= j && i1 < n) t1 = A[i1 * ld + j] - dot_rows(Lm + i1 * ld, Lj, j);
+    const double* Lj = Lm + tj;
+    if (i0 >= j && i0 < n) t0 = A[ti0 + j] - dot_rows(Lm + ti0, Lj, j);
+    if (i1 >= j && i1 < n) t1 = A[ti1 + j] - dot_rows(Lm + ti1, Lj, j);
     double piv = __shfl_sync(FULL, j < 32 ? t0 : t1, j & 31);
     if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
     double inv = rsqrt(piv);
-    if (i0 == j || i1 == j) { Lm[j * ld + j] = piv * inv; dinv[j] = inv; }
-    if (i0 > j && i0 < n) Lm[i0 * ld + j] = t0 * inv;
-    if (i1 > j && i1 < n) Lm[i1 * ld + j] = t1 * inv;
+    if (i0 == j || i1 == j) { Lm[tj + j] = piv * inv; dinv[j] = inv; }
+    if (i0 > j && i0 < n) Lm[ti0 + j] = t0 * inv;
+    if (i1 > j && i1 < n) Lm[ti1 + j] = t1 * inv;
     __syncwarp();
+    tj += j + 1;
   }
 }
 
-// solve (L L^T) x = b; b, x are workspace vectors (may alias); n <= 64
-__device__ __noinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int ld, int lane) {
+// solve (L L^T) x = b; L packed; b, x are workspace vectors (may alias); n <= 64
+__device__ __noinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int lane) {
   if (n <= 32) {
     double xi = lane < n ? b[lane] : 0.0;
-    const double* Li = Lm + lane * ld;
+    const double* Li = Lm + tri(lane);
     _Pragma("unroll 1") for (int j = 0; j < n; j++) {          // forward: L y = b
       double yj = __shfl_sync(FULL, xi, j) * dinv[j];
       if (lane == j) xi = yj; else if (lane > j && lane < n) xi -= Li[j] * yj;
     }
+    int tj = tri(n - 1);
     _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {      // backward: L^T x = y
       double yj = __shfl_sync(FULL, xi, j) * dinv[j];
-      if (lane == j) xi = yj; else if (lane < j) xi -= Lm[j * ld + lane] * yj;
+      if (lane == j) xi = yj; else if (lane < j) xi -= Lm[tj + lane] * yj;
+      tj -= j;
     }
     __syncwarp();
     if (lane < n) x[lane] = xi;
     __syncwarp();
     return;
   }
-  double x0 = lane < n ? b[lane] : 0.0, x1 = lane + 32 < n ? b[lane + 32] : 0.0;
+  const int i1 = lane + 32;
+  const double* L0 = Lm + tri(lane); const double* L1 = Lm + tri(i1);
+  double x0 = lane < n ? b[lane] : 0.0, x1 = i1 < n ? b[i1] : 0.0;
   _Pragma("unroll 1") for (int j = 0; j < n; j++) {
     double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
     double yj = v * dinv[j];
-    if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= Lm[lane * ld + j] * yj; if (lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
-    else { if (lane + 32 == j) x1 = yj; else if (lane + 32 > j && lane + 32 < n) x1 -= Lm[(lane + 32) * ld + j] * yj; }
+    if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= L0[j] * yj; if (i1 < n) x1 -= L1[j] * yj; }
+    else { if (i1 == j) x1 = yj; else if (i1 > j && i1 < n) x1 -= L1[j] * yj; }
   }
+  int tj = tri(n - 1);
   _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {
     double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
     double yj = v * dinv[j];
-    if (j < 32) { if (lane == j) x0 = yj; else if (lane < j) x0 -= Lm[j * ld + lane] * yj; }
-    else { if (lane + 32 == j) x1 = yj; else if (lane + 32 < j) x1 -= Lm[j * ld + lane + 32] * yj; if (lane < n) x0 -= Lm[j * ld + lane] * yj; }
+    if (j < 32) { if (lane == j) x0 = yj; else if (lane < j) x0 -= Lm[tj + lane] * yj; }
+    else { if (i1 == j) x1 = yj; else if (i1 < j) x1 -= Lm[tj + i1] * yj; if (lane < n) x0 -= Lm[tj + lane] * yj; }
+    tj -= j;
   }
   __syncwarp();
   if (lane < n) x[lane] = x0;
-  if (lane + 32 < n) x[lane + 32] = x1;
+  if (i1 < n) x[i1] = x1;
   __syncwarp();
 }
 
@@ -481,7 +518,7 @@ __device__ __forceinline__ void crb_and_factor(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double* crb = W(crb); double* M = c.pM;
   _Pragma("unroll 1") for (int i = lane; i < 10 * m.nbody; i += 32) crb[i] = W(cinert)[i];
-  _Pragma("unroll 1") for (int i = lane; i < nv * ld; i += 32) M[i] = 0;
+  _Pragma("unroll 1") for (int i = lane; i < tri(nv); i += 32) M[i] = 0;
   __syncwarp();
   tree_accumulate(c, crb, 10, false);
   FOR_LANES(i, nv) {
@@ -493,7 +530,7 @@ __device__ __forceinline__ void crb_and_factor(const Ctx& c) {
       double s = 0;
       for (int k = 0; k < 6; k++) s += cj[k] * buf[k];
       if (j == i) s += m.dof_armature[i];
-      M[i * ld + j] = s; M[j * ld + i] = s;
+      M[tri(i) + j] = s;      // packed lower triangle: j walks the ancestors of i, so j <= i
     }
   }
   __syncwarp();
@@ -1136,8 +1173,8 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
   }
   __syncwarp();
   // factor M into the H buffer (free until the Newton solver assembles its Hessian there)
-  chol_factor(W(M), W(H), W(dinv), nv, m.ldv, lane);
-  chol_solve(W(H), W(dinv), W(smooth), W(qaccs), nv, m.ldv, lane);
+  chol_factor(W(M), W(H), W(dinv), nv, lane);
+  chol_solve(W(H), W(dinv), W(smooth), W(qaccs), nv, lane);
 }
 
 // --- Newton solver ---------------------------------------------------------------------------------
@@ -1146,7 +1183,7 @@ struct Primal { double cost, gauss; int nact, changed; };
 // Ma = M qacc ; jar = J qacc - aref
 __device__ __forceinline__ void compute_Ma_jar(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
-  FOR_LANES(i, nv) W(Ma)[i] = dot_rows(W(M) + i * ld, W(qacc), nv);
+  FOR_LANES(i, nv) W(Ma)[i] = symv_row(W(M), W(qacc), nv, i);
   FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * ld, W(qacc), nv) - W(aref)[r];
   __syncwarp();
 }
@@ -1202,8 +1239,9 @@ __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int n
     _Pragma("unroll 1") for (int j = lane; j < nv; j += 32) {
       _Pragma("unroll 1") for (int i0 = (j & ~7); i0 < nv; i0 += 8) {
         double acc[8];
+        const int t0 = tri(i0) + j;      // packed (i0 + q, j) sits at t0 + q * i0 + q (q + 1) / 2; rows above the diagonal are skipped
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = (i0 + q < nv) ? W(M)[(i0 + q) * ld + j] : 0.0;
+        for (int q = 0; q < 8; q++) acc[q] = (i0 + q < nv && i0 + q >= j) ? W(M)[t0 + q * i0 + ((q * (q + 1)) >> 1)] : 0.0;
         _Pragma("unroll 1") for (int a = 0; a < nact; a++) {
           int r = alist[a];
           const double* Jr = W(J) + r * ld;
@@ -1212,13 +1250,13 @@ __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int n
           for (int q = 0; q < 8; q++) if (i0 + q < nv) acc[q] += Jr[i0 + q] * sj;
         }
 #pragma unroll
-        for (int q = 0; q < 8; q++) if (i0 + q < nv) W(H)[(i0 + q) * ld + j] = acc[q];
+        for (int q = 0; q < 8; q++) if (i0 + q < nv && i0 + q >= j) W(H)[t0 + q * i0 + ((q * (q + 1)) >> 1)] = acc[q];
       }
     }
     __syncwarp();
-    chol_factor(W(H), W(H), W(dinv), nv, ld, lane);   // in place: column j only reads columns < j and A[.][j]
+    chol_factor(W(H), W(H), W(dinv), nv, lane);   // in place
   }
-  chol_solve(W(H), W(dinv), W(grad), W(search), nv, ld, lane);
+  chol_solve(W(H), W(dinv), W(grad), W(search), nv, lane);
   FOR_LANES(i, nv) W(search)[i] = -W(search)[i];
   __syncwarp();
   return gnorm;
@@ -1247,7 +1285,7 @@ __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Prim
   double gtol = m.tolerance * m.ls_tolerance * snorm * (m.meaninertia * max(1, nv));
   double g1 = 0, g2 = 0;
   FOR_LANES(i, nv) {
-    double s = dot_rows(W(M) + i * ld, W(search), nv);
+    double s = symv_row(W(M), W(search), nv, i);
     W(Mv)[i] = s;
     g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
   }
@@ -1583,11 +1621,13 @@ __device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv; double h = m.timestep;
   advance_act(c, W(act), W(actdot), 1.0, h);
   if (m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
-    _Pragma("unroll 1") for (int j = lane; j < nv; j += 32) _Pragma("unroll 1") for (int i = j; i < nv; i++) W(H)[i * ld + j] = W(M)[i * ld + j] + (i == j ? h * m.dof_damping[i] : 0.0);
+    _Pragma("unroll 1") for (int i = lane; i < tri(nv); i += 32) W(H)[i] = W(M)[i];
     FOR_LANES(i, nv) W(tmpv)[i] = W(smooth)[i] + W(qcon)[i];
     __syncwarp();
-    chol_factor(W(H), W(H), W(dinv), nv, ld, lane);
-    chol_solve(W(H), W(dinv), W(tmpv), W(tmpv), nv, ld, lane);
+    FOR_LANES(i, nv) W(H)[tri(i) + i] += h * m.dof_damping[i];
+    __syncwarp();
+    chol_factor(W(H), W(H), W(dinv), nv, lane);
+    chol_solve(W(H), W(dinv), W(tmpv), W(tmpv), nv, lane);
     FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
   } else FOR_LANES(i, nv) W(qvel)[i] += h * W(qacc)[i];
   FOR_LANES(i, nv) W(qaccws)[i] = W(qacc)[i];
@@ -1620,7 +1660,7 @@ __device__ __forceinline__ void write_outputs(const Ctx& c, const b200mj_io& io,
         if (io.site_xmat) for (int i = 0; i < 9; i++) io.site_xmat[(e * m.nsite + s) * 9 + i] = mm[i];
       }
     }
-    if (io.qM) _Pragma("unroll 1") for (int i = lane; i < m.nv * m.nv; i += 32) io.qM[e * m.nv * m.nv + i] = c.pM[(i / m.nv) * m.ldv + (i % m.nv)];
+    if (io.qM) _Pragma("unroll 1") for (int i = lane; i < m.nv * m.nv; i += 32) { int r = i / m.nv, q = i % m.nv; io.qM[e * m.nv * m.nv + i] = c.pM[r >= q ? tri(r) + q : tri(q) + r]; }
     if (io.ncon && lane == 0) io.ncon[e] = ncon;
     if (io.nefc && lane == 0) io.nefc[e] = nefc;
     FOR_LANES(k, ncon) {
@@ -1895,7 +1935,7 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
                      W(bias)[i] = hrow[H.bias + i]; W(passive)[i] = hrow[H.passive + i]; }
   FOR_LANES(i, m.na) W(act)[i] = io.act[e * m.na + i];
   FOR_LANES(i, m.nu) W(ctrl)[i] = io.ctrl ? io.ctrl[e * m.nu + i] : 0.0;
-  copy_row(W(M), hrow + H.M, nv * ld, lane);
+  copy_row(W(M), hrow + H.M, tri(nv), lane);
   copy_row(W(J), hrow + H.J, nefc * ld, lane);
   FOR_LANES(r, nefc) { W(efcD)[r] = hrow[H.efcD + r]; W(aref)[r] = hrow[H.aref + r];
                        reinterpret_cast<int*>(W(eqflag))[r] = reinterpret_cast<const int*>(hrow + H.eqflag)[r]; W(efcSD)[r] = 0; }
@@ -1964,6 +2004,7 @@ static void build_layout(b200mj_model* M) {
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };   // keep 16-byte alignment
   int nv = m.nv, nb = m.nbody, ld = m.ldv, nj = m.njmax;
+  const int ntri = nv * (nv + 1) / 2;   // packed lower triangle (M, H)
   L.qpos = take(m.nq); L.qvel = take(nv); L.act = take(m.na); L.ctrl = take(m.nu); L.qaccws = take(nv); L.actdot = take(m.na);
   L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb); L.xipos = take(3 * nb);
   L.scom = take(3 * nb); L.slinvel = take(3 * nb);
@@ -1974,10 +2015,10 @@ static void build_layout(b200mj_model* M) {
   int h0 = o;
   L.crb = take(10 * nb); L.cacc = take(6 * nb); L.cfrc = take(6 * nb);
   L.gxpos = take(3 * m.ngeom); L.gxmat = take(9 * m.ngeom); L.xanchor = take(3 * m.njnt); L.xaxis = take(3 * m.njnt);
-  if (o - h0 < nv * ld) take(nv * ld - (o - h0));
+  if (o - h0 < ntri) take(ntri - (o - h0));
   L.H = h0;
   L.tenlen = take(m.ntendon); L.tenJ = take(m.ntendon * ld); L.actforce = take(m.nu);
-  L.M = take(nv * ld); L.dinv = take(nv);
+  L.M = take(ntri); L.dinv = take(nv);
   L.J = take((m.npair > 0 && nj * ld < STAGE_DOUBLES) ? STAGE_DOUBLES : nj * ld); L.efcD = take(nj); L.efcSD = take(nj); L.aref = take(nj); L.jar = take(nj); L.jv = take(nj);
   L.force = take(nj); L.eqflag = take((nj + 1) / 2); L.actlist = take((nj + 1) / 2);
   L.bias = take(nv); L.passive = take(nv); L.qfact = take(nv); L.smooth = take(nv); L.qaccs = take(nv); L.qacc = take(nv);
@@ -2015,7 +2056,7 @@ static void build_layout(b200mj_model* M) {
       o = 0;
       A.qpos = take(m.nq); A.qvel = take(nv); A.act = take(m.na); A.ctrl = take(m.nu); A.qaccws = take(nv); A.actdot = take(m.na);
       A.tenlen = take(m.ntendon); A.tenJ = take(m.ntendon * ld); A.actforce = take(m.nu);
-      A.M = take(nv * ld); A.H = take(nv * ld); A.dinv = take(nv);
+      A.M = take(ntri); A.H = take(ntri); A.dinv = take(nv);
       A.J = take(rows * ld); A.efcD = take(rows); A.efcSD = take(rows); A.aref = take(rows); A.jar = take(rows); A.jv = take(rows);
       A.force = take(rows); A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
       A.bias = take(nv); A.passive = take(nv); A.qfact = take(nv); A.smooth = take(nv); A.qaccs = take(nv); A.qacc = take(nv);
@@ -2051,7 +2092,7 @@ static void build_layout(b200mj_model* M) {
     }
     Hand& Hd = M->hand;
     o = 0;
-    Hd.M = take(nv * ld); Hd.J = take(nj * ld); Hd.efcD = take(nj); Hd.aref = take(nj); Hd.eqflag = take((nj + 1) / 2);
+    Hd.M = take(ntri); Hd.J = take(nj * ld); Hd.efcD = take(nj); Hd.aref = take(nj); Hd.eqflag = take((nj + 1) / 2);
     Hd.bias = take(nv); Hd.passive = take(nv); Hd.tenlen = take(m.ntendon); Hd.tenJ = take(m.ntendon * ld); Hd.counts = take(2);
     Hd.total = o;
     Hand2& H2 = M->hand2;
@@ -2242,6 +2283,8 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   static int ngroups_env = -1;
   if (ngroups_env < 0) { const char* e = getenv("B200MJ_GROUPS"); ngroups_env = e ? atoi(e) : 1; if (ngroups_env < 1) ngroups_env = 1; if (ngroups_env > 3) ngroups_env = 3; }
   int ngroups = (all_split && batch >= 2048) ? ngroups_env : 1;
+  static int acc_pad = -1;    // occupancy experiments only: extra dynamic shared memory per acceleration CTA
+  if (acc_pad < 0) { const char* e = getenv("B200MJ_ACC_PAD"); acc_pad = e ? atoi(e) : 0; }
   if (ngroups > 1) cudaEventRecord(M->ev_fork, st);
   for (int g = 0; g < ngroups; g++) {
     const int e0 = (int)((long long)batch * g / ngroups), e1 = (int)((long long)batch * (g + 1) / ngroups), cnt = e1 - e0;
@@ -2258,9 +2301,9 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         int gt = b == 0 ? -1 : M->rows_cap[b - 1], le = M->rows_cap[b];
         cudaStream_t sb = b == 0 ? sm : M->gaux[g][b];     // buckets are independent: let them share the SMs
         if (b > 0) cudaStreamWaitEvent(sb, M->ev_pos[g], 0);
-        if (last) b200mj_acclast_kernel<<<cnt, 32, M->smem_accs_b[b], sb>>>(M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        if (last) b200mj_acclast_kernel<<<cnt, 32, M->smem_accs_b[b] + acc_pad, sb>>>(M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                             e1, 0, s == 0, gt, le, flags, e0);
-        else b200mj_acc_kernel<<<cnt, 32, M->smem_acc_b[b], sb>>>(M->dm, M->lay_acc_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        else b200mj_acc_kernel<<<cnt, 32, M->smem_acc_b[b] + acc_pad, sb>>>(M->dm, M->lay_acc_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                   e1, 0, s == 0, gt, le, flags, e0);
         if (b > 0) { cudaEventRecord(M->ev_acc[g][b], sb); cudaStreamWaitEvent(sm, M->ev_acc[g][b], 0); }
         g_launches++;
