@@ -53,6 +53,7 @@ struct Lay {
   int con;                               // contact records, 16 doubles each
   int rk;                                // RK4 scratch: X0q, X0v, X0a, accv, acca, accd
   int sens;                              // sensordata staging
+  int vold;                              // last-step acceleration kernel: qvel before integration (for rne_post_constraint)
   int total;
 };
 
@@ -1942,15 +1943,6 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   FOR_LANES(t, m.ntendon) W(tenlen)[t] = hrow[H.tenlen + t];
   copy_row(W(tenJ), hrow + H.tenJ, m.ntendon * ld, lane);
   const bool want_sens = LAST && (flags & B200MJ_STEP_SENSORS) != 0;
-  if (want_sens) {
-    const double* d2 = hand2 + e * H2.total;
-#define UNDUMP(dst, src, n) copy_row(W(dst), d2 + H2.src, (n), lane);
-    UNDUMP(xpos, xpos, 3 * m.nbody) UNDUMP(xquat, xquat, 4 * m.nbody) UNDUMP(xmat, xmat, 9 * m.nbody) UNDUMP(xipos, xipos, 3 * m.nbody)
-    UNDUMP(scom, scom, 3 * m.nbody) UNDUMP(cinert, cinert, 10 * m.nbody) UNDUMP(cdof, cdof, 6 * m.nv) UNDUMP(cdofdot, cdofdot, 6 * m.nv)
-    UNDUMP(cvel, cvel, 6 * m.nbody) UNDUMP(con, con, ncon * CON_STRIDE)
-#undef UNDUMP
-    if (io.sensordata) FOR_LANES(i, m.nsensordata) W(sens)[i] = io.sensordata[e * m.nsensordata + i];
-  }
   double time = io.time ? io.time[e] : 0.0;
   __syncwarp();
   int w_badctrl = 0, w_badqacc = 0;
@@ -1959,14 +1951,8 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   b200mj_io io_noforce = io; io_noforce.qfrc_applied = nullptr; io_noforce.xfrc_applied = nullptr;
   fwd_acceleration(c, io_noforce, env);
   int niter = solve_newton(c, nefc);
-  if (LAST) {
-    if (want_sens) {
-      if (m.acc_sensors) rne_post_constraint(c, io_noforce, env, ncon);
-      sensors(c, 4, ncon);
-    }
-    write_outputs(c, io, env, ncon, nefc, niter, false, true, false);
-    if (want_sens && io.sensordata) FOR_LANES(i, m.nsensordata) io.sensordata[e * m.nsensordata + i] = W(sens)[i];
-  }
+  if (LAST) write_outputs(c, io, env, ncon, nefc, niter, false, true, false);
+  if (want_sens) FOR_LANES(i, nv) W(vold)[i] = W(qvel)[i];
   if (check_bad(c, W(qacc), nv)) { w_badqacc = 1; reset_state(c, &time); }
   else euler_step(c, &time);
   // ---- store state ----
@@ -1978,6 +1964,24 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
     int* w = io.warning + e * BMJ_NWARNING;
     if (w_badctrl) w[BMJ_WARN_BADCTRL] += 1;
     if (w_badqacc) w[BMJ_WARN_BADQACC] += 1;
+  }
+  if (want_sens) {
+    // Acceleration-stage sensors of the step just taken (MuJoCo evaluates them in mj_forward, before the state
+    // advances): the solver's storage is dead now, so the position-stage dump is loaded over it (a workspace that
+    // held both at once allowed 6 instead of 14 environments per SM).
+    __syncwarp();
+    FOR_LANES(i, nv) W(qvel)[i] = W(vold)[i];
+    const double* d2 = hand2 + e * H2.total;
+#define UNDUMP(dst, src, n) copy_row(W(dst), d2 + H2.src, (n), lane);
+    UNDUMP(xpos, xpos, 3 * m.nbody) UNDUMP(xquat, xquat, 4 * m.nbody) UNDUMP(xmat, xmat, 9 * m.nbody) UNDUMP(xipos, xipos, 3 * m.nbody)
+    UNDUMP(scom, scom, 3 * m.nbody) UNDUMP(cinert, cinert, 10 * m.nbody) UNDUMP(cdof, cdof, 6 * m.nv) UNDUMP(cdofdot, cdofdot, 6 * m.nv)
+    UNDUMP(cvel, cvel, 6 * m.nbody) UNDUMP(con, con, ncon * CON_STRIDE)
+#undef UNDUMP
+    if (io.sensordata) FOR_LANES(i, m.nsensordata) W(sens)[i] = io.sensordata[e * m.nsensordata + i];
+    __syncwarp();
+    if (m.acc_sensors) rne_post_constraint(c, io_noforce, env, ncon);
+    sensors(c, 4, ncon);
+    if (io.sensordata) FOR_LANES(i, m.nsensordata) io.sensordata[e * m.nsensordata + i] = W(sens)[i];
   }
 }
 
@@ -2056,16 +2060,23 @@ static void build_layout(b200mj_model* M) {
       o = 0;
       A.qpos = take(m.nq); A.qvel = take(nv); A.act = take(m.na); A.ctrl = take(m.nu); A.qaccws = take(nv); A.actdot = take(m.na);
       A.tenlen = take(m.ntendon); A.tenJ = take(m.ntendon * ld); A.actforce = take(m.nu);
+      A.force = take(rows); A.qacc = take(nv); A.vold = take(with_sens ? nv : 0);
+      // Everything below is dead once the state has been integrated; the sensor-carrying variant then re-uses the
+      // storage for the position-stage dump that rne_post_constraint and the acceleration-stage sensors read.
+      const int u0 = o;
       A.M = take(ntri); A.H = take(ntri); A.dinv = take(nv);
       A.J = take(rows * ld); A.efcD = take(rows); A.efcSD = take(rows); A.aref = take(rows); A.jar = take(rows); A.jv = take(rows);
-      A.force = take(rows); A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
-      A.bias = take(nv); A.passive = take(nv); A.qfact = take(nv); A.smooth = take(nv); A.qaccs = take(nv); A.qacc = take(nv);
+      A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
+      A.bias = take(nv); A.passive = take(nv); A.qfact = take(nv); A.smooth = take(nv); A.qaccs = take(nv);
       A.qcon = take(nv); A.Ma = take(nv); A.grad = take(nv); A.search = take(nv); A.Mv = take(nv); A.tmpv = take(nv);
       if (with_sens) {
+        const int acc_end = o;
+        o = u0;
         A.xpos = take(3 * nb); A.xquat = take(4 * nb); A.xmat = take(9 * nb); A.xipos = take(3 * nb); A.scom = take(3 * nb);
         A.cinert = take(10 * nb); A.cdof = take(6 * nv); A.cdofdot = take(6 * nv); A.cvel = take(6 * nb);
         A.cacc = take(6 * nb); A.cfrc = take(6 * nb); A.cfrcext = take(6 * nb); A.con = take(m.nconmax * CON_STRIDE);
         A.sens = take(m.nsensordata);
+        if (o < acc_end) o = acc_end;
       }
       A.total = o;
       return (size_t)o * sizeof(double);
