@@ -245,27 +245,142 @@ __device__ __forceinline__ double symv_row(const double* Sp, const double* v, in
   return (s0 + s1) + (s2 + s3);
 }
 
-__device__ __noinline__ void chol_factor(const double* A, double* Lm, double* dinv, int n, int lane) {
-  // left-looking, one row (two when n > 32) per lane; the pivot travels by shuffle, so one sync per column.
-  // dinv[j] = 1 / L[j][j] is kept so that neither the factor nor the triangular solves divide.
-  // A and Lm are packed lower triangles and may alias (column j only reads columns < j and A[.][j]).
+// forward substitution L y = b (L packed, n <= 64); b and y may alias
+__device__ __noinline__ void chol_forward(const double* Lm, const double* dinv, const double* b, double* y, int n, int lane) {
   if (n <= 32) {
-    const int ti = tri(lane);
-    const double* Li = Lm + ti;
-    int tj = 0;
+    double xi = lane < n ? b[lane] : 0.0;
+    const double* Li = Lm + tri(lane);
     _Pragma("unroll 1") for (int j = 0; j < n; j++) {
-      double t = 0;
-      if (lane >= j && lane < n) t = A[ti + j] - dot_rows(Li, Lm + tj, j);
-      double piv = __shfl_sync(FULL, t, j);
-      if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
-      double inv = rsqrt(piv);
-      if (lane == j) { Lm[tj + j] = piv * inv; dinv[j] = inv; }
-      else if (lane > j && lane < n) Lm[ti + j] = t * inv;
+      double yj = __shfl_sync(FULL, xi, j) * dinv[j];
+      if (lane == j) xi = yj; else if (lane > j && lane < n) xi -= Li[j] * yj;
+    }
+    __syncwarp();
+    if (lane < n) y[lane] = xi;
+    __syncwarp();
+    return;
+  }
+  const int i1 = lane + 32;
+  const double* L0 = Lm + tri(lane); const double* L1 = Lm + tri(i1);
+  double x0 = lane < n ? b[lane] : 0.0, x1 = i1 < n ? b[i1] : 0.0;
+  _Pragma("unroll 1") for (int j = 0; j < n; j++) {
+    double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
+    double yj = v * dinv[j];
+    if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= L0[j] * yj; if (i1 < n) x1 -= L1[j] * yj; }
+    else { if (i1 == j) x1 = yj; else if (i1 > j && i1 < n) x1 -= L1[j] * yj; }
+  }
+  __syncwarp();
+  if (lane < n) y[lane] = x0;
+  if (i1 < n) y[i1] = x1;
+  __syncwarp();
+}
+
+// backward substitution L^T x = y (L packed, n <= 64); y and x may alias
+__device__ __noinline__ void chol_back(const double* Lm, const double* dinv, const double* y, double* x, int n, int lane) {
+  if (n <= 32) {
+    double xi = lane < n ? y[lane] : 0.0;
+    int tj = tri(n - 1);
+    _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {
+      double xj = __shfl_sync(FULL, xi, j) * dinv[j];
+      if (lane == j) xi = xj; else if (lane < j) xi -= Lm[tj + lane] * xj;
+      tj -= j;
+    }
+    __syncwarp();
+    if (lane < n) x[lane] = xi;
+    __syncwarp();
+    return;
+  }
+  const int i1 = lane + 32;
+  double x0 = lane < n ? y[lane] : 0.0, x1 = i1 < n ? y[i1] : 0.0;
+  int tj = tri(n - 1);
+  _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {
+    double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
+    double xj = v * dinv[j];
+    if (j < 32) { if (lane == j) x0 = xj; else if (lane < j) x0 -= Lm[tj + lane] * xj; }
+    else { if (i1 == j) x1 = xj; else if (i1 < j) x1 -= Lm[tj + i1] * xj; if (lane < n) x0 -= Lm[tj + lane] * xj; }
+    tj -= j;
+  }
+  __syncwarp();
+  if (lane < n) x[lane] = x0;
+  if (i1 < n) x[i1] = x1;
+  __syncwarp();
+}
+
+// solve (L L^T) x = b with an existing factor
+__device__ __forceinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int lane) {
+  chol_forward(Lm, dinv, b, x, n, lane);
+  chol_back(Lm, dinv, x, x, n, lane);
+}
+
+// Cholesky factor of a packed symmetric matrix, A -> Lm (may alias), dinv[j] = 1 / L[j][j] (neither the factor nor
+// the triangular solves divide). When a right-hand side b is given, y = L^-1 b comes out as well (b, y may alias).
+//
+// n < 32: left-looking by blocks of four columns, one row per lane. The part of the four dot products that lies
+// left of the block shares its loads of the lane's own row (5 loads per 4 multiply-adds instead of 8), the four
+// accumulators are the independent chains that hide the DFMA latency, and inside the block the new columns stay in
+// registers: pivots and the 6 cross terms travel by shuffle, so there is one shared-memory round trip per block
+// instead of one per column. The right-hand side rides along as row n of the matrix on the spare lane n — the
+// forward substitution costs no extra pass.
+__device__ __noinline__ void chol_factor(const double* A, double* Lm, double* dinv, int n, int lane, const double* b, double* y) {
+  if (n < 32) {
+    const bool isrow = lane < n, isrhs = (b != nullptr) && lane == n, live = isrow || isrhs;
+    const int ti = tri(lane);
+    const double* Ai = isrow ? A + ti : (isrhs ? b : A);   // this lane's row of A (read at the block's columns)
+    double* Li = isrow ? Lm + ti : (isrhs ? y : Lm);       // this lane's row of L (idle lanes read row 0, never write)
+    int tj0 = 0;                                           // tri(j0)
+    _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += 4) {
+      const int j1 = min(j0 + 1, n - 1), j2 = min(j0 + 2, n - 1), j3 = min(j0 + 3, n - 1);   // tail block: clamp
+      const double* r0 = Lm + tj0; const double* r1 = Lm + tri(j1); const double* r2 = Lm + tri(j2); const double* r3 = Lm + tri(j3);
+      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      _Pragma("unroll 1") for (int k = 0; k < j0; k += 4) {      // j0 is a multiple of 4
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double a = Li[k + q];
+          t0 += a * r0[k + q]; t1 += a * r1[k + q]; t2 += a * r2[k + q]; t3 += a * r3[k + q];
+        }
+      }
+      const bool on0 = live && lane >= j0, on1 = live && lane >= j0 + 1 && j0 + 1 < n,
+                 on2 = live && lane >= j0 + 2 && j0 + 2 < n, on3 = live && lane >= j0 + 3 && j0 + 3 < n;
+      t0 = on0 ? Ai[j0] - t0 : 0.0; t1 = on1 ? Ai[j0 + 1] - t1 : 0.0; t2 = on2 ? Ai[j0 + 2] - t2 : 0.0; t3 = on3 ? Ai[j0 + 3] - t3 : 0.0;
+      double l0, l1 = 0, l2 = 0;
+      {
+        double piv = __shfl_sync(FULL, t0, j0);
+        if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+        const double inv = rsqrt(piv);
+        l0 = t0 * inv;
+        if (lane == j0) { Li[j0] = piv * inv; dinv[j0] = inv; } else if (on0) Li[j0] = l0;
+      }
+      if (j0 + 1 < n) {
+        t1 -= l0 * __shfl_sync(FULL, l0, j0 + 1);
+        double piv = __shfl_sync(FULL, t1, j0 + 1);
+        if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+        const double inv = rsqrt(piv);
+        l1 = t1 * inv;
+        if (lane == j0 + 1) { Li[j0 + 1] = piv * inv; dinv[j0 + 1] = inv; } else if (on1) Li[j0 + 1] = l1;
+      }
+      if (j0 + 2 < n) {
+        t2 -= l0 * __shfl_sync(FULL, l0, j0 + 2);
+        t2 -= l1 * __shfl_sync(FULL, l1, j0 + 2);
+        double piv = __shfl_sync(FULL, t2, j0 + 2);
+        if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+        const double inv = rsqrt(piv);
+        l2 = t2 * inv;
+        if (lane == j0 + 2) { Li[j0 + 2] = piv * inv; dinv[j0 + 2] = inv; } else if (on2) Li[j0 + 2] = l2;
+      }
+      if (j0 + 3 < n) {
+        t3 -= l0 * __shfl_sync(FULL, l0, j0 + 3);
+        t3 -= l1 * __shfl_sync(FULL, l1, j0 + 3);
+        t3 -= l2 * __shfl_sync(FULL, l2, j0 + 3);
+        double piv = __shfl_sync(FULL, t3, j0 + 3);
+        if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+        const double inv = rsqrt(piv);
+        if (lane == j0 + 3) { Li[j0 + 3] = piv * inv; dinv[j0 + 3] = inv; } else if (on3) Li[j0 + 3] = t3 * inv;
+      }
       __syncwarp();
-      tj += j + 1;
+      tj0 += 4 * j0 + 10;      // tri(j0 + 4) - tri(j0)
     }
     return;
   }
+  // n >= 32: two rows per lane, one column at a time; the right-hand side takes a separate pass
   const int i0 = lane, i1 = lane + 32, ti0 = tri(i0), ti1 = tri(i1);
   int tj = 0;
   _Pragma("unroll 1") for (int j = 0; j < n; j++) {
@@ -282,49 +397,7 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
     __syncwarp();
     tj += j + 1;
   }
-}
-
-// solve (L L^T) x = b; L packed; b, x are workspace vectors (may alias); n <= 64
-__device__ __noinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int lane) {
-  if (n <= 32) {
-    double xi = lane < n ? b[lane] : 0.0;
-    const double* Li = Lm + tri(lane);
-    _Pragma("unroll 1") for (int j = 0; j < n; j++) {          // forward: L y = b
-      double yj = __shfl_sync(FULL, xi, j) * dinv[j];
-      if (lane == j) xi = yj; else if (lane > j && lane < n) xi -= Li[j] * yj;
-    }
-    int tj = tri(n - 1);
-    _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {      // backward: L^T x = y
-      double yj = __shfl_sync(FULL, xi, j) * dinv[j];
-      if (lane == j) xi = yj; else if (lane < j) xi -= Lm[tj + lane] * yj;
-      tj -= j;
-    }
-    __syncwarp();
-    if (lane < n) x[lane] = xi;
-    __syncwarp();
-    return;
-  }
-  const int i1 = lane + 32;
-  const double* L0 = Lm + tri(lane); const double* L1 = Lm + tri(i1);
-  double x0 = lane < n ? b[lane] : 0.0, x1 = i1 < n ? b[i1] : 0.0;
-  _Pragma("unroll 1") for (int j = 0; j < n; j++) {
-    double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
-    double yj = v * dinv[j];
-    if (j < 32) { if (lane == j) x0 = yj; else if (lane > j && lane < n) x0 -= L0[j] * yj; if (i1 < n) x1 -= L1[j] * yj; }
-    else { if (i1 == j) x1 = yj; else if (i1 > j && i1 < n) x1 -= L1[j] * yj; }
-  }
-  int tj = tri(n - 1);
-  _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {
-    double v = __shfl_sync(FULL, j < 32 ? x0 : x1, j & 31);
-    double yj = v * dinv[j];
-    if (j < 32) { if (lane == j) x0 = yj; else if (lane < j) x0 -= Lm[tj + lane] * yj; }
-    else { if (i1 == j) x1 = yj; else if (i1 < j) x1 -= Lm[tj + i1] * yj; if (lane < n) x0 -= Lm[tj + lane] * yj; }
-    tj -= j;
-  }
-  __syncwarp();
-  if (lane < n) x[lane] = x0;
-  if (i1 < n) x[i1] = x1;
-  __syncwarp();
+  if (b) chol_forward(Lm, dinv, b, y, n, lane);
 }
 
 // bottom-up accumulation child -> parent for a [nbody, width] table. Bodies are numbered parents-first, so one
@@ -1174,8 +1247,8 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
   }
   __syncwarp();
   // factor M into the H buffer (free until the Newton solver assembles its Hessian there)
-  chol_factor(W(M), W(H), W(dinv), nv, lane);
-  chol_solve(W(H), W(dinv), W(smooth), W(qaccs), nv, lane);
+  chol_factor(W(M), W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
+  chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
 }
 
 // --- Newton solver ---------------------------------------------------------------------------------
@@ -1255,9 +1328,9 @@ __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int n
       }
     }
     __syncwarp();
-    chol_factor(W(H), W(H), W(dinv), nv, lane);   // in place
-  }
-  chol_solve(W(H), W(dinv), W(grad), W(search), nv, lane);
+    chol_factor(W(H), W(H), W(dinv), nv, lane, W(grad), W(search));   // in place, forward substitution included
+  } else chol_forward(W(H), W(dinv), W(grad), W(search), nv, lane);
+  chol_back(W(H), W(dinv), W(search), W(search), nv, lane);
   FOR_LANES(i, nv) W(search)[i] = -W(search)[i];
   __syncwarp();
   return gnorm;
@@ -1627,8 +1700,8 @@ __device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
     __syncwarp();
     FOR_LANES(i, nv) W(H)[tri(i) + i] += h * m.dof_damping[i];
     __syncwarp();
-    chol_factor(W(H), W(H), W(dinv), nv, lane);
-    chol_solve(W(H), W(dinv), W(tmpv), W(tmpv), nv, lane);
+    chol_factor(W(H), W(H), W(dinv), nv, lane, W(tmpv), W(tmpv));
+    chol_back(W(H), W(dinv), W(tmpv), W(tmpv), nv, lane);
     FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
   } else FOR_LANES(i, nv) W(qvel)[i] += h * W(qacc)[i];
   FOR_LANES(i, nv) W(qaccws)[i] = W(qacc)[i];
