@@ -45,6 +45,9 @@ class BatchedEnvironment:
     self._step_count = torch.zeros(physics.batch, dtype=torch.int64, device=physics.device)
     self._reset_next = torch.ones(physics.batch, dtype=torch.bool, device=physics.device)
     self._auto_reset = auto_reset
+    # host-side upper bound of every environment's step count: while it is below the step limit no environment can
+    # be LAST, so step() need not read `_reset_next` back (a device->host sync per step otherwise)
+    self._count_ub = float('inf')     # unknown until the first check
     # Optional: replay the task's reward/observation torch ops (~80 tiny launches) as one CUDA graph. The returned
     # reward / observation tensors are then static buffers that the next step overwrites.
     self._graph_task_ops = graph_task_ops
@@ -70,6 +73,7 @@ class BatchedEnvironment:
     self._task.initialize_episode(self._physics, None)
     self._step_count.zero_()
     self._reset_next.zero_()
+    self._count_ub = 0
     obs = self._task.get_observation(self._physics)
     B = self._physics.batch
     return TimeStep(torch.full((B,), FIRST, device=self._physics.device), None, None, obs)
@@ -93,16 +97,19 @@ class BatchedEnvironment:
     return self._graph_out
 
   def step(self, action):
-    if self._auto_reset and bool(self._reset_next.any()):
-      mask = self._reset_next
-      self._task.initialize_episode(self._physics, mask)
-      self._step_count[mask] = 0
-      self._reset_next = torch.zeros_like(mask)
+    if self._auto_reset and self._count_ub >= self._step_limit:
+      if bool(self._reset_next.any()):
+        mask = self._reset_next
+        self._task.initialize_episode(self._physics, mask)
+        self._step_count[mask] = 0
+        self._reset_next = torch.zeros_like(mask)
+      self._count_ub = int(self._step_count.max())      # slow path only: one more readback, then exact again
     self._task.before_step(action, self._physics)
     self._physics.step(self._n_sub_steps)
     self._task.after_step(self._physics)
     reward, obs = self._reward_and_observation()
     self._step_count += 1
+    self._count_ub += 1
     last = self._step_count >= self._step_limit
     self._reset_next = last
     step_type = torch.where(last, LAST, MID)
