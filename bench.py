@@ -139,12 +139,22 @@ def time_cpu(warmup_steps=5, timed_steps=150, nenv_per_proc=8, procs=None):
   return value, procs, sample, dt * 1e3 / timed_steps
 
 
+def cpu_sample_sizes(steps, warmup):
+  """The CPU arm's bounded sample of the GPU arm's workload: the same untimed settle (warmup + 1 env-steps from the
+  same family of seeded states, so the timed window sees the same contact load), the same number of timed env-steps
+  (clamped to 20..300), and enough environments per process for a few seconds of work on every core."""
+  warm = min(max(warmup, 3) + 1, 60)
+  timed = max(20, min(steps, 300))
+  nenv = max(4, min(48, 1600 // timed))
+  return warm, timed, nenv
+
+
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  steps = max(1, args.steps)
-  value, cores, sample, ms = time_cpu(max(3, min(args.warmup, 10)), max(60, min(steps * 6, 300)))
+  warm, timed, nenv = cpu_sample_sizes(max(1, args.steps), args.warmup)
+  value, cores, sample, ms = time_cpu(warm, timed, nenv)
   line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
               ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
               config=dict(workload='suite.humanoid:run, 5 physics substeps per env-step, random actions',
@@ -294,7 +304,7 @@ def run_gpu(args):
       prof = json.load(open(pj))
     cpu = None
     if world == 1 and not args.no_cpu:
-      v, cores, sample, _ = time_cpu(5, 150)
+      v, cores, sample, _ = time_cpu(*cpu_sample_sizes(args.steps, args.warmup))
       cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
