@@ -305,12 +305,6 @@ __device__ __noinline__ void chol_back(const double* Lm, const double* dinv, con
   __syncwarp();
 }
 
-// solve (L L^T) x = b with an existing factor
-__device__ __forceinline__ void chol_solve(const double* Lm, const double* dinv, const double* b, double* x, int n, int lane) {
-  chol_forward(Lm, dinv, b, x, n, lane);
-  chol_back(Lm, dinv, x, x, n, lane);
-}
-
 // Cholesky factor of a packed symmetric matrix, A -> Lm (may alias), dinv[j] = 1 / L[j][j] (neither the factor nor
 // the triangular solves divide). When a right-hand side b is given, y = L^-1 b comes out as well (b, y may alias).
 //

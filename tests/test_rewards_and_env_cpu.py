@@ -59,3 +59,75 @@ def test_compute_n_steps():
     control.compute_n_steps(0.001, 0.005)
   with pytest.raises(ValueError, match='integer multiple'):
     control.compute_n_steps(0.026, 0.005)
+
+
+# ---- BatchedEnvironment loop with a mock physics / task (the reference tests its loop the same way, --------------
+# ---- dm_control/rl/control_test.py:33-50) ---------------------------------------------------------------------------
+class _MockPhysics:
+  legacy_step = True
+
+  def __init__(self, batch):
+    self.batch, self.device = batch, torch.device('cpu')
+    self.calls = []
+
+  def timestep(self):
+    return 0.01
+
+  def step(self, n):
+    self.calls.append(('step', n))
+
+
+class _MockTask:
+  def __init__(self, physics):
+    self.resets = []
+    self._p = physics
+
+  def initialize_episode(self, physics, env_mask):
+    self.resets.append(None if env_mask is None else env_mask.clone())
+
+  def before_step(self, action, physics):
+    physics.calls.append(('before_step', None))
+
+  def after_step(self, physics):
+    physics.calls.append(('after_step', None))
+
+  def get_reward(self, physics):
+    return torch.full((physics.batch,), 0.5, dtype=torch.float64)
+
+  def get_observation(self, physics):
+    return dict(x=torch.zeros(physics.batch, 3, dtype=torch.float64))
+
+
+def test_environment_call_order_and_time_limit():
+  """rl/control.py:99-127: before_step -> physics.step(n_sub_steps) -> after_step; the step that reaches the time
+  limit is LAST, the next call re-initialises exactly those environments; no reset-flag readback in between."""
+  phys = _MockPhysics(4)
+  task = _MockTask(phys)
+  env = control.BatchedEnvironment(phys, task, time_limit=0.06, control_timestep=0.02)   # 3 control steps, 2 sub-steps
+  assert env.n_sub_steps == 2 and env.control_timestep() == pytest.approx(0.02)
+  ts = env.reset()
+  assert ts.step_type.tolist() == [control.FIRST] * 4 and ts.reward is None and len(task.resets) == 1
+  types = []
+  for _ in range(5):
+    ts = env.step(torch.zeros(4, 1))
+    types.append(int(ts.step_type[0]))
+    assert ts.reward.tolist() == [0.5] * 4 and ts.discount.tolist() == [1.0] * 4
+  assert types == [control.MID, control.MID, control.LAST, control.MID, control.MID]
+  assert phys.calls[:3] == [('before_step', None), ('step', 2), ('after_step', None)]
+  assert len(task.resets) == 2 and task.resets[1].tolist() == [True] * 4     # one masked re-initialisation, after LAST
+  # partial reset requested from outside (e.g. diverged environments): only those environments are re-initialised
+  env._reset_next = torch.tensor([False, True, False, False]); env._count_ub = float('inf')
+  env.step(torch.zeros(4, 1))
+  assert task.resets[-1].tolist() == [False, True, False, False]
+  assert env._step_count.tolist() == [3, 1, 3, 3]
+
+
+def test_environment_first_step_without_reset_initialises():
+  """control.py:102: stepping before reset() re-initialises (here: every environment, through the mask)."""
+  phys = _MockPhysics(2)
+  task = _MockTask(phys)
+  env = control.BatchedEnvironment(phys, task)
+  env.step(torch.zeros(2, 1))
+  assert len(task.resets) == 1 and task.resets[0].tolist() == [True, True]
+  env.step(torch.zeros(2, 1))
+  assert len(task.resets) == 1
