@@ -111,7 +111,16 @@ class BatchedEnvironment:
     self._step_count += 1
     self._count_ub += 1
     last = self._step_count >= self._step_limit
+    discount = torch.ones_like(reward)
+    # task termination (control.py:113-118): None = the task never terminates; otherwise a [B] tensor holding the
+    # terminal discount for the environments that end now and NaN for the others. The time limit wins (discount 1).
+    get_term = getattr(self._task, 'get_termination', None)
+    term = get_term(self._physics) if get_term is not None else None
+    if term is not None:
+      ended = ~torch.isnan(term)
+      discount = torch.where(ended & ~last, term, discount)
+      last = last | ended
+      self._count_ub = float('inf')       # episodes may end at any step: check the flags on the next call
     self._reset_next = last
     step_type = torch.where(last, LAST, MID)
-    discount = torch.ones_like(reward)
     return TimeStep(step_type, reward, discount, obs)

@@ -1,13 +1,13 @@
-"""Batched twins of the hot-path suite domains (reference: dm_control/suite/{cartpole,cheetah,humanoid,quadruped}.py).
+"""Batched twins of the hot-path suite domains (reference: dm_control/suite/{cartpole,cheetah,humanoid,lqr,quadruped}.py).
 
 `load(domain, task, batch=...)` mirrors `suite.load` (suite/__init__.py:93-114) and returns a
 `control.BatchedEnvironment`.
 """
 from __future__ import annotations
 
-from . import cartpole, cheetah, humanoid, quadruped
+from . import cartpole, cheetah, humanoid, lqr, quadruped
 
-_DOMAINS = dict(cartpole=cartpole, cheetah=cheetah, humanoid=humanoid, quadruped=quadruped)
+_DOMAINS = dict(cartpole=cartpole, cheetah=cheetah, humanoid=humanoid, lqr=lqr, quadruped=quadruped)
 
 
 def load(domain_name, task_name, batch=1, seed=0, **kw):

@@ -25,6 +25,11 @@ class Task:
   def after_step(self, physics):
     pass
 
+  def get_termination(self, physics):
+    """Reference: base.py (`get_termination` returns None = continue). Batched form: None, or a [B] tensor with the
+    terminal discount where an episode ends now and NaN elsewhere."""
+    return None
+
   def action_spec(self, physics):
     m = physics.model
     lo = torch.as_tensor(m.actuator_ctrlrange[:, 0].copy())

@@ -131,3 +131,22 @@ def test_environment_first_step_without_reset_initialises():
   assert len(task.resets) == 1 and task.resets[0].tolist() == [True, True]
   env.step(torch.zeros(2, 1))
   assert len(task.resets) == 1
+
+
+def test_environment_task_termination():
+  """control.py:113-121: a task termination ends the episode with the task's discount; the time limit wins with 1."""
+  phys = _MockPhysics(3)
+  task = _MockTask(phys)
+  nan = float('nan')
+  script = [torch.tensor([nan, nan, nan]), torch.tensor([nan, 0.0, nan]), torch.tensor([0.25, nan, nan])]
+  task.get_termination = lambda physics: script.pop(0).to(torch.float64)
+  env = control.BatchedEnvironment(phys, task, time_limit=0.03, control_timestep=0.01)     # 3 control steps
+  env.reset()
+  ts = env.step(torch.zeros(3, 1))
+  assert ts.step_type.tolist() == [control.MID] * 3 and ts.discount.tolist() == [1.0] * 3
+  ts = env.step(torch.zeros(3, 1))
+  assert ts.step_type.tolist() == [control.MID, control.LAST, control.MID] and ts.discount.tolist() == [1.0, 0.0, 1.0]
+  ts = env.step(torch.zeros(3, 1))                  # env 1 was re-initialised (count 1); envs 0 and 2 reach the time limit
+  assert task.resets[-1].tolist() == [False, True, False]
+  assert ts.step_type.tolist() == [control.LAST, control.MID, control.LAST]
+  assert ts.discount.tolist() == [1.0, 1.0, 1.0]    # time limit: discount 1 even where the task also terminated (0.25)
