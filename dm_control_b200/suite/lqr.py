@@ -108,8 +108,8 @@ class LQRLevel(base.Task):
 
   def get_termination(self, physics):
     """Discount 0 where the state norm fell below 1e-6, NaN (= keep going) elsewhere."""
-    done = physics.state_norm() < self._TERMINAL_TOL
-    return torch.where(done, torch.zeros_like(physics.data.time[:, 0]), torch.full_like(physics.data.time[:, 0], float('nan')))
+    norm = physics.state_norm()
+    return torch.where(norm < self._TERMINAL_TOL, torch.zeros_like(norm), torch.full_like(norm, float('nan')))
 
 
 def solve(mass, stiffness, damping, dt, n_controls, control_cost_coef):
