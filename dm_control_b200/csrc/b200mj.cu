@@ -12,7 +12,15 @@
 //
 // No CPU fallback exists: if this library is missing the Python facade raises.
 
+#ifdef B200MJ_CPU_EMU
+// tests/emu/cuda_emu.h: lock-step CPU emulation of the warp / CTA primitives so that the `-m "not gpu"` tests can run
+// THIS source for logic errors without a GPU. Test infrastructure only: the product library is built by nvcc without
+// this macro, and nothing in dm_control_b200/ ever loads the emulation build.
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#define B200MJ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -104,9 +112,14 @@ __device__ __forceinline__ void mul_quat(double* r, const double* a, const doubl
   double z = a[0]*b[3] + a[1]*b[2] - a[2]*b[1] + a[3]*b[0];
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
+// mju_normalize4 semantics: a quaternion whose norm is already within mjMINVAL of 1 is left untouched, which makes
+// the operation idempotent — mj_kinematics normalises qpos in place at every position stage, and step(n) must stay
+// bit-identical to n x step() (engine_test.py:627-663) although the latter passes through one more position stage
+// per call.
 __device__ __forceinline__ void normalize4(double* q) {
   double n = sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
-  if (n < BMJ_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n; }
+  if (n < BMJ_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+  else if (fabs(n - 1) > BMJ_MINVAL) { double inv = 1 / n; q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv; }
 }
 __device__ __forceinline__ void quat2mat(double* m, const double* q) {
   double q00 = q[0]*q[0], q11 = q[1]*q[1], q22 = q[2]*q[2], q33 = q[3]*q[3];
@@ -2320,7 +2333,7 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
   if (const char* pad = getenv("B200MJ_EXTRA_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
   static int sync_level = -1;
   if (sync_level < 0) { const char* sl = getenv("B200MJ_SYNC_LEVEL"); sync_level = sl ? atoi(sl) : 1; }
-  b200mj_step_kernel<<<grid, 32 * epb, smem, (cudaStream_t)stream>>>(M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level);
+  B200MJ_LAUNCH(b200mj_step_kernel, grid, 32 * epb, smem, (cudaStream_t)stream, M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
@@ -2372,7 +2385,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     const int gp = (cnt + M->epb_pos - 1) / M->epb_pos;
     for (int s = 0; s < nsplit; s++) {
       const bool last = all_split && s == nstep - 1;
-      b200mj_pos_kernel<<<gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm>>>(M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+      B200MJ_LAUNCH(b200mj_pos_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                                e1, 0, flags, last && want_sens, e0);
       g_launches++;
       if (M->nbucket > 1) cudaEventRecord(M->ev_pos[g], sm);
@@ -2385,9 +2398,9 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         int gt = b == 0 ? -1 : M->rows_cap[b - 1], le = M->rows_cap[b];
         cudaStream_t sb = b == 0 ? sm : M->gaux[g][b];     // buckets are independent: let them share the SMs
         if (b > 0) cudaStreamWaitEvent(sb, M->ev_pos[g], 0);
-        if (last) b200mj_acclast_kernel<<<cnt, 32, M->smem_accs_b[b] + acc_pad, sb>>>(M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        if (last) B200MJ_LAUNCH(b200mj_acclast_kernel, cnt, 32, M->smem_accs_b[b] + acc_pad, sb, M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                             e1, 0, s == 0, gt, le, flags, e0);
-        else b200mj_acc_kernel<<<cnt, 32, M->smem_acc_b[b] + acc_pad, sb>>>(M->dm, M->lay_acc_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        else B200MJ_LAUNCH(b200mj_acc_kernel, cnt, 32, M->smem_acc_b[b] + acc_pad, sb, M->dm, M->lay_acc_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                   e1, 0, s == 0, gt, le, flags, e0);
         if (b > 0) cudaEventRecord(M->ev_acc[g][b], sb);
         g_launches++;
@@ -2395,7 +2408,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
       for (int b = 1; b < M->nbucket; b++) cudaStreamWaitEvent(sm, M->ev_acc[g][b], 0);   // join after the main-stream bucket is queued
     }
     if (all_split) {
-      b200mj_posfinal_kernel<<<gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm>>>(M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+      B200MJ_LAUNCH(b200mj_posfinal_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                                     e1, 0, flags, 0, e0);
       g_launches++;
     }

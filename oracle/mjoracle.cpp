@@ -160,7 +160,8 @@ static inline void mul_quat(real* r, const real* a, const real* b) {
 }
 static inline void normalize4(real* q) {
   real n = std::sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
-  if (n < BMJ_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { for (int i = 0; i < 4; i++) q[i] /= n; }
+  if (n < BMJ_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+  else if (std::fabs(n - 1) > BMJ_MINVAL) { real inv = 1 / n; for (int i = 0; i < 4; i++) q[i] *= inv; }   // idempotent, as mju_normalize4
 }
 static inline void quat2mat(real* m, const real* q) {
   real q00 = q[0]*q[0], q11 = q[1]*q[1], q22 = q[2]*q[2], q33 = q[3]*q[3];

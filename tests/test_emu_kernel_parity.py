@@ -1,0 +1,134 @@
+"""The CUDA engine's own source (dm_control_b200/csrc/b200mj.cu), compiled for the CPU with the lock-step emulation
+of tests/emu/cuda_emu.h, against the oracle — no GPU needed.
+
+This is NOT a product path (nothing in dm_control_b200/ loads the emulation build, and `BatchedPhysics` still refuses
+to run without CUDA); it exists so that the round's CPU test tier exercises the kernels' logic — layouts and aliasing,
+the packed Cholesky, collision/constraint assembly, the split-kernel handover and the launch orchestration behind the
+C ABI — and not only the host code around them. The `-m gpu` tests remain the parity tests proper: the emulation says
+nothing about races, memory spaces or performance, and `rsqrt` is `1/sqrt` here.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+import b200mj_emu as emu   # noqa: E402
+
+from dm_control_b200 import testing_models as tm   # noqa: E402
+
+pytestmark = pytest.mark.timeout(600)
+TOL = 1e-8
+
+
+def relerr(a, b):
+  a, b = np.asarray(a), np.asarray(b)
+  return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b)))) if a.size else 0.0
+
+
+def _setup(name, B, seed, oracle_mod, **kw):
+  model = tm.load(name)
+  q0, v0 = tm.initial_states(model, name, B, seed)
+  p = emu.EmuPhysics(model, B, **kw)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0
+  p.forward()
+  oracles = []
+  for e in range(B):
+    o = oracle_mod.OraclePhysics(model)
+    o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward()
+    oracles.append(o)
+  return model, p, oracles
+
+
+@pytest.mark.parametrize('name,B', [('cartpole', 2), ('pendulum_free', 2), ('cheetah', 3), ('humanoid', 3),
+                                    ('quadruped', 2), ('slide_box', 1), ('free_box', 1), ('cmu_humanoid', 2)])
+def test_forward_fields(name, B, oracle_mod):
+  model, p, oracles = _setup(name, B, 11, oracle_mod)
+  for f in ('xpos', 'xquat', 'xmat', 'xipos', 'geom_xpos', 'geom_xmat', 'site_xpos', 'site_xmat', 'subtree_com', 'cvel',
+            'qfrc_bias', 'qfrc_passive', 'qacc', 'qfrc_constraint', 'qfrc_actuator', 'sensordata'):
+    g = getattr(p.data, f).reshape(B, -1)
+    o = np.stack([np.asarray(getattr(oo, f)).reshape(-1) for oo in oracles])
+    assert relerr(g, o) < 1e-10, (name, f, relerr(g, o))
+  assert relerr(p.data.qM, np.stack([oo.M_dense() for oo in oracles])) < 1e-13       # packed triangle -> dense output
+  np.testing.assert_array_equal(p.data.ncon, [o.ncon for o in oracles])
+  np.testing.assert_array_equal(p.data.nefc, [o.nefc for o in oracles])
+  for e, o in enumerate(oracles):
+    np.testing.assert_allclose(p.data.efc_force[e, :o.nefc], o.efc('efc_force'), rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize('name,B,ncontrol,nsub', [('cartpole', 2, 20, 1), ('pendulum_free', 2, 12, 2), ('cheetah', 2, 30, 1),
+                                                   ('humanoid', 2, 5, 5), ('quadruped', 2, 4, 4), ('cmu_humanoid', 2, 1, 6)])
+def test_rollout(name, B, ncontrol, nsub, oracle_mod):
+  """Fixed action tape, legacy step ordering (engine.py:147-162); every control step is compared: state to 1e-8,
+  contact count and geom pairs exactly, sensors to 1e-7."""
+  model, p, oracles = _setup(name, B, 5 if name == 'humanoid' else 0, oracle_mod)      # seeds whose first steps touch the floor
+  tape = np.random.RandomState(1).uniform(-1, 1, (ncontrol, B, model.nu))
+  saw_contact = 0
+  for t in range(ncontrol):
+    p.data.ctrl[:] = tape[t]
+    p.step(nsub)
+    for e, o in enumerate(oracles):
+      o.ctrl[:] = tape[t, e]
+      o.control_step(nsub)
+      assert relerr(p.data.qpos[e], o.qpos) < TOL and relerr(p.data.qvel[e], o.qvel) < TOL, (name, t, e)
+      assert int(p.data.ncon[e]) == o.ncon, (name, t, e)
+      pairs = [(c.geom1, c.geom2) for c in o.contact]
+      assert [tuple(x) for x in p.data.contact_geom[e, :o.ncon]] == pairs, (name, t, e)
+      saw_contact += o.ncon
+      if model.nsensordata:
+        o.subtree_vel()
+        assert relerr(p.data.sensordata[e], o.sensordata) < 1e-7, (name, t, e)
+      assert relerr(p.data.subtree_com[e], o.subtree_com) < 1e-9
+  if name not in ('cartpole',):
+    assert saw_contact > 0, 'the rollout should exercise the contact path'
+  assert not p.data.warning.any()
+
+
+def test_nstep_equals_repeated_steps_and_batch_independence(oracle_mod):
+  """engine_test.py:627-663 on the emulated kernels: step(3) is bitwise 3 x step(1); an environment's trajectory does
+  not depend on which batch it sits in."""
+  model = tm.load('humanoid')
+  q0, v0 = tm.initial_states(model, 'humanoid', 3, 5)
+  ctrl = np.random.RandomState(2).uniform(-1, 1, (3, model.nu))
+  def run(sel, chunks):
+    p = emu.EmuPhysics(model, len(sel))
+    p.data.qpos[:] = q0[sel]; p.data.qvel[:] = v0[sel]; p.forward(); p.data.ctrl[:] = ctrl[sel]
+    for n in chunks:
+      p.step(n)
+    return p.data.qpos.copy(), p.data.qvel.copy(), p.data.sensordata.copy()
+  a = run([0, 1, 2], [3])
+  b = run([0, 1, 2], [1, 1, 1])
+  c = run([1], [3])
+  for x, y in zip(a, b):
+    np.testing.assert_array_equal(x, y)
+  for x, y in zip(a, c):
+    np.testing.assert_array_equal(x[1:2], y)
+
+
+def test_bad_control_and_divergence_warnings():
+  """engine_test.py:487-547 semantics at the C ABI: NaN ctrl -> BADCTRL counter (ctrl treated as 0), a huge qpos ->
+  BADQPOS and an in-place reset to qpos0."""
+  model = tm.load('cheetah')
+  p = emu.EmuPhysics(model, 3)
+  p.forward()
+  p.data.ctrl[1, 0] = np.nan
+  p.data.qpos[2, 0] = 1e15
+  p.step(1)
+  w = p.data.warning
+  BADQPOS, BADCTRL = 4, 7                         # mjtWarning indices (include/b200mj_model_fields.h)
+  assert w[0].sum() == 0
+  assert w[1, BADCTRL] == 1 and w[1].sum() == 1
+  assert w[2, BADQPOS] == 1
+  assert np.isfinite(p.data.qpos).all() and abs(p.data.qpos[2, 0]) < 1.0
+
+
+def test_workspaces_fit_and_buckets_are_described():
+  p = emu.EmuPhysics(tm.load('humanoid'), 1)
+  d = p.describe()
+  assert d['pos_envs_per_cta'] == 5 and d['pos_workspace_bytes'] * 5 <= 227 * 1024
+  rows = [b['rows'] for b in d['acc_buckets']]
+  assert rows == sorted(rows) and rows[-1] == p.model.njmax
+  assert all(b['workspace_bytes'] <= b['last_step_workspace_bytes'] <= 227 * 1024 for b in d['acc_buckets'])
+  # packed M/H: the smallest bucket holds 16 environments per SM (1 KB reserved per CTA)
+  assert (227 * 1024) // (d['acc_buckets'][0]['workspace_bytes'] + 1024) >= 16
