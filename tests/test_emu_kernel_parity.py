@@ -41,8 +41,8 @@ def _setup(name, B, seed, oracle_mod, **kw):
   return model, p, oracles
 
 
-@pytest.mark.parametrize('name,B', [('cartpole', 2), ('pendulum_free', 2), ('cheetah', 3), ('humanoid', 3),
-                                    ('quadruped', 2), ('slide_box', 1), ('free_box', 1), ('cmu_humanoid', 2)])
+@pytest.mark.parametrize('name,B', [('cartpole', 8), ('pendulum_free', 8), ('cheetah', 16), ('humanoid', 16),
+                                    ('quadruped', 8), ('slide_box', 4), ('free_box', 4), ('cmu_humanoid', 4)])
 def test_forward_fields(name, B, oracle_mod):
   model, p, oracles = _setup(name, B, 11, oracle_mod)
   for f in ('xpos', 'xquat', 'xmat', 'xipos', 'geom_xpos', 'geom_xmat', 'site_xpos', 'site_xmat', 'subtree_com', 'cvel',
@@ -57,12 +57,12 @@ def test_forward_fields(name, B, oracle_mod):
     np.testing.assert_allclose(p.data.efc_force[e, :o.nefc], o.efc('efc_force'), rtol=1e-7, atol=1e-7)
 
 
-@pytest.mark.parametrize('name,B,ncontrol,nsub', [('cartpole', 2, 20, 1), ('pendulum_free', 2, 12, 2), ('cheetah', 2, 30, 1),
-                                                   ('humanoid', 2, 5, 5), ('quadruped', 2, 4, 4), ('cmu_humanoid', 2, 1, 6)])
+@pytest.mark.parametrize('name,B,ncontrol,nsub', [('cartpole', 8, 60, 1), ('pendulum_free', 8, 50, 2), ('cheetah', 16, 100, 1),
+                                                   ('humanoid', 16, 20, 5), ('quadruped', 8, 15, 4), ('cmu_humanoid', 4, 6, 6)])
 def test_rollout(name, B, ncontrol, nsub, oracle_mod):
   """Fixed action tape, legacy step ordering (engine.py:147-162); every control step is compared: state to 1e-8,
   contact count and geom pairs exactly, sensors to 1e-7."""
-  model, p, oracles = _setup(name, B, 5 if name == 'humanoid' else 0, oracle_mod)      # seeds whose first steps touch the floor
+  model, p, oracles = _setup(name, B, 0, oracle_mod)
   tape = np.random.RandomState(1).uniform(-1, 1, (ncontrol, B, model.nu))
   saw_contact = 0
   for t in range(ncontrol):
@@ -132,3 +132,30 @@ def test_workspaces_fit_and_buckets_are_described():
   assert all(b['workspace_bytes'] <= b['last_step_workspace_bytes'] <= 227 * 1024 for b in d['acc_buckets'])
   # packed M/H: the smallest bucket holds 16 environments per SM (1 KB reserved per CTA)
   assert (227 * 1024) // (d['acc_buckets'][0]['workspace_bytes'] + 1024) >= 16
+
+
+def test_environment_groups_and_large_batch(oracle_mod):
+  """Batches of 2048 and more are split into two environment groups on separate streams (b200mj_step); the split
+  must not change any environment's result. 2050 cheetahs against the same states stepped as three smaller batches
+  and, for a sample, against the oracle."""
+  model = tm.load('cheetah')
+  B = 2050
+  q0, v0 = tm.initial_states(model, 'cheetah', B, 3)
+  ctrl = np.random.RandomState(4).uniform(-1, 1, (B, model.nu))
+  def run(sel):
+    p = emu.EmuPhysics(model, len(sel))
+    p.data.qpos[:] = q0[sel]; p.data.qvel[:] = v0[sel]; p.forward(); p.data.ctrl[:] = ctrl[sel]
+    for _ in range(3):
+      p.step(2)
+    return p.data.qpos.copy(), p.data.qvel.copy(), p.data.ncon.copy()
+  big = run(np.arange(B))
+  for lo, hi in ((0, 700), (700, 1500), (1500, B)):
+    part = run(np.arange(lo, hi))
+    for x, y in zip(big, part):
+      np.testing.assert_array_equal(x[lo:hi], y)
+  for e in (0, 1024, 1025, 2049):
+    o = oracle_mod.OraclePhysics(model)
+    o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward(); o.ctrl[:] = ctrl[e]
+    for _ in range(3):
+      o.control_step(2)
+    assert relerr(big[0][e], o.qpos) < TOL and relerr(big[1][e], o.qvel) < TOL and int(big[2][e]) == o.ncon
