@@ -159,3 +159,42 @@ def test_environment_groups_and_large_batch(oracle_mod):
     for _ in range(3):
       o.control_step(2)
     assert relerr(big[0][e], o.qpos) < TOL and relerr(big[1][e], o.qvel) < TOL and int(big[2][e]) == o.ncon
+
+
+_KNOB_SCRIPT = r'''
+import hashlib, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], 'tests', 'emu'))
+import b200mj_emu as emu
+from dm_control_b200 import testing_models as tm
+h = hashlib.sha256()
+for name, B, nsteps, nsub in (('humanoid', 6, 6, 5), ('quadruped', 4, 5, 4), ('pendulum_free', 4, 20, 2)):
+  model = tm.load(name)
+  q0, v0 = tm.initial_states(model, name, B, 0)
+  p = emu.EmuPhysics(model, B)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+  tape = np.random.RandomState(9).uniform(-1, 1, (nsteps, B, model.nu))
+  for t in range(nsteps):
+    p.data.ctrl[:] = tape[t]; p.step(nsub)
+    for f in ('qpos', 'qvel', 'sensordata', 'xpos', 'subtree_linvel', 'ncon', 'contact_geom', 'qacc', 'efc_force'):
+      h.update(np.ascontiguousarray(getattr(p.data, f)).tobytes())
+print(h.hexdigest())
+'''
+
+
+def test_launch_knobs_do_not_change_results():
+  """The fused kernel, the hybrid and the all-split path, any row-bucket partition, bucket launch order and
+  environment grouping are scheduling choices: every one of them must reproduce the default path bit for bit
+  (states, sensors, contacts, constraint forces, over rollouts with contacts)."""
+  import subprocess
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  def digest(**env):
+    e = dict(os.environ); e.update(env)
+    out = subprocess.run([sys.executable, '-c', _KNOB_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout.strip().splitlines()[-1]
+  ref = digest()
+  for knobs in (dict(B200MJ_SPLIT='0'), dict(B200MJ_SPLIT='1'), dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_BUCKETS='6,12,24'),
+                dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'), dict(B200MJ_ENVS_PER_BLOCK='2', B200MJ_SPLIT='0'),
+                dict(B200MJ_SYNC_LEVEL='0', B200MJ_SPLIT='0')):
+    assert digest(**knobs) == ref, knobs
