@@ -2235,6 +2235,20 @@ int b200mj_describe(const b200mj_model* M, char* buf, int n) {
 
 int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int nr, b200mj_model** out) {
   if (!idata || !rdata || !out || ni <= 0 || nr <= 0) return -1;
+  {   // the blob starts with one (offset, length) pair per field of b200mj_model_fields.h: refuse a malformed directory
+    int nfields = 0;
+#define CNT(name) nfields++;
+    B200MJ_MODEL_FIELDS(CNT, CNT)
+#undef CNT
+    if (ni < 2 * nfields) return -1;
+    int k = 0; bool bad = false;
+#define CHK_I(name) { long off = idata[2*k], len = idata[2*k+1]; if (off < 2 * nfields || len < 0 || off + len > ni) bad = true; k++; }
+#define CHK_R(name) { long off = idata[2*k], len = idata[2*k+1]; if (off < 0 || len < 0 || off + len > nr) bad = true; k++; }
+    B200MJ_MODEL_FIELDS(CHK_I, CHK_R)
+#undef CHK_I
+#undef CHK_R
+    if (bad) return -1;
+  }
   b200mj_model* M = new b200mj_model();
   memset(M, 0, sizeof(*M));
   if (cudaMalloc(&M->d_idata, (size_t)ni * sizeof(int)) != cudaSuccess) { delete M; return -2; }
@@ -2321,6 +2335,10 @@ int b200mj_model_set_capacity(b200mj_model* M, int nconmax, int njmax) {
   if (!M || nconmax < 0 || njmax < 0) return -1;
   M->dm.nconmax = nconmax; M->dm.njmax = njmax;
   build_layout(M);
+  // the handover rows are sized by the layout: drop them, the next b200mj_step allocates for the new capacities
+  if (M->d_hand) cudaFree(M->d_hand);
+  if (M->d_hand2) cudaFree(M->d_hand2);
+  M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0;
   return M->envs_per_block < 1 ? -4 : 0;
 }
 

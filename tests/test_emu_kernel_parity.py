@@ -198,3 +198,42 @@ def test_launch_knobs_do_not_change_results():
                 dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'), dict(B200MJ_ENVS_PER_BLOCK='2', B200MJ_SPLIT='0'),
                 dict(B200MJ_SYNC_LEVEL='0', B200MJ_SPLIT='0')):
     assert digest(**knobs) == ref, knobs
+
+
+def test_malformed_blob_is_refused_and_capacity_change_reallocates(oracle_mod):
+  """b200mj_model_create validates the directory of the blob; b200mj_model_set_capacity drops handover rows sized for
+  the old capacities (the next step reallocates) — exercised through the emulated library's own host code."""
+  import ctypes
+  L = emu.load()
+  model = tm.load('cheetah')
+  idata, rdata = model.pack()
+  def create(i, r):
+    h = ctypes.c_void_p()
+    rc = L.b200mj_model_create(i.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), i.size,
+                               r.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), r.size, ctypes.byref(h))
+    if rc == 0:
+      L.b200mj_model_destroy(h)
+    return rc
+  assert create(idata, rdata) == 0
+  bad = idata.copy(); bad[1] = idata.size + 5            # first field's length runs past the blob
+  assert create(bad, rdata) == -1
+  bad = idata.copy(); bad[0] = -3
+  assert create(bad, rdata) == -1
+  assert create(idata[:20].copy(), rdata) == -1          # directory truncated
+  # capacity change between steps
+  L.b200mj_model_set_capacity.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+  p = emu.EmuPhysics(model, 2)
+  q0, v0 = tm.initial_states(model, 'cheetah', 2, 0)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward(); p.step(2)
+  assert L.b200mj_model_set_capacity(p._h, int(model.nconmax) + 7, int(model.njmax) + 40) == 0
+  # io arrays sized by the old capacities stay valid for the fields that do not depend on them; re-bind the others
+  m2 = model.copy(); m2.set_capacity(int(model.nconmax) + 7, int(model.njmax) + 40)
+  p2 = emu.EmuPhysics(m2, 2)
+  p2.data.qpos[:] = q0; p2.data.qvel[:] = v0; p2.forward(); p2.step(2)
+  for name in ('efc_force', 'contact_dist', 'contact_pos', 'contact_frame', 'contact_geom', 'contact_efc_address'):
+    a = getattr(p2.data, name)
+    setattr(p.data, name, np.zeros_like(a))
+    setattr(p._io, name, ctypes.cast(getattr(p.data, name).ctypes.data, dict(emu.blib.IO_FIELDS)[name]))
+  p.step(2); p2.step(2)
+  np.testing.assert_array_equal(p.data.qpos, p2.data.qpos)
+  np.testing.assert_array_equal(p.data.qvel, p2.data.qvel)
