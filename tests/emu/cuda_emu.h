@@ -83,11 +83,19 @@ inline emu_dim3 blockDim, gridDim;
 
 alignas(16) inline thread_local double smem[232448 / 8];     // dynamic shared memory of the block this OS thread runs
 
+// Scheduling order of the fibers of a block: ascending thread index by default, descending with B200MJ_EMU_ORDER=reverse.
+// Code that is correct under CUDA's memory model (every cross-lane dependency through shared memory separated by a
+// collective or a barrier) gives the same results under both; a missing __syncwarp() shows up as a difference,
+// because only one of the two orders happens to run the producer before the consumer.
+inline int emu_dir() { static const int d = [] { const char* e = std::getenv("B200MJ_EMU_ORDER"); return (e && e[0] == 'r') ? -1 : 1; }(); return d; }
+inline int emu_next(const emu_block* b, int i) {
+  const int n = (int)b->f.size(), d = emu_dir();
+  do { i += d; if (i == n) i = 0; else if (i < 0) i = n - 1; } while (b->f[i].done);
+  return i;
+}
 inline void emu_yield() {
   emu_block* b = emu_blk;
-  const int n = (int)b->f.size();
-  int i = b->cur;
-  do { i = i + 1 == n ? 0 : i + 1; } while (b->f[i].done);
+  int i = emu_next(b, b->cur);
   if (i == b->cur) return;
   emu_fiber* from = &b->f[b->cur];
   b->cur = i; emu_cur = &b->f[i];
@@ -110,8 +118,7 @@ inline void emu_fiber_entry() {
   emu_drop(me->warp->bar); emu_drop(b->bar);
   void* dummy;
   if (--b->live == 0) emu_switch(&dummy, b->sched_sp);       // last one out returns to the block runner
-  int i = b->cur; const int n = (int)b->f.size();
-  do { i = i + 1 == n ? 0 : i + 1; } while (b->f[i].done);
+  int i = emu_next(b, b->cur);
   b->cur = i; emu_cur = &b->f[i];
   emu_switch(&dummy, b->f[i].sp);
   std::abort();                                                // a finished fiber is never resumed
@@ -177,8 +184,9 @@ inline void emu_run_block(unsigned bidx, unsigned block, const std::function<voi
     for (int k = 0; k < 6; k++) sp[k] = nullptr;
     f.sp = sp;
   }
-  emu_blk = &blk; blk.cur = 0; emu_cur = &blk.f[0];
-  emu_switch(&blk.sched_sp, blk.f[0].sp);
+  const int first = emu_dir() > 0 ? 0 : (int)block - 1;
+  emu_blk = &blk; blk.cur = first; emu_cur = &blk.f[first];
+  emu_switch(&blk.sched_sp, blk.f[first].sp);
   emu_blk = nullptr; emu_cur = nullptr;
 }
 template <class K, class... A> inline void emu_launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... args) {

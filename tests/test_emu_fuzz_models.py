@@ -222,3 +222,38 @@ def test_random_model_rollout(seed, oracle_mod):
         assert relerr(p.data.sensordata[e], o.sensordata) < 1e-5, (seed, t, e)
       ncon_seen += o.ncon
   assert not p.data.warning.any()
+
+
+_ORDER_SCRIPT = r'''
+import hashlib, os, sys
+import numpy as np
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, 'tests')); sys.path.insert(0, os.path.join(root, 'tests', 'emu'))
+import b200mj_emu as emu
+from test_emu_fuzz_models import Gen
+from dm_control_b200 import mjcf_compile
+h = hashlib.sha256()
+for seed in range(0, 120, 3):
+  model = mjcf_compile.compile_xml(Gen(seed).xml())
+  rs = np.random.RandomState(1000 + seed)
+  p = emu.EmuPhysics(model, 2)
+  p.data.qvel[:] = rs.uniform(-1, 1, (2, model.nv)); p.forward()
+  for t in range(12):
+    p.data.ctrl[:] = rs.uniform(-1, 1, (2, model.nu)); p.step(int(rs.choice([1, 2])))
+    for f in ('qpos', 'qvel', 'sensordata', 'ncon', 'contact_geom', 'qacc', 'efc_force', 'act'):
+      h.update(np.ascontiguousarray(getattr(p.data, f)).tobytes())
+print(h.hexdigest())
+'''
+
+
+def test_lane_order_does_not_change_results():
+  """Race check without a GPU: 40 random models stepped with the emulator scheduling the lanes of each block in
+  ascending and in descending order must agree bit for bit (see cuda_emu.h: emu_dir)."""
+  import subprocess
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  def digest(**env):
+    e = dict(os.environ); e.update(env)
+    out = subprocess.run([sys.executable, '-c', _ORDER_SCRIPT, root], env=e, capture_output=True, text=True, timeout=800)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout.strip().splitlines()[-1]
+  assert digest() == digest(B200MJ_EMU_ORDER='reverse')
