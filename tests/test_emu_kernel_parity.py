@@ -240,3 +240,33 @@ def test_malformed_blob_is_refused_and_capacity_change_reallocates(oracle_mod):
   p.step(2); p2.step(2)
   np.testing.assert_array_equal(p.data.qpos, p2.data.qpos)
   np.testing.assert_array_equal(p.data.qvel, p2.data.qvel)
+
+
+@pytest.mark.parametrize('nconmax,njmax', [(2, 96), (32, 6), (1, 3)])
+def test_capacity_overflow_raises_warnings_like_the_oracle(nconmax, njmax, oracle_mod):
+  """Too small <size nconmax njmax>: contacts / rows beyond the capacity are dropped with mjWARN_CONTACTFULL /
+  mjWARN_CNSTRFULL; kernel and oracle must drop the same ones, keep running, and agree on the state."""
+  model = tm.load('humanoid').copy()
+  model.set_capacity(nconmax, njmax)
+  B = 4
+  q0, v0 = tm.initial_states(model, 'humanoid', B, 0)
+  q0[:, 2] = 0.12                                  # lying low: many floor contacts at once
+  p = emu.EmuPhysics(model, B)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+  oracles = []
+  for e in range(B):
+    o = oracle_mod.OraclePhysics(model)
+    o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward()
+    oracles.append(o)
+  CONTACTFULL, CNSTRFULL = 1, 2
+  for t in range(6):
+    p.step(2)
+    for e, o in enumerate(oracles):
+      o.control_step(2)
+      assert int(p.data.ncon[e]) == o.ncon <= nconmax and int(p.data.nefc[e]) == o.nefc <= njmax
+      assert relerr(p.data.qpos[e], o.qpos) < 1e-7 and relerr(p.data.qvel[e], o.qvel) < 1e-6, (t, e)
+  wk = p.data.warning
+  wo = np.stack([np.asarray(o.warning)[:8] for o in oracles])
+  assert wk[:, CONTACTFULL].sum() + wk[:, CNSTRFULL].sum() > 0, 'the capacities should have overflowed'
+  np.testing.assert_array_equal(wk[:, CONTACTFULL] > 0, wo[:, CONTACTFULL] > 0)
+  np.testing.assert_array_equal(wk[:, CNSTRFULL] > 0, wo[:, CNSTRFULL] > 0)
