@@ -324,6 +324,7 @@ def run_gpu(args):
                       traffic=prof.get('dram_bytes_per_step', prof.get('dram_bytes_per_launch')), peak_source=peak_src,
                       kernel='b200mj step group: [pos_kernel, acc_kernel x row-buckets] x (n_sub_steps-1), [pos_kernel, acclast_kernel x row-buckets], posfinal_kernel',
                       dominant_kernel=prof.get('dominant_kernel', 'b200mj_acc_kernel'),
+                      dominant_kernel_utilisation_pct=prof.get('dominant_kernel_utilisation_pct'),
                       kernel_ms=kernel_ms, kernel_share_of_step=kernel_ms / (ms_total / args.steps),
                       algorithmic_bytes_per_launch=ALGO_BYTES_PER_ENV_STEP * BATCH,
                       note='latency/issue-bound fp64 kernel: compulsory traffic is ~4 kB per env-step, see DESIGN.md'),

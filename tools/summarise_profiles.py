@@ -34,7 +34,9 @@ if os.path.exists(rep):
           'sm__inst_executed.avg.per_cycle_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
           'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_shared_mem',
           'sm__icc_request_hit_rate.pct', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
-          'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct']
+          'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct',
+          'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+          'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active']
   unit = dict(zip(rows[0], rows[1]))
   metrics = {k: (d.get(k), unit.get(k)) for k in keep if k in d}
   stalls = {k.split('issue_stalled_')[1]: float(d[k]) for k in rows[0] if 'pcsamp_warps_issue_stalled' in k and 'not_issued' not in k}
@@ -46,6 +48,15 @@ if os.path.exists(rep):
     f = float(v.replace(',', ''))
     return f * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(u, 1)
   summary['dram_bytes_per_launch'] = num('dram__bytes_read.sum') + num('dram__bytes_write.sum')
+  # what the dominant kernel is actually bound by (it is nowhere near the HBM roofline): issue slots and pipes
+  def pct(k):
+    try: return round(float(d[k].replace(',', '')), 2)
+    except Exception: return None
+  summary['dominant_kernel_utilisation_pct'] = dict(
+      issue_slots=pct('smsp__issue_active.avg.pct_of_peak_sustained_active'), lsu_pipe=pct('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'),
+      fp64_pipe=pct('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'), alu_pipe=pct('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'),
+      fma_pipe=pct('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'), ipc_per_sm=pct('sm__inst_executed.avg.per_cycle_active'),
+      warps_active=pct('sm__warps_active.avg.pct_of_peak_sustained_active'))
   summary['kernel_ms_under_ncu'] = float(d['gpu__time_duration.sum'].replace(',', '')) * {'ms': 1, 'us': 1e-3, 'ns': 1e-6, 'msecond': 1, 'usecond': 1e-3, 'nsecond': 1e-6}.get(unit['gpu__time_duration.sum'], 1)
   src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'], capture_output=True, text=True).stdout
   open(os.path.join(G, 'bench_src_cs.csv'), 'w').write(src)
