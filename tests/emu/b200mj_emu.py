@@ -51,7 +51,7 @@ def load():
 class EmuPhysics:
   """B environments stepped by the emulated kernels; `data.<field>` are numpy arrays with a leading batch axis."""
 
-  def __init__(self, model, batch, sensors=True, full_final=True, legacy_step=True):
+  def __init__(self, model, batch, sensors=True, full_final=True, legacy_step=True, applied_forces=False):
     self._L = load()
     self.model, self.batch = model, int(batch)
     self._sensors, self._full_final, self.legacy_step = sensors, full_final, legacy_step
@@ -70,7 +70,7 @@ class EmuPhysics:
       setattr(self.data, name, np.zeros((batch,) + tuple(shp(model)), np.int32))
     for name, ctype in blib.IO_FIELDS:
       a = getattr(self.data, name, None)
-      if a is None or a.size == 0 or name in ('qfrc_applied', 'xfrc_applied'):
+      if a is None or a.size == 0 or (name in ('qfrc_applied', 'xfrc_applied') and not applied_forces):
         setattr(self._io, name, ctypes.cast(None, ctype))
       else:
         setattr(self._io, name, ctypes.cast(a.ctypes.data, ctype))
@@ -90,6 +90,20 @@ class EmuPhysics:
                                 blib.STEP_SENSORS if self._sensors else 0, None)
     if rc:
       raise RuntimeError(f'b200mj_forward (emulation) failed: {rc}')
+
+  def step_host(self, ctrl_host, obs_dev, obs_host, nstep=1):
+    """b200mj_step_host: host action block in, packed observation block out."""
+    vp = ctypes.c_void_p
+    self._L.b200mj_step_host.argtypes = [vp, ctypes.POINTER(blib.IO), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp,
+                                         ctypes.c_int, vp]
+    rc = self._L.b200mj_step_host(self._h, ctypes.byref(self._io), self.batch, int(nstep), self._flags(),
+                                  ctrl_host.ctypes.data, self.data.ctrl.ctypes.data, obs_dev.ctypes.data, obs_host.ctypes.data,
+                                  obs_dev.shape[1], None)
+    if rc:
+      raise RuntimeError(f'b200mj_step_host (emulation) failed: {rc}')
+
+  def set_disableflags(self, flags):
+    self._L.b200mj_model_set_disableflags(self._h, int(flags))
 
   def describe(self):
     import json

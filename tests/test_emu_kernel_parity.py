@@ -270,3 +270,64 @@ def test_capacity_overflow_raises_warnings_like_the_oracle(nconmax, njmax, oracl
   assert wk[:, CONTACTFULL].sum() + wk[:, CNSTRFULL].sum() > 0, 'the capacities should have overflowed'
   np.testing.assert_array_equal(wk[:, CONTACTFULL] > 0, wo[:, CONTACTFULL] > 0)
   np.testing.assert_array_equal(wk[:, CNSTRFULL] > 0, wo[:, CNSTRFULL] > 0)
+
+
+@pytest.mark.parametrize('name', ['humanoid', 'pendulum_free', 'quadruped'])
+def test_non_legacy_ordering_and_applied_forces(name, oracle_mod):
+  """`legacy_step = False` (engine.py:176: mj_step x n, nothing recomputed afterwards) and user forces
+  (`qfrc_applied`, `xfrc_applied`) are served by the fused kernel: against the oracle's mj_step."""
+  model = tm.load(name)
+  B = 3
+  q0, v0 = tm.initial_states(model, name, B, 2)
+  p = emu.EmuPhysics(model, B, legacy_step=False, applied_forces=True)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0
+  rs = np.random.RandomState(6)
+  p.data.qfrc_applied[:] = rs.uniform(-2, 2, p.data.qfrc_applied.shape)
+  p.data.xfrc_applied[:, 1:] = rs.uniform(-5, 5, p.data.xfrc_applied[:, 1:].shape)
+  p.forward()
+  oracles = []
+  for e in range(B):
+    o = oracle_mod.OraclePhysics(model)
+    o.qpos[:] = q0[e]; o.qvel[:] = v0[e]
+    o.qfrc_applied[:] = p.data.qfrc_applied[e]; o.xfrc_applied[:] = p.data.xfrc_applied[e]
+    o.forward()
+    oracles.append(o)
+    assert relerr(p.data.qacc[e], o.qacc) < 1e-9
+  for t in range(8):
+    ctrl = rs.uniform(-1, 1, (B, model.nu))
+    p.data.ctrl[:] = ctrl
+    p.step(3)
+    for e, o in enumerate(oracles):
+      o.ctrl[:] = ctrl[e]
+      o.step(3)
+      assert relerr(p.data.qpos[e], o.qpos) < TOL and relerr(p.data.qvel[e], o.qvel) < TOL, (name, t, e)
+
+
+def test_step_host_and_disable_flags(oracle_mod):
+  """b200mj_step_host (host action buffer in, observation block out) equals b200mj_step on the same inputs;
+  b200mj_model_set_disableflags / the extra flags of b200mj_forward act like `model.disable()` (core.py:389-426)."""
+  model = tm.load('cheetah')
+  B = 4
+  q0, v0 = tm.initial_states(model, 'cheetah', B, 1)
+  a, b = emu.EmuPhysics(model, B), emu.EmuPhysics(model, B)
+  for p in (a, b):
+    p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+  ctrl = np.random.RandomState(3).uniform(-1, 1, (B, model.nu))
+  obs_host = np.zeros((B, model.nq))
+  a.step_host(ctrl.copy(), a.data.qpos, obs_host, nstep=2)
+  b.data.ctrl[:] = ctrl; b.step(2)
+  np.testing.assert_array_equal(a.data.qpos, b.data.qpos)
+  np.testing.assert_array_equal(obs_host, b.data.qpos)
+  np.testing.assert_array_equal(a.data.ctrl, ctrl)
+  # gravity + contact disabled: a resting cheetah with zero control does not accelerate
+  c = emu.EmuPhysics(model, 1)
+  c.set_disableflags((1 << 4) | (1 << 6))
+  c.forward()
+  assert np.abs(c.data.qacc).max() < 1e-12 and int(c.data.ncon[0]) == 0
+  # actuation disabled only for this forward (reset()/after_reset(), engine.py:325-333)
+  d = emu.EmuPhysics(model, 1)
+  d.data.ctrl[:] = 1.0
+  d.forward(extra_disableflags=1 << 10)
+  assert np.abs(d.data.actuator_force).max() == 0
+  d.forward()
+  assert np.abs(d.data.actuator_force).max() > 0
