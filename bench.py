@@ -249,7 +249,7 @@ def run_gpu(args):
     actions.uniform_(-1, 1, generator=gen)
     env._task.before_step(actions, phys)
     kev[i][0].record()
-    phys.step(env.n_sub_steps)                         # the one launch of b200mj_step_kernel
+    phys.step(env.n_sub_steps)                         # one b200mj_step call: the step's whole kernel group
     kev[i][1].record()
     env._task.after_step(phys)
     reward, obs = env._reward_and_observation()
