@@ -5,6 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip('torch')
+from conftest import DEV, EMULATE                   # noqa: E402  ('cuda'; 'cpu' only under B200MJ_EMULATE_GPU=1)
 from dm_control_b200 import testing_models as tm   # noqa: E402
 from dm_control_b200 import mjcf_compile as mc    # noqa: E402
 
@@ -66,7 +67,7 @@ def test_run_to_run_determinism_and_batch_invariance():
   big, small, again = _phys('humanoid', 4096), _phys('humanoid', 64), _phys('humanoid', 4096)
   for p in (big, small, again):
     _seed(p, 'humanoid', 9)
-  tape = torch.as_tensor(np.random.RandomState(3).uniform(-1, 1, (10, 4096, 21)), device='cuda')
+  tape = torch.as_tensor(np.random.RandomState(3).uniform(-1, 1, (10, 4096, 21)), device=DEV)
   for t in range(10):
     big.set_control(tape[t]); again.set_control(tape[t]); small.set_control(tape[t, :64])
     big.step(5); again.step(5); small.step(5)
@@ -104,11 +105,12 @@ def test_bad_control_and_bad_state_raise_physics_error():
     phys.step()                    # suppressed: logged only
 
 
+@pytest.mark.skipif(EMULATE, reason='BASELINE-size batch: device only')
 def test_full_batch_properties_humanoid_8192():
   """BASELINE.json size: properties that need no oracle (finite, bounded, contacts present, clock exact)."""
   phys = _phys('humanoid', 8192, outputs=('xpos', 'subtree_com', 'sensordata', 'ncon'))
   _seed(phys, 'humanoid', 1)
-  g = torch.Generator(device='cuda').manual_seed(0)
+  g = torch.Generator(device=DEV).manual_seed(0)
   for _ in range(40):
     phys.data.ctrl.uniform_(-1, 1, generator=g)
     phys.step(5)
@@ -137,12 +139,13 @@ def test_step_host_equals_step():
   ctrl = torch.rand(16, 6, dtype=torch.float64).mul_(2).sub_(1).pin_memory()
   obs_host = torch.empty(16, 3, dtype=torch.float64).pin_memory()
   for _ in range(5):
-    a.set_control(ctrl.cuda()); a.step(3)
+    a.set_control(ctrl.to(DEV)); a.step(3)
     b.step_host(ctrl, b.data.sensordata, obs_host, nstep=3)
   assert torch.equal(a.get_state(), b.get_state())
   assert torch.equal(obs_host, a.data.sensordata.cpu())
 
 
+@pytest.mark.skipif(EMULATE, reason='spawns fresh interpreters on the device; tests/test_emu_kernel_parity.py has the emulated twin')
 def test_fused_and_split_paths_agree_bitwise(monkeypatch):
   """B200MJ_SPLIT=0 (one fused kernel) and the default split path are the same arithmetic."""
   import subprocess, sys, os, json
@@ -150,7 +153,7 @@ def test_fused_and_split_paths_agree_bitwise(monkeypatch):
           "from dm_control_b200 import testing_models as tm; from dm_control_b200.physics import BatchedPhysics;"
           "m = tm.load('humanoid'); q, v = tm.initial_states(m, 'humanoid', 32, 5); p = BatchedPhysics(m, batch=32);"
           "p.data.qpos.copy_(torch.as_tensor(q)); p.data.qvel.copy_(torch.as_tensor(v)); p.forward();"
-          "g = torch.Generator(device='cuda').manual_seed(0);"
+          "g = torch.Generator(device=DEV).manual_seed(0);"
           "[ (p.data.ctrl.uniform_(-1, 1, generator=g), p.step(5)) for _ in range(6) ];"
           "print(json.dumps(dict(q=p.data.qpos.cpu().tolist(), s=p.data.sensordata.cpu().tolist(), n=p.data.ncon.cpu().tolist())))"
           ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -4,6 +4,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip('torch')
+from conftest import DEV   # noqa: E402  ('cuda'; 'cpu' only under B200MJ_EMULATE_GPU=1)
 
 
 @pytest.mark.parametrize('domain,task,nu,obs_dim', [('cartpole', 'swingup', 1, 5), ('cheetah', 'run', 6, 17),
@@ -14,10 +15,10 @@ def test_task_conformance(domain, task, nu, obs_dim):
   env = suite.load(domain, task, batch=B, seed=3)
   ts = env.reset()
   assert ts.reward is None and int(ts.step_type[0]) == 0
-  g = torch.Generator(device='cuda').manual_seed(0)
+  g = torch.Generator(device=DEV).manual_seed(0)
   dims, seen = None, []
   for t in range(12):
-    a = torch.rand(B, nu, generator=g, device='cuda', dtype=torch.float64) * 2 - 1     # suite_test.py:32-45 policy
+    a = torch.rand(B, nu, generator=g, device=DEV, dtype=torch.float64) * 2 - 1     # suite_test.py:32-45 policy
     ts = env.step(a)
     flat = torch.cat([v.reshape(B, -1) for v in ts.observation.values()], dim=1)
     assert flat.shape == (B, obs_dim), flat.shape                                       # SURVEY §8a observation sizes
@@ -35,9 +36,9 @@ def test_same_seed_same_trajectory():
   for _ in range(2):
     env = suite.load('cheetah', 'run', batch=16, seed=11)
     env.reset()
-    g = torch.Generator(device='cuda').manual_seed(5)
+    g = torch.Generator(device=DEV).manual_seed(5)
     for _ in range(5):
-      ts = env.step(torch.rand(16, 6, generator=g, device='cuda', dtype=torch.float64) * 2 - 1)
+      ts = env.step(torch.rand(16, 6, generator=g, device=DEV, dtype=torch.float64) * 2 - 1)
     outs.append(torch.cat([v.reshape(16, -1) for v in ts.observation.values()], dim=1))
   assert torch.equal(outs[0], outs[1])
 
@@ -47,9 +48,9 @@ def test_humanoid_reward_matches_numpy_formula():
   from dm_control_b200 import suite
   env = suite.load('humanoid', 'run', batch=32, seed=1)
   env.reset()
-  g = torch.Generator(device='cuda').manual_seed(2)
+  g = torch.Generator(device=DEV).manual_seed(2)
   for _ in range(8):
-    ts = env.step(torch.rand(32, 21, generator=g, device='cuda', dtype=torch.float64) * 2 - 1)
+    ts = env.step(torch.rand(32, 21, generator=g, device=DEV, dtype=torch.float64) * 2 - 1)
   p = env.physics
   head = p.head_height().cpu().numpy(); up = p.torso_upright().cpu().numpy(); ctrl = p.control().cpu().numpy()
   com = p.center_of_mass_velocity().cpu().numpy()
@@ -71,7 +72,7 @@ def test_time_limit_and_auto_reset():
   from dm_control_b200 import suite, control
   env = suite.load('cartpole', 'swingup', batch=8, seed=0, time_limit=0.05)   # 5 control steps of 0.01 s
   env.reset()
-  a = torch.zeros(8, 1, dtype=torch.float64, device='cuda')
+  a = torch.zeros(8, 1, dtype=torch.float64, device=DEV)
   types = []
   for _ in range(7):
     ts = env.step(a)
@@ -82,7 +83,7 @@ def test_time_limit_and_auto_reset():
   env2 = suite.load('cheetah', 'run', batch=6, seed=2)
   env2.reset()
   before = env2.physics.get_state().clone()
-  mask = torch.tensor([True, False, False, True, False, False], device='cuda')
+  mask = torch.tensor([True, False, False, True, False, False], device=DEV)
   env2.task.initialize_episode(env2.physics, mask)
   after = env2.physics.get_state()
   assert torch.equal(after[~mask], before[~mask])
