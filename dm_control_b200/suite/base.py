@@ -40,8 +40,9 @@ class Task:
 
 
 def randomize_limited_and_rotational_joints(physics, gen, env_mask=None):
-  """Batched `suite/utils/randomizers.py:35-88`: limited hinge/slide uniform in range, unlimited hinge in
-  [-pi, pi], free-joint quaternion from `rand(4)` normalised (the reference's documented quirk)."""
+  """Batched `suite/utils/randomizers.py:35-88`: limited hinge/slide uniform in range, limited ball within its cone,
+  unlimited hinge in [-pi, pi], unlimited ball uniform on the 3-sphere, free-joint quaternion from `rand(4)`
+  normalised (the reference's documented quirk); slides without limits and free-joint positions stay put."""
   import math
   m, d = physics.model, physics.data
   B = physics.batch
@@ -52,6 +53,12 @@ def randomize_limited_and_rotational_joints(physics, gen, env_mask=None):
     if m.jnt_limited[j]:
       if t in (2, 3):
         q[:, qa] = torch.rand(B, generator=gen, device=physics.device, dtype=torch.float64) * (hi - lo) + lo
+      elif t == 1:
+        # limited ball joint: random axis, rotation angle uniform in [0, range_max] (randomizers.py:25-33)
+        axis = torch.randn(B, 3, generator=gen, device=physics.device, dtype=torch.float64)
+        axis = axis / axis.norm(dim=1, keepdim=True)
+        half = 0.5 * hi * torch.rand(B, 1, generator=gen, device=physics.device, dtype=torch.float64)
+        q[:, qa:qa + 4] = torch.cat([torch.cos(half), torch.sin(half) * axis], dim=1)
     else:
       if t == 3:
         q[:, qa] = (torch.rand(B, generator=gen, device=physics.device, dtype=torch.float64) * 2 - 1) * math.pi
