@@ -51,7 +51,7 @@ def load():
 class EmuPhysics:
   """B environments stepped by the emulated kernels; `data.<field>` are numpy arrays with a leading batch axis."""
 
-  def __init__(self, model, batch, sensors=True, full_final=True, legacy_step=True, applied_forces=False):
+  def __init__(self, model, batch, sensors=True, full_final=True, legacy_step=True, applied_forces=False, outputs='all'):
     self._L = load()
     self.model, self.batch = model, int(batch)
     self._sensors, self._full_final, self.legacy_step = sensors, full_final, legacy_step
@@ -68,8 +68,11 @@ class EmuPhysics:
       setattr(self.data, name, np.zeros((batch,) + tuple(shp(model)), np.float64))
     for name, shp in BatchedPhysics._INT_FIELDS:
       setattr(self.data, name, np.zeros((batch,) + tuple(shp(model)), np.int32))
+    state = ('qpos', 'qvel', 'act', 'qacc_warmstart', 'time', 'ctrl', 'qfrc_applied', 'xfrc_applied', 'warning')
     for name, ctype in blib.IO_FIELDS:
       a = getattr(self.data, name, None)
+      if outputs != 'all' and name not in state and name not in outputs:
+        a = None                                   # this output pointer crosses the ABI as NULL
       if a is None or a.size == 0 or (name in ('qfrc_applied', 'xfrc_applied') and not applied_forces):
         setattr(self._io, name, ctypes.cast(None, ctype))
       else:

@@ -331,3 +331,29 @@ def test_step_host_and_disable_flags(oracle_mod):
   assert np.abs(d.data.actuator_force).max() == 0
   d.forward()
   assert np.abs(d.data.actuator_force).max() > 0
+
+
+@pytest.mark.parametrize('name,nsub', [('humanoid', 5), ('quadruped', 4), ('cartpole', 1), ('pendulum_free', 2)])
+@pytest.mark.parametrize('outputs,sensors,full_final', [((), False, False), (('sensordata',), True, False), (('xpos', 'ncon'), False, True)])
+def test_null_outputs_and_flag_combinations_leave_the_state_alone(name, nsub, outputs, sensors, full_final):
+  """Any output pointer may be NULL and the sensor / full-final work is optional (include/b200mj.h): whatever subset
+  is requested, the state trajectory is bit-identical to the run that materialises everything, and the requested
+  outputs carry the same values."""
+  model = tm.load(name)
+  B = 3
+  q0, v0 = tm.initial_states(model, name, B, 0)
+  tape = np.random.RandomState(12).uniform(-1, 1, (6, B, model.nu))
+  def run(**kw):
+    p = emu.EmuPhysics(model, B, **kw)
+    p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+    for t in range(6):
+      p.data.ctrl[:] = tape[t]; p.step(nsub)
+    return p
+  full = run()
+  part = run(outputs=outputs, sensors=sensors, full_final=full_final)
+  for f in ('qpos', 'qvel', 'act', 'qacc_warmstart', 'time'):
+    np.testing.assert_array_equal(getattr(part.data, f), getattr(full.data, f))
+  for f in outputs:
+    if f == 'ncon' and not full_final:
+      continue
+    np.testing.assert_array_equal(getattr(part.data, f), getattr(full.data, f))
