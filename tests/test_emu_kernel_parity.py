@@ -357,3 +357,56 @@ def test_null_outputs_and_flag_combinations_leave_the_state_alone(name, nsub, ou
     if f == 'ncon' and not full_final:
       continue
     np.testing.assert_array_equal(getattr(part.data, f), getattr(full.data, f))
+
+
+_ASAN_SCRIPT = r'''
+import os, sys
+import numpy as np
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, 'tests', 'emu'))
+import b200mj_emu as emu
+emu._SO = sys.argv[2]
+emu.build = lambda force=False: emu._SO
+from dm_control_b200 import testing_models as tm
+for name, B, nsteps, nsub in (('humanoid', 4, 6, 5), ('quadruped', 3, 4, 4), ('pendulum_free', 4, 16, 2), ('cartpole', 3, 8, 1),
+                               ('cmu_humanoid', 2, 2, 6), ('cheetah', 2050, 2, 1)):
+  model = tm.load(name)
+  q0, v0 = tm.initial_states(model, name, B, 0)
+  p = emu.EmuPhysics(model, B)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+  tape = np.random.RandomState(9).uniform(-1, 1, (nsteps, B, model.nu))
+  for t in range(nsteps):
+    p.data.ctrl[:] = tape[t]; p.step(nsub)
+print('ASAN RUN COMPLETE')
+'''
+
+
+def test_address_sanitizer_finds_nothing():
+  """memcheck without a GPU: the kernel source built with -fsanitize=address under the emulation. Every "device"
+  buffer (model blob, io arrays, handover rows) is a heap allocation with red zones, so an out-of-bounds access of the
+  kernels is reported with file:line; a deliberately undersized output buffer is the positive control."""
+  import shutil, subprocess
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  libasan = subprocess.run(['g++', '-print-file-name=libasan.so'], capture_output=True, text=True).stdout.strip()
+  if not os.path.isabs(libasan) or not os.path.exists(libasan):
+    pytest.skip('libasan not available')
+  so = os.path.join(root, 'tests', 'emu', '_build', 'libb200mj_emu_asan.so')
+  src = os.path.join(root, 'dm_control_b200', 'csrc', 'b200mj.cu')
+  hdr = os.path.join(root, 'tests', 'emu', 'cuda_emu.h')
+  if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(['g++', '-std=c++20', '-O1', '-g', '-fno-omit-frame-pointer', '-fsanitize=address', '-fPIC', '-shared',
+                           '-pthread', '-x', 'c++', '-DB200MJ_CPU_EMU', '-Wno-unknown-pragmas', '-I' + os.path.dirname(hdr), '-o', so, src])
+  env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0')
+  out = subprocess.run([sys.executable, '-c', _ASAN_SCRIPT, root, so], env=env, capture_output=True, text=True, timeout=900)
+  assert 'ERROR: AddressSanitizer' not in out.stderr, out.stderr[-3000:]
+  assert out.returncode == 0 and 'ASAN RUN COMPLETE' in out.stdout, (out.returncode, out.stderr[-2000:])
+  control = _ASAN_SCRIPT.split("for name, B")[0] + '''
+import ctypes
+model = tm.load('cheetah'); p = emu.EmuPhysics(model, 4)
+small = np.zeros((3, model.nv))
+p._io.qacc = ctypes.cast(small.ctypes.data, dict(emu.blib.IO_FIELDS)['qacc'])
+p.forward()
+'''
+  out = subprocess.run([sys.executable, '-c', control, root, so], env=env, capture_output=True, text=True, timeout=300)
+  assert 'heap-buffer-overflow' in out.stderr and 'write_outputs' in out.stderr
