@@ -197,3 +197,29 @@ def test_total_momentum_rate_is_weight(name):
   dP = (out[0] - out[1]) / (2 * eps)
   weight = float(np.sum(model.body_mass)) * np.asarray(model.opt.gravity, dtype=np.float64)
   np.testing.assert_allclose(dP, weight, rtol=1e-6, atol=1e-6 * np.abs(weight).max())
+
+
+@pytest.mark.parametrize('theta_deg,mu,slides', [(20, 0.5, False), (10, 0.3, False), (35, 0.5, True), (30, 0.3, True)])
+def test_coulomb_stick_slip_threshold_on_an_incline(theta_deg, mu, slides):
+  """A flat box on a plane under tilted gravity sticks when tan(theta) < mu and slides when tan(theta) > mu, and while
+  it slides the time-averaged friction is the Coulomb force mu*m*g*cos(theta) (pyramidal cone: exact along a pyramid
+  axis; the soft contact chatters, hence the 5 % band on the average)."""
+  import math
+  from dm_control_b200 import mjcf_compile
+  th, g, dt = math.radians(theta_deg), 9.81, 0.002
+  xml = (f'<mujoco><option timestep="{dt}" gravity="{g * math.sin(th)} 0 {-g * math.cos(th)}"/><worldbody>'
+         f'<geom name="floor" type="plane" size="50 50 .1" friction="{mu} .005 .0001"/>'
+         f'<body name="box" pos="0 0 .02"><freejoint/><geom name="box" type="box" size=".3 .3 .02" friction="{mu} .005 .0001"/></body>'
+         '</worldbody></mujoco>')
+  o = om.OraclePhysics(mjcf_compile.compile_xml(xml))
+  o.forward()
+  v = []
+  for _ in range(600):
+    o.step(1)
+    v.append(float(o.qvel[0]))
+  if not slides:
+    assert abs(v[-1]) < 5e-3 and abs(v[-1] - v[-201]) < 1e-6          # at rest (soft-constraint creep only)
+  else:
+    a = (v[-1] - v[-401]) / (400 * dt)
+    friction = g * math.sin(th) - a
+    assert friction == pytest.approx(mu * g * math.cos(th), rel=0.05)
