@@ -62,6 +62,7 @@ struct Lay {
   int rk;                                // RK4 scratch: X0q, X0v, X0a, accv, acca, accd
   int sens;                              // sensordata staging
   int vold;                              // last-step acceleration kernel: qvel before integration (for rne_post_constraint)
+  int colbuf;                            // compile-time-size algebra: column broadcast buffer (TN_COLBUF_DOUBLES)
   int total;
 };
 
@@ -89,6 +90,7 @@ struct b200mj_model {
   double* d_rdata;
   int envs_per_block;
   size_t smem_per_env;
+  int tn_nv;                  // nv when a compile-time-size acceleration kernel exists for this model, else 0
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -405,6 +407,157 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
     tj += j + 1;
   }
   if (b) chol_forward(Lm, dinv, b, y, n, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compile-time-size dense algebra for the acceleration kernels (nv = N known at compile time, N <= 31).
+//
+// The runtime-size routines above walk the packed triangle in shared memory with rolled loops: 87 % of their
+// instructions are address arithmetic, loop control and LDS, and every one waits on the one before (profiles/
+// r1_step_kernel_by_function.txt: 57 % of the acceleration kernel's stall samples). Here one lane owns one ROW of the
+// matrix in REGISTERS (N doubles), every loop is fully unrolled, so each multiply-add is one DFMA with register
+// operands and an immediate-offset broadcast load:
+//   * tn_factor: right-looking Cholesky. Column j is published once through a 2 x 32-double shared buffer
+//     (STS, __syncwarp, then lane-invariant LDS.128 broadcasts), the trailing update is N-1-j independent DFMAs per
+//     lane. The Newton Hessian  H = M + sum_active D_r J_r^T J_r  is assembled straight into the row registers, and the right-hand side rides along as row N on the spare lane N, so
+//     the forward substitution costs nothing.
+//   * tn_back / tn_forward: triangular solves with the column (row) of L in registers, pre-scaled by 1/L_jj and with
+//     the diagonal zeroed: one shuffle + one DFMA per unknown, nothing else.
+// ------------------------------------------------------------------------------------------------
+#define TN_COLBUF_DOUBLES 64
+
+// 1/sqrt(x) for x in [mjMINVAL, huge): hardware seed + two Newton steps, no special-case slow path (the library
+// rsqrt() carries a subroutine call for denormals / infinities, and a call inside the unrolled factorisation makes
+// ptxas mirror the whole register-resident row into local memory).
+__device__ __forceinline__ double pos_rsqrt(double x) {
+#ifdef B200MJ_CPU_EMU
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+#endif
+}
+
+template <int N>
+__device__ __noinline__ void tn_factor(const double* Msrc, double* Lm, double* dinv, int lane, const double* b, double* y,
+                                       const double* J, const double* SD, const int* alist, int nact, double* colbuf) {
+  constexpr int LD = N | 1;
+  double a[N];
+  const bool isrow = lane < N, isrhs = (b != nullptr) && lane == N;
+  const int ti = tri(isrow ? lane : 0);
+  {
+    const double* src = isrow ? Msrc + ti : (isrhs ? b : Msrc);
+    const int cnt = isrow ? lane + 1 : (isrhs ? N : 0);
+#pragma unroll
+    for (int k = 0; k < N; k++) a[k] = k < cnt ? src[k] : 0.0;
+  }
+  if (nact > 0) {                      // Newton Hessian: += sum over active rows of D_r J_r^T J_r (lower triangle is what counts)
+    _Pragma("unroll 1") for (int t = 0; t < nact; t++) {
+      const int r = alist[t];
+      const double* Jr = J + r * LD;
+      const double sj = isrow ? SD[r] * Jr[lane] : 0.0;
+#pragma unroll
+      for (int k = 0; k < N; k++) a[k] += sj * Jr[k];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    double* cb = colbuf + (j & 1) * 32;      // double-buffered: one __syncwarp per column is enough
+    cb[lane] = a[j];                         // raw column j (lanes < j hold upper-triangle junk that nobody reads)
+    __syncwarp();
+    double piv = cb[j];
+    if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+    const double inv = pos_rsqrt(piv);
+    const double lj = (lane == j ? piv : a[j]) * inv;      // L[i][j]; the diagonal is sqrt(piv)
+    a[j] = lj;
+    if (lane == j) dinv[j] = inv;
+    const double cc = lj * inv;                            // raw_i / piv : a[i][k] -= raw_i raw_k / piv
+    int k = j + 1;
+    if (k < N && (k & 1)) { a[k] -= cc * cb[k]; k++; }
+#pragma unroll
+    for (; k + 1 < N; k += 2) {
+      const double2 s2 = *reinterpret_cast<const double2*>(cb + k);
+      a[k] -= cc * s2.x; a[k + 1] -= cc * s2.y;
+    }
+    if (k < N) a[k] -= cc * cb[k];
+  }
+  if (isrow) {
+#pragma unroll
+    for (int k = 0; k < N; k++) if (k <= lane) Lm[ti + k] = a[k];
+  } else if (isrhs) {
+#pragma unroll
+    for (int k = 0; k < N; k++) y[k] = a[k];
+  }
+  __syncwarp();
+}
+
+// L^T x = y with column `lane` of L in registers; x = -x when negate (Newton search direction). y, x may alias.
+template <int N>
+__device__ __noinline__ void tn_back(const double* Lm, const double* dinv, const double* y, double* x, int lane, int negate) {
+  const bool on = lane < N;
+  const int li = on ? lane : 0;
+  const double d = on ? dinv[li] : 0.0;
+  double c[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) c[i] = (on && i > lane) ? Lm[((i * (i + 1)) >> 1) + li] * d : 0.0;
+  double z = on ? y[li] * d : 0.0;
+#pragma unroll
+  for (int i = N - 1; i >= 1; i--) { const double xi = __shfl_sync(FULL, z, i); z -= c[i] * xi; }
+  __syncwarp();
+  if (on) x[li] = negate ? -z : z;
+  __syncwarp();
+}
+
+// L y = b with row `lane` of L in registers. b, y may alias.
+template <int N>
+__device__ __noinline__ void tn_forward(const double* Lm, const double* dinv, const double* b, double* y, int lane) {
+  const bool on = lane < N;
+  const int li = on ? lane : 0, ti = tri(li);
+  const double d = on ? dinv[li] : 0.0;
+  double r[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = (on && k < lane) ? Lm[ti + k] * d : 0.0;
+  double z = on ? b[li] * d : 0.0;
+#pragma unroll
+  for (int j = 0; j < N - 1; j++) { const double yj = __shfl_sync(FULL, z, j); z -= r[j] * yj; }
+  __syncwarp();
+  if (on) y[li] = z;
+  __syncwarp();
+}
+
+// row `lane` of (symmetric M, packed lower triangle) * v ; v is 16-byte aligned
+template <int N>
+__device__ __forceinline__ double tn_symv_row(const double* Mp, const double* v, int lane) {
+  const int li = lane < N ? lane : N - 1, ti = tri(li);
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+  for (int k = 0; k + 1 < N; k += 2) {
+    const double2 v2 = *reinterpret_cast<const double2*>(v + k);
+    const double m0 = Mp[k <= li ? ti + k : ((k * (k + 1)) >> 1) + li];
+    const double m1 = Mp[k + 1 <= li ? ti + k + 1 : (((k + 1) * (k + 2)) >> 1) + li];
+    if ((k & 2) == 0) { s0 += m0 * v2.x; s1 += m1 * v2.y; } else { s2 += m0 * v2.x; s3 += m1 * v2.y; }
+  }
+  if (N & 1) s0 += Mp[N - 1 <= li ? ti + N - 1 : (((N - 1) * N) >> 1) + li] * v[N - 1];
+  return (s0 + s1) + (s2 + s3);
+}
+
+// dot product of one Jacobian row (this lane's) with a 16-byte-aligned nv-vector
+template <int N>
+__device__ __forceinline__ double tn_dot_row(const double* row, const double* v) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+  for (int k = 0; k + 1 < N; k += 2) {
+    const double2 v2 = *reinterpret_cast<const double2*>(v + k);
+    if ((k & 2) == 0) { s0 += row[k] * v2.x; s1 += row[k + 1] * v2.y; } else { s2 += row[k] * v2.x; s3 += row[k + 1] * v2.y; }
+  }
+  if (N & 1) s0 += row[N - 1] * v[N - 1];
+  return (s0 + s1) + (s2 + s3);
 }
 
 // bottom-up accumulation child -> parent for a [nbody, width] table. Bodies are numbered parents-first, so one
@@ -1225,6 +1378,7 @@ __device__ __forceinline__ void fwd_actuation(const Ctx& c) {
   __syncwarp();
 }
 
+template <int NVT>
 __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& io, int env) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
   FOR_LANES(i, nv) {
@@ -1254,18 +1408,29 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
   }
   __syncwarp();
   // factor M into the H buffer (free until the Newton solver assembles its Hessian there)
-  chol_factor(W(M), W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
-  chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
+  if constexpr (NVT > 0) {
+    tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(smooth), W(qaccs), nullptr, nullptr, nullptr, 0, W(colbuf));
+    tn_back<NVT>(W(H), W(dinv), W(qaccs), W(qaccs), lane, 0);
+  } else {
+    chol_factor(W(M), W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
+    chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
+  }
 }
 
 // --- Newton solver ---------------------------------------------------------------------------------
 struct Primal { double cost, gauss; int nact, changed; };
 
 // Ma = M qacc ; jar = J qacc - aref
+template <int NVT>
 __device__ __forceinline__ void compute_Ma_jar(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
-  FOR_LANES(i, nv) W(Ma)[i] = symv_row(W(M), W(qacc), nv, i);
-  FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * ld, W(qacc), nv) - W(aref)[r];
+  if constexpr (NVT > 0) {
+    if (lane < NVT) W(Ma)[lane] = tn_symv_row<NVT>(W(M), W(qacc), lane);
+    FOR_LANES(r, nefc) W(jar)[r] = tn_dot_row<NVT>(W(J) + r * ld, W(qacc)) - W(aref)[r];
+  } else {
+    FOR_LANES(i, nv) W(Ma)[i] = symv_row(W(M), W(qacc), nv, i);
+    FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * ld, W(qacc), nv) - W(aref)[r];
+  }
   __syncwarp();
 }
 
@@ -1309,11 +1474,19 @@ __device__ __forceinline__ Primal constraint_update(const Ctx& c, int nefc) {
 
 // grad; (re)assemble H = M + J^T diag(SD) J and factor it only when the active set changed; search = -H^-1 grad.
 // Returns |grad|.
+template <int NVT>
 __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int nact, bool refactor) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double gpart = 0;
   FOR_LANES(i, nv) { double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; W(grad)[i] = g; gpart += g * g; }
   double gnorm = sqrt(warp_sum(gpart));
+  if constexpr (NVT > 0) {
+    __syncwarp();
+    if (refactor) tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(grad), W(search), W(J), W(efcSD), reinterpret_cast<const int*>(W(actlist)), nact, W(colbuf));
+    else tn_forward<NVT>(W(H), W(dinv), W(grad), W(search), lane);
+    tn_back<NVT>(W(H), W(dinv), W(search), W(search), lane, 1);
+    return gnorm;
+  }
   if (refactor) {
     const int* alist = reinterpret_cast<const int*>(W(actlist));
     // lane j owns column j (and j+32) of the lower triangle; rows in register blocks of 8
@@ -1357,6 +1530,7 @@ __device__ __forceinline__ void ls_eval(const Ctx& c, int nefc, double alpha, co
   *d2 = 2 * q2;
 }
 
+template <int NVT>
 __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Primal& pr) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   double sp = 0;
@@ -1365,12 +1539,21 @@ __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Prim
   if (snorm < BMJ_MINVAL) return 0;
   double gtol = m.tolerance * m.ls_tolerance * snorm * (m.meaninertia * max(1, nv));
   double g1 = 0, g2 = 0;
-  FOR_LANES(i, nv) {
-    double s = symv_row(W(M), W(search), nv, i);
-    W(Mv)[i] = s;
-    g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
+  if constexpr (NVT > 0) {
+    if (lane < NVT) {
+      double s = tn_symv_row<NVT>(W(M), W(search), lane);
+      W(Mv)[lane] = s;
+      g1 += W(search)[lane] * (W(Ma)[lane] - W(smooth)[lane]); g2 += 0.5 * W(search)[lane] * s;
+    }
+    FOR_LANES(r, nefc) W(jv)[r] = tn_dot_row<NVT>(W(J) + r * ld, W(search));
+  } else {
+    FOR_LANES(i, nv) {
+      double s = symv_row(W(M), W(search), nv, i);
+      W(Mv)[i] = s;
+      g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
+    }
+    FOR_LANES(r, nefc) W(jv)[r] = dot_rows(W(J) + r * ld, W(search), nv);
   }
-  FOR_LANES(r, nefc) W(jv)[r] = dot_rows(W(J) + r * ld, W(search), nv);
   double qg[3] = {pr.gauss, warp_sum(g1), warp_sum(g2)};
   __syncwarp();
   double d1, d2;
@@ -1398,6 +1581,7 @@ __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Prim
 // level 1: coarse points (pass start, before / after the solver); 2: every stage boundary; 3: also every Newton trip
 #define PHASE_SYNC(level) do { if (c.sync_level >= (level)) __syncthreads(); } while (0)
 
+template <int NVT>
 __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
   Primal pr; pr.cost = 0; pr.gauss = 0; pr.nact = 0; pr.changed = 1;
@@ -1411,14 +1595,15 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
       if (cand == 0) {
         FOR_LANES(i, nv) W(qacc)[i] = W(qaccws)[i];
         __syncwarp();
-        compute_Ma_jar(c, nefc);
+        compute_Ma_jar<NVT>(c, nefc);
       } else if (cand == 1) {
         // park the warm-start products (Mv / jv are free until the first line search); for the unconstrained
         // candidate M qacc_smooth = qfrc_smooth by construction, so only J qacc_smooth is a product
         FOR_LANES(i, nv) { W(Mv)[i] = W(Ma)[i]; W(qacc)[i] = W(qaccs)[i]; W(Ma)[i] = W(smooth)[i]; }
         FOR_LANES(r, nefc) W(jv)[r] = W(jar)[r];
         __syncwarp();
-        FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * m.ldv, W(qacc), nv) - W(aref)[r];
+        if constexpr (NVT > 0) { FOR_LANES(r, nefc) W(jar)[r] = tn_dot_row<NVT>(W(J) + r * m.ldv, W(qacc)) - W(aref)[r]; }
+        else { FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * m.ldv, W(qacc), nv) - W(aref)[r]; }
         __syncwarp();
       } else {
         if (!(warm && cost_warm < pr.cost)) break;
@@ -1441,7 +1626,7 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
     // every warp of the CTA takes the same number of trips: finished environments idle at the barrier
     if (c.sync_level >= 3) { if (!__syncthreads_or(!done)) break; } else if (done) break;
     if (!done) {
-      double gnorm = newton_direction(c, nefc, pr.nact, refactor);
+      double gnorm = newton_direction<NVT>(c, nefc, pr.nact, refactor);
       bool stop = false;
       if (iter > 0) {
         double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
@@ -1449,7 +1634,7 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
       }
       if (iter >= m.iterations) stop = true;
       double alpha = 0;
-      if (!stop) { alpha = line_search(c, nefc, pr); if (alpha == 0) stop = true; }
+      if (!stop) { alpha = line_search<NVT>(c, nefc, pr); if (alpha == 0) stop = true; }
       if (stop) done = true;
       else {
         FOR_LANES(i, nv) { W(qacc)[i] += alpha * W(search)[i]; W(Ma)[i] += alpha * W(Mv)[i]; }
@@ -1698,10 +1883,20 @@ __device__ __forceinline__ void reset_state(const Ctx& c, double* time) {
   __syncwarp();
 }
 
+template <int NVT>
 __device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv; double h = m.timestep;
   advance_act(c, W(act), W(actdot), 1.0, h);
-  if (m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
+  if (NVT > 0 && m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
+    if constexpr (NVT > 0) {
+      // M is dead after the solver: M + h diag(damping) is formed in place
+      FOR_LANES(i, nv) { W(tmpv)[i] = W(smooth)[i] + W(qcon)[i]; W(M)[tri(i) + i] += h * m.dof_damping[i]; }
+      __syncwarp();
+      tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(tmpv), W(tmpv), nullptr, nullptr, nullptr, 0, W(colbuf));
+      tn_back<NVT>(W(H), W(dinv), W(tmpv), W(tmpv), lane, 0);
+      FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
+    }
+  } else if (m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
     _Pragma("unroll 1") for (int i = lane; i < tri(nv); i += 32) W(H)[i] = W(M)[i];
     FOR_LANES(i, nv) W(tmpv)[i] = W(smooth)[i] + W(qcon)[i];
     __syncwarp();
@@ -1832,9 +2027,9 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
     if (!final_pass) {
       PHASE_SYNC(2);
       fwd_actuation(c);
-      fwd_acceleration(c, io, env);
+      fwd_acceleration<0>(c, io, env);
       PHASE_SYNC(1);
-      niter = solve_newton(c, nefc);
+      niter = solve_newton<0>(c, nefc);
     }
     if (sub == 0) { r_ncon = ncon; r_nefc = nefc; if (!final_pass) r_niter = niter; }
     const bool out_acc = !final_pass && sub == 0 && last;
@@ -1847,7 +2042,7 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
     // ---------------- integration ----------------
     PHASE_SYNC(2);
     if (sub == 0 && check_bad(c, W(qacc), m.nv)) { w_badqacc++; reset_state(c, &time); step_idx++; continue; }
-    if (!rk4) { euler_step(c, &time); step_idx++; }
+    if (!rk4) { euler_step<0>(c, &time); step_idx++; }
     else {
       // classic RK4 over (qpos, qvel, act): stage `sub` has just produced F_sub = (qvel, qacc, act_dot)
       const int nq = m.nq, nv = m.nv, na = m.na; const double h = m.timestep;
@@ -1993,7 +2188,7 @@ b200mj_posfinal_kernel(const __grid_constant__ DevModel m, const __grid_constant
 }
 
 // LAST = last physics step of a fused step(): acceleration-stage sensors and outputs are produced here
-template <bool LAST>
+template <bool LAST, int NVT>
 __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L, const Hand& H, const Hand2& H2, const b200mj_io& io,
                                                 const double* hand, const double* hand2, int batch, int extra_disable, int first_pass,
                                                 int rows_gt, int rows_le, int flags, int env0) {
@@ -2009,7 +2204,7 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   // fewer than rows_gt+1) rows are served by the launch with the matching workspace and leave at once here
   if (nefc <= rows_gt || nefc > rows_le) return;
   Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, 0);
-  const int nv = m.nv, ld = m.ldv;
+  const int nv = NVT > 0 ? NVT : m.nv, ld = NVT > 0 ? (NVT | 1) : m.ldv;
   // ---- load state + handover ----
   FOR_LANES(i, m.nq) W(qpos)[i] = io.qpos[e * m.nq + i];
   FOR_LANES(i, nv) { W(qvel)[i] = io.qvel[e * nv + i]; W(qaccws)[i] = io.qacc_warmstart ? io.qacc_warmstart[e * nv + i] : 0.0;
@@ -2029,12 +2224,12 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   if (check_bad(c, W(ctrl), m.nu)) { w_badctrl = first_pass; FOR_LANES(i, m.nu) W(ctrl)[i] = 0; __syncwarp(); }
   fwd_actuation(c);
   b200mj_io io_noforce = io; io_noforce.qfrc_applied = nullptr; io_noforce.xfrc_applied = nullptr;
-  fwd_acceleration(c, io_noforce, env);
-  int niter = solve_newton(c, nefc);
+  fwd_acceleration<NVT>(c, io_noforce, env);
+  int niter = solve_newton<NVT>(c, nefc);
   if (LAST) write_outputs(c, io, env, ncon, nefc, niter, false, true, false);
   if (want_sens) FOR_LANES(i, nv) W(vold)[i] = W(qvel)[i];
   if (check_bad(c, W(qacc), nv)) { w_badqacc = 1; reset_state(c, &time); }
-  else euler_step(c, &time);
+  else euler_step<NVT>(c, &time);
   // ---- store state ----
   FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];
   FOR_LANES(i, nv) { io.qvel[e * nv + i] = W(qvel)[i]; if (io.qacc_warmstart) io.qacc_warmstart[e * nv + i] = W(qaccws)[i]; }
@@ -2069,19 +2264,48 @@ extern "C" __global__ void __launch_bounds__(256)
 b200mj_acc_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                   const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
                   int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0) {
-  acc_kernel_body<false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
+  acc_kernel_body<false, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
 }
 extern "C" __global__ void __launch_bounds__(256)
 b200mj_acclast_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                       const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
                       int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0) {
-  acc_kernel_body<true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
+  acc_kernel_body<true, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
+}
+
+// Acceleration kernels with nv fixed at compile time (register-resident algebra, tn_* above). One instantiation per
+// nv of B200MJ_NV_LIST — the dofs of the benchmark configurations (cheetah 9, quadruped 22, humanoid 27) and a few
+// common small sizes; any other model runs the runtime-size kernels above. Same arguments, same handover format.
+#ifndef B200MJ_NV_LIST
+#define B200MJ_NV_LIST(X) X(6) X(9) X(12) X(18) X(22) X(27)
+#endif
+template <bool LAST, int NVT>
+__global__ void __launch_bounds__(32, 16)
+b200mj_acc_tn_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
+                     const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
+                     int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0) {
+  acc_kernel_body<LAST, NVT>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------------
 static int64_t g_launches = 0;
+
+typedef void (*acc_kernel_fn)(const DevModel, const Lay, const Hand, const Hand2, const b200mj_io, const double*, const double*,
+                              int, int, int, int, int, int, int);
+// the compile-time-size acceleration kernel for nv dofs, or nullptr (B200MJ_TN=0 disables them: A/B runs)
+static acc_kernel_fn tn_kernel(int nv, bool last) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B200MJ_TN"); on = e ? atoi(e) : 1; }
+  if (!on) return nullptr;
+  switch (nv) {
+#define TN_CASE(n) case n: return last ? (acc_kernel_fn)b200mj_acc_tn_kernel<true, n> : (acc_kernel_fn)b200mj_acc_tn_kernel<false, n>;
+    B200MJ_NV_LIST(TN_CASE)
+#undef TN_CASE
+    default: return nullptr;
+  }
+}
 
 static void build_layout(b200mj_model* M) {
   DevModel& m = M->dm; Lay& L = M->lay;
@@ -2140,7 +2364,7 @@ static void build_layout(b200mj_model* M) {
       o = 0;
       A.qpos = take(m.nq); A.qvel = take(nv); A.act = take(m.na); A.ctrl = take(m.nu); A.qaccws = take(nv); A.actdot = take(m.na);
       A.tenlen = take(m.ntendon); A.tenJ = take(m.ntendon * ld); A.actforce = take(m.nu);
-      A.force = take(rows); A.qacc = take(nv); A.vold = take(with_sens ? nv : 0);
+      A.force = take(rows); A.qacc = take(nv); A.vold = take(with_sens ? nv : 0); A.colbuf = take(M->tn_nv ? TN_COLBUF_DOUBLES : 0);
       // Everything below is dead once the state has been integrated; the sensor-carrying variant then re-uses the
       // storage for the position-stage dump that rne_post_constraint and the acceleration-stage sensors read.
       const int u0 = o;
@@ -2292,6 +2516,7 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   for (int i = 0; i < n_condim; i++) if (h_condim[i] != 1 && h_condim[i] != 3) unsupported = true;
   for (int i = 0; i < n_fl; i++) if (h_fl[i] != 0) unsupported = true;
   if (unsupported) { b200mj_model_destroy(M); return -3; }
+  M->tn_nv = tn_kernel(m.nv, false) ? m.nv : 0;
   build_layout(M);
   if (M->envs_per_block < 1) { b200mj_model_destroy(M); return -4; }
   for (int g = 0; g < 3; g++) {
@@ -2306,6 +2531,10 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   cudaFuncSetAttribute(b200mj_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_acclast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_posfinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (M->tn_nv) {
+    cudaFuncSetAttribute(tn_kernel(M->tn_nv, false), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tn_kernel(M->tn_nv, true), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
   *out = M;
   return 0;
 }
@@ -2416,7 +2645,12 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         int gt = b == 0 ? -1 : M->rows_cap[b - 1], le = M->rows_cap[b];
         cudaStream_t sb = b == 0 ? sm : M->gaux[g][b];     // buckets are independent: let them share the SMs
         if (b > 0) cudaStreamWaitEvent(sb, M->ev_pos[g], 0);
-        if (last) B200MJ_LAUNCH(b200mj_acclast_kernel, cnt, 32, M->smem_accs_b[b] + acc_pad, sb, M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        if (M->tn_nv) {
+          acc_kernel_fn fn = tn_kernel(M->tn_nv, last);
+          const Lay& la = last ? M->lay_accs_b[b] : M->lay_acc_b[b];
+          B200MJ_LAUNCH(fn, cnt, 32, (last ? M->smem_accs_b[b] : M->smem_acc_b[b]) + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                        e1, 0, s == 0, gt, le, flags, e0);
+        } else if (last) B200MJ_LAUNCH(b200mj_acclast_kernel, cnt, 32, M->smem_accs_b[b] + acc_pad, sb, M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                             e1, 0, s == 0, gt, le, flags, e0);
         else B200MJ_LAUNCH(b200mj_acc_kernel, cnt, 32, M->smem_acc_b[b] + acc_pad, sb, M->dm, M->lay_acc_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                   e1, 0, s == 0, gt, le, flags, e0);

@@ -193,14 +193,58 @@ def test_launch_knobs_do_not_change_results():
     out = subprocess.run([sys.executable, '-c', _KNOB_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout.strip().splitlines()[-1]
+  # the default path: acceleration kernels with nv fixed at compile time (register-resident algebra)
   ref = digest()
-  for knobs in (dict(B200MJ_SPLIT='0'), dict(B200MJ_SPLIT='1'), dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_BUCKETS='6,12,24'),
-                dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'), dict(B200MJ_ENVS_PER_BLOCK='2', B200MJ_SPLIT='0'),
-                dict(B200MJ_SYNC_LEVEL='0', B200MJ_SPLIT='0'),
+  for knobs in (dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_BUCKETS='6,12,24'), dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'),
                 # the emulator running the lanes of every block in descending instead of ascending order: a cross-lane
                 # dependency through shared memory that no collective or barrier separates would change the result
-                dict(B200MJ_EMU_ORDER='reverse'), dict(B200MJ_EMU_ORDER='reverse', B200MJ_SPLIT='0')):
+                dict(B200MJ_EMU_ORDER='reverse')):
     assert digest(**knobs) == ref, knobs
+  # B200MJ_TN=0: the runtime-size acceleration kernels share their arithmetic with the fused kernel, so there the
+  # fused, hybrid and all-split paths must agree bit for bit as well
+  ref0 = digest(B200MJ_TN='0')
+  for knobs in (dict(B200MJ_SPLIT='0'), dict(B200MJ_SPLIT='1'), dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_ENVS_PER_BLOCK='2', B200MJ_SPLIT='0'),
+                dict(B200MJ_SYNC_LEVEL='0', B200MJ_SPLIT='0'), dict(B200MJ_EMU_ORDER='reverse', B200MJ_SPLIT='0')):
+    assert digest(B200MJ_TN='0', **knobs) == ref0, knobs
+
+
+_TN_SCRIPT = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], 'tests', 'emu'))
+import b200mj_emu as emu
+from dm_control_b200 import testing_models as tm
+out = {}
+for name, B, nsteps, nsub in (('humanoid', 6, 6, 5), ('quadruped', 4, 5, 4), ('cheetah', 4, 8, 3)):
+  model = tm.load(name)
+  q0, v0 = tm.initial_states(model, name, B, 0)
+  p = emu.EmuPhysics(model, B)
+  p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+  tape = np.random.RandomState(9).uniform(-1, 1, (nsteps, B, model.nu))
+  for t in range(nsteps):
+    p.data.ctrl[:] = tape[t]; p.step(nsub)
+  out[name] = dict(qpos=p.data.qpos.tolist(), qvel=p.data.qvel.tolist(), ncon=p.data.ncon.tolist(), sens=p.data.sensordata.tolist())
+print(json.dumps(out))
+'''
+
+
+def test_compile_time_size_kernels_match_runtime_size_kernels():
+  """The acceleration kernels with nv fixed at compile time (tn_* algebra: other summation order, other Cholesky
+  variant) against the runtime-size kernels on the same rollouts: same contacts, states equal to rounding noise."""
+  import subprocess, json
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  res = []
+  for tn in ('1', '0'):
+    e = dict(os.environ, B200MJ_TN=tn)
+    out = subprocess.run([sys.executable, '-c', _TN_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res.append(json.loads(out.stdout.strip().splitlines()[-1]))
+  for name in res[0]:
+    a, b = res[0][name], res[1][name]
+    assert a['ncon'] == b['ncon'], name
+    for f in ('qpos', 'qvel', 'sens'):
+      x, y = np.asarray(a[f]), np.asarray(b[f])
+      assert np.abs(x - y).max() <= 1e-8 * (1 + np.abs(y).max()), (name, f, np.abs(x - y).max())
 
 
 def test_malformed_blob_is_refused_and_capacity_change_reallocates(oracle_mod):

@@ -153,17 +153,24 @@ def test_fused_and_split_paths_agree_bitwise(monkeypatch):
           "from dm_control_b200 import testing_models as tm; from dm_control_b200.physics import BatchedPhysics;"
           "m = tm.load('humanoid'); q, v = tm.initial_states(m, 'humanoid', 32, 5); p = BatchedPhysics(m, batch=32);"
           "p.data.qpos.copy_(torch.as_tensor(q)); p.data.qvel.copy_(torch.as_tensor(v)); p.forward();"
-          "g = torch.Generator(device=DEV).manual_seed(0);"
+          "g = torch.Generator(device='cuda').manual_seed(0);"
           "[ (p.data.ctrl.uniform_(-1, 1, generator=g), p.step(5)) for _ in range(6) ];"
           "print(json.dumps(dict(q=p.data.qpos.cpu().tolist(), s=p.data.sensordata.cpu().tolist(), n=p.data.ncon.cpu().tolist())))"
           ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   outs = []
-  for split in ('0', '1', '2'):
-    env = dict(os.environ, B200MJ_SPLIT=split)
+  # B200MJ_TN=0: runtime-size acceleration kernels (they share their arithmetic with the fused kernel); the last run is the
+  # default path, acceleration kernels with nv fixed at compile time (other summation order: equal to rounding noise only)
+  for split, tn in (('0', '0'), ('1', '0'), ('2', '0'), ('2', '1')):
+    env = dict(os.environ, B200MJ_SPLIT=split, B200MJ_TN=tn)
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
   assert outs[0] == outs[1] == outs[2]
+  import numpy as np
+  assert outs[3]['n'] == outs[2]['n']
+  for f in ('q', 's'):
+    a, b = np.asarray(outs[3][f]), np.asarray(outs[2][f])
+    assert np.abs(a - b).max() <= 1e-8 * (1 + np.abs(b).max()), (f, np.abs(a - b).max())
 
 
 SLIDING_CUBE = """
