@@ -58,6 +58,8 @@ _CACHE = {}
 
 
 def load(name):
+  if name.endswith('_floor'):        # same model, other family of start states (initial_states)
+    name = name[:-len('_floor')]
   if name in _CACHE:
     return _CACHE[name]
   if name in XML:
@@ -80,6 +82,19 @@ def initial_states(model, name, batch, seed=0):
   nq, nv = model.nq, model.nv
   q = np.tile(model.qpos0, (batch, 1)).astype(np.float64)
   v = np.zeros((batch, nv))
+  if name.endswith('_floor'):
+    # upright, a little above the floor, small joint offsets, at rest: the model drops onto its feet / toes and stays
+    # in contact (the tumbling starts below launch a deeply penetrating quadruped into the air instead)
+    for e in range(batch):
+      rs = np.random.RandomState(seed * 100003 + e + 555)
+      for j in range(model.njnt):
+        t, qa = model.jnt_type[j], model.jnt_qposadr[j]
+        if t == 0:
+          q[e, qa + 2] = model.qpos0[qa + 2] + rs.uniform(0.02, 0.12)
+        elif t in (2, 3) and model.jnt_limited[j]:
+          lo, hi = model.jnt_range[j]
+          q[e, qa] = np.clip(model.qpos0[qa] + rs.uniform(-0.1, 0.1), lo + 0.02 * (hi - lo), hi - 0.02 * (hi - lo))
+    return q, v
   for e in range(batch):
     rs = np.random.RandomState(seed * 100003 + e)
     for j in range(model.njnt):
