@@ -84,6 +84,8 @@ struct b200mj_model {
   // environment groups x row buckets run on their own streams (independent work: hides each launch's tail)
   cudaStream_t gmain[3], gaux[3][4]; cudaEvent_t ev_fork, ev_join[3], ev_pos[3], ev_acc[3][4]; int streams_ok;
   double* d_hand; int hand_batch;
+  // the trailing mj_step1 of the last split-path step left a complete handover for this (io, batch): see B200MJ_STEP_REUSE_POS
+  const double* reuse_qpos; int reuse_batch; int reuse_flags; int reuse_ok;
   int epb_pos, epb_acc;
   size_t smem_pos, smem_acc;
   int* d_idata;
@@ -426,7 +428,7 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
 // ------------------------------------------------------------------------------------------------
 #define TN_COLBUF_DOUBLES 64
 
-// 1/sqrt(x) for x in [mjMINVAL, huge): hardware seed + two Newton steps, no special-case slow path (the library
+// 1/sqrt(x) for x in [mjMINVAL, huge): hardware seed + one cubic step, no special-case slow path (the library
 // rsqrt() carries a subroutine call for denormals / infinities, and a call inside the unrolled factorisation makes
 // ptxas mirror the whole register-resident row into local memory).
 __device__ __forceinline__ double pos_rsqrt(double x) {
@@ -435,12 +437,20 @@ __device__ __forceinline__ double pos_rsqrt(double x) {
 #else
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double h = 0.5 * x;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
+  // one third-order step: e = 1 - x y^2, y <- y (1 + e/2 + 3 e^2 / 8): 2^-22 seed -> full double precision
+  const double e = fma(-x, y * y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  y = fma(y * e, p, y);
   return y;
+#endif
+}
+
+// a zero the compiler cannot see through: keeps ptxas from cloning the 20 KB tn_factor per call site (instruction cache)
+__device__ __forceinline__ int opaque_zero() {
+#ifdef B200MJ_CPU_EMU
+  return 0;
+#else
+  int z; asm volatile("mov.s32 %0, 0;" : "=r"(z)); return z;
 #endif
 }
 
@@ -457,28 +467,38 @@ __device__ __noinline__ void tn_factor(const double* Msrc, double* Lm, double* d
 #pragma unroll
     for (int k = 0; k < N; k++) a[k] = k < cnt ? src[k] : 0.0;
   }
-  if (nact > 0) {                      // Newton Hessian: += sum over active rows of D_r J_r^T J_r (lower triangle is what counts)
-    _Pragma("unroll 1") for (int t = 0; t < nact; t++) {
-      const int r = alist[t];
-      const double* Jr = J + r * LD;
-      const double sj = isrow ? SD[r] * Jr[lane] : 0.0;
+  // Newton Hessian: += sum over active rows of D_r J_r^T J_r (lower triangle is what counts)
+  _Pragma("unroll 1") for (int t = 0; t < nact; t++) {
+    const int r = alist[t];
+    const double* Jr = J + r * LD;
+    const double sj = isrow ? SD[r] * Jr[lane] : 0.0;
 #pragma unroll
-      for (int k = 0; k < N; k++) a[k] += sj * Jr[k];
-    }
+    for (int k = 0; k < N; k++) a[k] += sj * Jr[k];
   }
+  // Software-pipelined right-looking elimination. The dependent chain of a column is
+  //   a[j] update -> pivot broadcast (shuffle) -> 1/sqrt -> scale -> first update of column j+1,
+  // and a warp issues in order: so the chain of column j+1 is started BEFORE the remaining N-j-2 independent updates
+  // of column j are issued, and those fill its latency. The column itself travels through a double-buffered shared
+  // row: iteration j reads buffer j&1 and publishes column j+1 into the other one, whose last readers (iteration j-1)
+  // are behind the __syncwarp that closed that iteration.
+  double piv = __shfl_sync(FULL, a[0], 0);
+  colbuf[lane] = a[0];
+  double inv = pos_rsqrt(piv < BMJ_MINVAL ? BMJ_MINVAL : piv);
+  __syncwarp();
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    double* cb = colbuf + (j & 1) * 32;      // double-buffered: one __syncwarp per column is enough
-    cb[lane] = a[j];                         // raw column j (lanes < j hold upper-triangle junk that nobody reads)
-    __syncwarp();
-    double piv = cb[j];
-    if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
-    const double inv = pos_rsqrt(piv);
-    const double lj = (lane == j ? piv : a[j]) * inv;      // L[i][j]; the diagonal is sqrt(piv)
+    const double* cb = colbuf + (j & 1) * 32;
+    const double lj = (lane == j ? (piv < BMJ_MINVAL ? BMJ_MINVAL : piv) : a[j]) * inv;      // L[i][j]; the diagonal is sqrt(piv)
+    const double cc = a[j] * (inv * inv);                  // raw_i / piv : a[i][k] -= raw_i raw_k / piv
     a[j] = lj;
     if (lane == j) dinv[j] = inv;
-    const double cc = lj * inv;                            // raw_i / piv : a[i][k] -= raw_i raw_k / piv
-    int k = j + 1;
+    if (j + 1 < N) {
+      a[j + 1] -= cc * cb[j + 1];
+      piv = __shfl_sync(FULL, a[j + 1], j + 1);            // next pivot: start its chain now
+      colbuf[((j + 1) & 1) * 32 + lane] = a[j + 1];        // raw column j+1 (lanes <= j hold junk that nobody reads)
+      inv = pos_rsqrt(piv < BMJ_MINVAL ? BMJ_MINVAL : piv);
+    }
+    int k = j + 2;
     if (k < N && (k & 1)) { a[k] -= cc * cb[k]; k++; }
 #pragma unroll
     for (; k + 1 < N; k += 2) {
@@ -486,6 +506,7 @@ __device__ __noinline__ void tn_factor(const double* Msrc, double* Lm, double* d
       a[k] -= cc * s2.x; a[k + 1] -= cc * s2.y;
     }
     if (k < N) a[k] -= cc * cb[k];
+    __syncwarp();
   }
   if (isrow) {
 #pragma unroll
@@ -1409,7 +1430,7 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
   __syncwarp();
   // factor M into the H buffer (free until the Newton solver assembles its Hessian there)
   if constexpr (NVT > 0) {
-    tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(smooth), W(qaccs), nullptr, nullptr, nullptr, 0, W(colbuf));
+    tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(smooth), W(qaccs), W(J), W(efcSD), reinterpret_cast<const int*>(W(actlist)), opaque_zero(), W(colbuf));
     tn_back<NVT>(W(H), W(dinv), W(qaccs), W(qaccs), lane, 0);
   } else {
     chol_factor(W(M), W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
@@ -1892,7 +1913,7 @@ __device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
       // M is dead after the solver: M + h diag(damping) is formed in place
       FOR_LANES(i, nv) { W(tmpv)[i] = W(smooth)[i] + W(qcon)[i]; W(M)[tri(i) + i] += h * m.dof_damping[i]; }
       __syncwarp();
-      tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(tmpv), W(tmpv), nullptr, nullptr, nullptr, 0, W(colbuf));
+      tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(tmpv), W(tmpv), W(J), W(efcSD), reinterpret_cast<const int*>(W(actlist)), opaque_zero(), W(colbuf));
       tn_back<NVT>(W(H), W(dinv), W(tmpv), W(tmpv), lane, 0);
       FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
     }
@@ -2150,8 +2171,10 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
     subtree_vel(c);
     if (want_sens) sensors(c, 3, ncon);
     write_outputs(c, io, env, ncon, nefc, 0, true, false, want_sens);
-  } else {
-    // hand over the small tables the actuation stage needs and the row counts
+  }
+  if (!FINAL || with_constraints) {
+    // hand over the small tables the actuation stage needs and the row counts (the trailing step1 does so too: the
+    // next call may start from its handover, B200MJ_STEP_REUSE_POS)
     FOR_LANES(t, m.ntendon) hrow[H.tenlen + t] = W(tenlen)[t];
     copy_row(hrow + H.tenJ, W(tenJ), m.ntendon * m.ldv, lane);
     if (lane == 0) { int* cnt = reinterpret_cast<int*>(hrow + H.counts); cnt[0] = ncon; cnt[1] = nefc; }
@@ -2557,6 +2580,7 @@ void b200mj_model_destroy(b200mj_model* M) {
 int b200mj_model_set_disableflags(b200mj_model* M, int disableflags) {
   if (!M) return -1;
   M->dm.disableflags = disableflags;
+  M->reuse_ok = 0;
   return 0;
 }
 
@@ -2567,12 +2591,13 @@ int b200mj_model_set_capacity(b200mj_model* M, int nconmax, int njmax) {
   // the handover rows are sized by the layout: drop them, the next b200mj_step allocates for the new capacities
   if (M->d_hand) cudaFree(M->d_hand);
   if (M->d_hand2) cudaFree(M->d_hand2);
-  M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0;
+  M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0; M->reuse_ok = 0;
   return M->envs_per_block < 1 ? -4 : 0;
 }
 
 static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, int mode, int extra, void* stream) {
   if (!M || !io || batch <= 0 || nstep < 0) return -1;
+  const_cast<b200mj_model*>(M)->reuse_ok = 0;      // the fused kernel leaves no handover behind
   if (!io->qpos || !io->qvel || (M->dm.na > 0 && !io->act)) return -1;
   int epb = M->envs_per_block;
   int grid = (batch + epb - 1) / epb;
@@ -2603,7 +2628,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   if (M->hand_batch < batch) {
     if (M->d_hand) cudaFree(M->d_hand);
     if (M->d_hand2) cudaFree(M->d_hand2);
-    M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0;
+    M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0; M->reuse_ok = 0;
     if (cudaMalloc(&M->d_hand, (size_t)batch * M->hand.total * sizeof(double)) != cudaSuccess) return -2;
     if (cudaMalloc(&M->d_hand2, (size_t)batch * M->hand2.total * sizeof(double)) != cudaSuccess) return -2;
     M->hand_batch = batch;
@@ -2615,6 +2640,10 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   // == 1: split kernels for the first nstep-1 physics steps, the fused kernel for the last one. == 0: fused only.
   const bool all_split = split_enabled() >= 2;
   const int nsplit = all_split ? nstep : nstep - 1;
+  // B200MJ_STEP_REUSE_POS: the previous call's trailing mj_step1 wrote this state's handover rows already
+  const bool reuse = (flags & B200MJ_STEP_REUSE_POS) && all_split && nstep >= 1 && M->reuse_ok && M->reuse_qpos == io->qpos &&
+                     M->reuse_batch == batch && M->reuse_flags == (flags & ~B200MJ_STEP_REUSE_POS);
+  M->reuse_ok = 0;
   // Environment groups (B200MJ_GROUPS, default 2 for batches >= 2048): the launch sequence of each group is
   // independent of the others, so groups run on their own streams and one group's position kernel fills the tail of
   // the other's acceleration kernels. Measured on the humanoid workload: 2 groups +2.1 %, 3 groups -6.5 % (with the
@@ -2632,9 +2661,11 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     const int gp = (cnt + M->epb_pos - 1) / M->epb_pos;
     for (int s = 0; s < nsplit; s++) {
       const bool last = all_split && s == nstep - 1;
-      B200MJ_LAUNCH(b200mj_pos_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                               e1, 0, flags, last && want_sens, e0);
-      g_launches++;
+      if (!(reuse && s == 0)) {
+        B200MJ_LAUNCH(b200mj_pos_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                                                                                 e1, 0, flags, last && want_sens, e0);
+        g_launches++;
+      }
       if (M->nbucket > 1) cudaEventRecord(M->ev_pos[g], sm);
       // optional largest-rows-first launch order: the big-workspace environments run longest, so they could start earliest and the
       // many small ones fill in around them (B200MJ_BUCKET_ORDER=1; measured equal to ascending order on the humanoid workload, so ascending stays the default)
@@ -2661,13 +2692,16 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     }
     if (all_split) {
       B200MJ_LAUNCH(b200mj_posfinal_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                                    e1, 0, flags, 0, e0);
+                                                                                    e1, 0, flags, want_sens, e0);
       g_launches++;
     }
     if (g > 0) { cudaEventRecord(M->ev_join[g], sm); cudaStreamWaitEvent(st, M->ev_join[g], 0); }
   }
   if (cudaGetLastError() != cudaSuccess) return -5;
-  if (all_split) return 0;
+  if (all_split) {
+    if (flags & B200MJ_STEP_FULL_FINAL) { M->reuse_ok = 1; M->reuse_qpos = io->qpos; M->reuse_batch = batch; M->reuse_flags = flags & ~B200MJ_STEP_REUSE_POS; }
+    return 0;
+  }
   return launch(M, io, batch, 1, flags, MODE_STEP, 0, stream);
 }
 

@@ -34,7 +34,7 @@ class IO(ctypes.Structure):
   _fields_ = IO_FIELDS
 
 
-STEP_LEGACY, STEP_FULL_FINAL, STEP_SENSORS = 1, 2, 4
+STEP_LEGACY, STEP_FULL_FINAL, STEP_SENSORS, STEP_REUSE_POS = 1, 2, 4, 8
 
 # every symbol include/b200mj.h declares
 SYMBOLS = ('b200mj_model_create', 'b200mj_model_destroy', 'b200mj_model_set_disableflags', 'b200mj_model_set_capacity',

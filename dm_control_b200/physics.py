@@ -95,6 +95,11 @@ class BatchedPhysics:
     self._sensors = bool(sensors)
     self._full_final = bool(full_final)
     self._suppress = False
+    # True while the position stage of the current state is the one the last step() left behind (its trailing
+    # mj_step1): the next step() then starts from it, as the reference's legacy ordering does. Every method that
+    # changes the state clears it; code that writes `data.qpos/qvel/act` directly must call forward() (the
+    # reference's contract) or mark_as_dirty().
+    self._pos_current = False
     self._handle = ctypes.c_void_p()
     self._upload_model()
     m, B = model, self.batch
@@ -135,6 +140,7 @@ class BatchedPhysics:
     return cls(mjcf_compile.compile_file(path), **kw)
 
   def _upload_model(self):
+    self._pos_current = False
     if self._handle:
       self._L.b200mj_model_destroy(self._handle)
       self._handle = ctypes.c_void_p()
@@ -157,6 +163,7 @@ class BatchedPhysics:
 
   def enable_applied_forces(self, on=True):
     """Route data.qfrc_applied / data.xfrc_applied into the step (off by default: saves two HBM reads per step)."""
+    self._pos_current = False
     for name, ctype in _lib.IO_FIELDS:
       if name in ('qfrc_applied', 'xfrc_applied'):
         t = getattr(self.data, name)
@@ -185,6 +192,8 @@ class BatchedPhysics:
       f |= _lib.STEP_FULL_FINAL
     if self._sensors:
       f |= _lib.STEP_SENSORS
+    if self._pos_current:
+      f |= _lib.STEP_REUSE_POS
     return f
 
   def _sync_model(self):
@@ -216,9 +225,15 @@ class BatchedPhysics:
       with torch.cuda.device(self.device):
         _lib.check(self._L.b200mj_step(self._handle, ctypes.byref(self._io), self.batch, int(nstep), self._flags(),
                                        self._stream()))
+    self._pos_current = bool(self.legacy_step and self._full_final and nstep >= 1)
+
+  def mark_as_dirty(self):
+    """The state tensors were written directly: the next step() recomputes the position stage first."""
+    self._pos_current = False
 
   def forward(self, extra_disableflags=0):
     """mj_forward on every environment (reference: engine.py:335-343)."""
+    self._pos_current = False
     self._sync_model()
     with self.check_invalid_state():
       with torch.cuda.device(self.device):
@@ -234,6 +249,7 @@ class BatchedPhysics:
           self._handle, ctypes.byref(self._io), self.batch, int(nstep), self._flags(),
           ctypes.c_void_p(ctrl_host.data_ptr()), ctypes.c_void_p(self.data.ctrl.data_ptr()),
           ctypes.c_void_p(obs_dev.data_ptr()), ctypes.c_void_p(obs_host.data_ptr()), nobs, self._stream()))
+    self._pos_current = bool(self.legacy_step and self._full_final and nstep >= 1)
 
   # ---- reference Physics API ----------------------------------------------------------------------------
   def set_control(self, control):
@@ -315,6 +331,7 @@ class BatchedPhysics:
     d.qpos.copy_(s[:, :m.nq])
     d.qvel.copy_(s[:, m.nq:m.nq + m.nv])
     d.act.copy_(s[:, m.nq + m.nv:])
+    self._pos_current = False
 
   # ---- warnings -> PhysicsError (reference: engine.py:345-368) -----------------------------------------
   @contextlib.contextmanager

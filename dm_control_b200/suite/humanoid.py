@@ -110,9 +110,9 @@ class Humanoid(base.Task):
 def _make(move_speed, pure_state=False):
   def make(batch=1, seed=0, time_limit=_DEFAULT_TIME_LIMIT, **physics_kw):
     physics_kw.setdefault('outputs', OUTPUTS)
-    # data.ncon is only read by the reset-time rejection sampling, which goes through forward(); the trailing
-    # mj_step1 of a step therefore skips collision (documented: data.ncon is stale after step() for this task)
-    physics_kw.setdefault('full_final', False)
+    # the trailing mj_step1 of a step runs collision + constraint assembly like the reference's (data.ncon and the
+    # contact list are those of the new state); its results are what the next step() starts from
+    # (B200MJ_STEP_REUSE_POS), so this costs no extra position stage
     physics = Physics(testing_models.load('humanoid'), batch=batch, **physics_kw)
     task = Humanoid(move_speed=move_speed, pure_state=pure_state, seed=seed)
     return control.BatchedEnvironment(physics, task, time_limit=time_limit, control_timestep=_CONTROL_TIMESTEP)

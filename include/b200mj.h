@@ -81,7 +81,11 @@ typedef struct b200mj_io {
 enum {
   B200MJ_STEP_LEGACY = 1,      /* reference legacy ordering: step2,(step1+step2)*(n-1),step1 (engine.py:147-162) */
   B200MJ_STEP_FULL_FINAL = 2,  /* final position stage also runs collision + constraint assembly (ncon, contacts) */
-  B200MJ_STEP_SENSORS = 4      /* evaluate sensors */
+  B200MJ_STEP_SENSORS = 4,     /* evaluate sensors */
+  B200MJ_STEP_REUSE_POS = 8    /* the caller has not touched the state since the previous b200mj_step on this io: start from
+                                  the position stage its trailing mj_step1 left behind, as the reference's legacy ordering
+                                  does (engine.py:147-162: step2 first). Ignored unless that previous call ran with
+                                  B200MJ_STEP_LEGACY | B200MJ_STEP_FULL_FINAL on the same (io->qpos, batch). */
 };
 
 /* Upload a compiled model blob (layout: b200mj_model_fields.h). */

@@ -51,7 +51,9 @@ def load():
 class EmuPhysics:
   """B environments stepped by the emulated kernels; `data.<field>` are numpy arrays with a leading batch axis."""
 
-  def __init__(self, model, batch, sensors=True, full_final=True, legacy_step=True, applied_forces=False, outputs='all'):
+  def __init__(self, model, batch, sensors=True, full_final=True, legacy_step=True, applied_forces=False, outputs='all',
+               reuse_pos=False):
+    self._reuse_pos, self._pos_current = reuse_pos, False
     self._L = load()
     self.model, self.batch = model, int(batch)
     self._sensors, self._full_final, self.legacy_step = sensors, full_final, legacy_step
@@ -84,11 +86,14 @@ class EmuPhysics:
             (blib.STEP_SENSORS if self._sensors else 0))
 
   def step(self, nstep=1):
-    rc = self._L.b200mj_step(self._h, ctypes.byref(self._io), self.batch, int(nstep), self._flags(), None)
+    flags = self._flags() | (8 if (self._reuse_pos and self._pos_current) else 0)
+    rc = self._L.b200mj_step(self._h, ctypes.byref(self._io), self.batch, int(nstep), flags, None)
+    self._pos_current = True
     if rc:
       raise RuntimeError(f'b200mj_step (emulation) failed: {rc}')
 
   def forward(self, extra_disableflags=0):
+    self._pos_current = False
     rc = self._L.b200mj_forward(self._h, ctypes.byref(self._io), self.batch, int(extra_disableflags),
                                 blib.STEP_SENSORS if self._sensors else 0, None)
     if rc:

@@ -7,6 +7,7 @@ the packed Cholesky, collision/constraint assembly, the split-kernel handover an
 C ABI — and not only the host code around them. The `-m gpu` tests remain the parity tests proper: the emulation says
 nothing about races, memory spaces or performance, and `rsqrt` is `1/sqrt` here.
 """
+import ctypes
 import os
 import sys
 
@@ -454,3 +455,28 @@ p.forward()
 '''
   out = subprocess.run([sys.executable, '-c', control, root, so], env=env, capture_output=True, text=True, timeout=300)
   assert 'heap-buffer-overflow' in out.stderr and 'write_outputs' in out.stderr
+
+
+@pytest.mark.parametrize('name,B,ncalls', [('humanoid', 6, 12), ('quadruped', 4, 8), ('pendulum_free', 4, 30), ('cheetah', 2050, 3)])
+def test_reuse_of_trailing_position_stage_is_bit_identical(name, B, ncalls):
+  """B200MJ_STEP_REUSE_POS: skipping the leading position kernel when the previous call's trailing mj_step1 already
+  produced its handover must not change a single bit — states, sensors, contacts, warnings — for calls of 1..3 steps."""
+  model = tm.load(name)
+  q0, v0 = tm.initial_states(model, name, B, 0)
+  rs = np.random.RandomState(8)
+  tape = rs.uniform(-1, 1, (ncalls, B, model.nu)); ns = rs.choice([1, 2, 3], ncalls)
+  def run(reuse):
+    p = emu.EmuPhysics(model, B, reuse_pos=reuse)
+    p.data.qpos[:] = q0; p.data.qvel[:] = v0; p.forward()
+    out = []
+    for t in range(ncalls):
+      p.data.ctrl[:] = tape[t]; p.step(int(ns[t]))
+      out.append([np.array(getattr(p.data, f)) for f in ('qpos', 'qvel', 'sensordata', 'ncon', 'nefc', 'contact_geom', 'qacc', 'efc_force', 'xpos', 'subtree_linvel', 'warning')])
+    return out, emu.load().b200mj_launch_count()
+  L = emu.load(); L.b200mj_launch_count.restype = ctypes.c_int64
+  n0 = L.b200mj_launch_count(); a, n1 = run(False); b, n2 = run(True)
+  for x, y in zip(a, b):
+    for u, v in zip(x, y):
+      np.testing.assert_array_equal(u, v)
+  groups = 2 if B >= 2048 else 1
+  assert (n1 - n0) - (n2 - n1) == (ncalls - 1) * groups        # one position launch saved per call and group after the first

@@ -106,6 +106,35 @@ def test_bad_control_and_bad_state_raise_physics_error():
 
 
 @pytest.mark.skipif(EMULATE, reason='BASELINE-size batch: device only')
+def test_sampled_environments_of_the_8192_batch_match_live_oracles(oracle_mod):
+  """BASELINE.json batch size against the oracle: 64 environments sampled across the 8 192 (both environment groups,
+  every row bucket) are re-run on the CPU oracle from the same start state and action tape; states, contact counts
+  and the ordered contact-pair lists must agree after 6 control steps of 5 physics steps."""
+  from oracle import oracle as om
+  B, nstep = 8192, 6
+  phys = _phys('humanoid', B)
+  _seed(phys, 'humanoid', 13)
+  q0, v0 = phys.data.qpos.cpu().numpy().copy(), phys.data.qvel.cpu().numpy().copy()
+  tape = np.random.RandomState(17).uniform(-1, 1, (nstep, B, 21))
+  for t in range(nstep):
+    phys.set_control(torch.as_tensor(tape[t], device=DEV)); phys.step(5)
+  q, v = phys.data.qpos.cpu().numpy(), phys.data.qvel.cpu().numpy()
+  ncon = phys.data.ncon.cpu().numpy(); cg = phys.data.contact_geom.cpu().numpy().reshape(B, -1, 2)
+  picks = np.unique(np.concatenate([np.random.RandomState(5).choice(B, 60, replace=False), [0, 4095, 4096, 8191]]))
+  in_contact = 0
+  for e in picks:
+    o = om.OraclePhysics(phys.model)
+    o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward()
+    for t in range(nstep):
+      o.ctrl[:] = tape[t, e]; o.control_step(5)
+    assert np.abs(q[e] - o.qpos).max() < 1e-7 and np.abs(v[e] - o.qvel).max() < 1e-6, int(e)
+    assert int(ncon[e]) == o.ncon, int(e)
+    assert [(int(a), int(b)) for a, b in cg[e, :ncon[e]]] == [(c.geom1, c.geom2) for c in o.contact], int(e)
+    in_contact += o.ncon > 0
+  assert in_contact >= 5     # the sample must exercise the contact path
+
+
+@pytest.mark.skipif(EMULATE, reason='BASELINE-size batch: device only')
 def test_full_batch_properties_humanoid_8192():
   """BASELINE.json size: properties that need no oracle (finite, bounded, contacts present, clock exact)."""
   phys = _phys('humanoid', 8192, outputs=('xpos', 'subtree_com', 'sensordata', 'ncon'))
