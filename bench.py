@@ -92,9 +92,28 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------------------
+def physical_cores():
+  """One logical CPU per physical core (sysfs topology), restricted to this process's affinity mask."""
+  allowed = sorted(os.sched_getaffinity(0))
+  seen = {}
+  for c in allowed:
+    try:
+      core = open(f'/sys/devices/system/cpu/cpu{c}/topology/core_id').read().strip()
+      pkg = open(f'/sys/devices/system/cpu/cpu{c}/topology/physical_package_id').read().strip()
+    except OSError:
+      core, pkg = str(c), '0'
+    seen.setdefault((pkg, core), c)
+  return sorted(seen.values())
+
+
 def _cpu_worker(args):
-  """One host process: builds its environments, waits at the shared start time, rolls them out in C."""
-  t, nenv, warmup_steps, timed_steps, start_at = args
+  """One host process pinned to one physical core: builds its environments, settles them, then rolls out `reps`
+  timed windows of `timed_steps` env-steps each inside one C call per environment; every window starts at a barrier."""
+  t, cpu, nenv, warmup_steps, timed_steps, reps, barrier = args
+  try:
+    os.sched_setaffinity(0, {cpu})
+  except OSError:
+    pass
   import numpy as np
   from dm_control_b200 import testing_models as tm
   from oracle import oracle as om
@@ -105,85 +124,145 @@ def _cpu_worker(args):
     o = om.OraclePhysics(model)
     o.qpos[:] = q0[e]; o.qvel[:] = v0[e]; o.forward()
     envs.append(o)
-  tape = np.random.RandomState(100 + t).uniform(-1, 1, (warmup_steps + timed_steps, nenv, model.nu))
+  total = warmup_steps + reps * timed_steps
+  tape = np.random.RandomState(100 + t).uniform(-1, 1, (total, nenv, model.nu))
   for j, o in enumerate(envs):
     o.rollout(tape[:warmup_steps, j], NSUB)
-  while time.time() < start_at:
-    time.sleep(0.001)
-  t0 = time.time()
-  for j, o in enumerate(envs):
-    o.rollout(tape[warmup_steps:, j], NSUB)
-  return t0, time.time()
+  spans = []
+  for r in range(reps):
+    lo = warmup_steps + r * timed_steps
+    if barrier is not None:
+      barrier.wait()
+    t0 = time.time()
+    for j, o in enumerate(envs):
+      o.rollout(tape[lo:lo + timed_steps, j], NSUB)
+    spans.append((t0, time.time()))
+  return spans
 
 
-def time_cpu(warmup_steps=5, timed_steps=150, nenv_per_proc=8, procs=None):
-  """Times `control_step(5)` (legacy ordering, engine.py:147-162) of the scalar CPU oracle on all host cores.
-
-  One forked process per core, each owning `nenv_per_proc` environments and stepping them inside one C call;
-  all processes start their timed rollouts at the same wall-clock instant and the slowest sets the time.
-  Sized to ~10-30 s of CPU work in total. Returns (env_steps_per_s, cores, sample description, ms per env-step).
-  """
+def _run_cpu(cores, nenv, warm, timed, reps):
   import multiprocessing as mp
+  ctx = mp.get_context('fork')
+  if len(cores) == 1:
+    return [_cpu_worker((0, cores[0], nenv, warm, timed, reps, None))]
+  barrier = ctx.Barrier(len(cores))
+  procs, pipes = [], []
+  def child(conn, a):
+    conn.send(_cpu_worker(a)); conn.close()
+  for t, cpu in enumerate(cores):
+    rx, tx = ctx.Pipe(duplex=False)
+    p = ctx.Process(target=child, args=(tx, (t, cpu, nenv, warm, timed, reps, barrier)))
+    p.start(); procs.append(p); pipes.append(rx)
+  out = [rx.recv() for rx in pipes]
+  for p in procs:
+    p.join()
+  return out
+
+
+def time_cpu(total_envs=BATCH, warmup_steps=21, reps=3, target_s=3.0):
+  """Times `control_step(5)` (legacy ordering, engine.py:147-162) of the scalar CPU oracle on the host's PHYSICAL cores.
+
+  1. calibration: one pinned process alone -> microseconds per physics step per core;
+  2. one pinned process per physical core, the BATCH environments split evenly (capped so that a window stays near
+     `target_s` seconds of work per process), `reps` timed windows, each started at a barrier; a window's time is the
+     span from the first start to the last finish; the best window is reported.
+  Returns a dict (value = env-steps/s of the best window)."""
   from oracle import oracle as om
   om.build()
-  procs = procs or os.cpu_count() or 1
-  ctx = mp.get_context('fork')
-  start_at = time.time() + 3.0 + 0.02 * procs          # leave time for every worker to build + warm up
-  with ctx.Pool(procs) as pool:
-    spans = pool.map(_cpu_worker, [(t, nenv_per_proc, warmup_steps, timed_steps, start_at) for t in range(procs)], chunksize=1)
-  dt = max(b for _, b in spans) - min(a for a, _ in spans)
-  nenv = procs * nenv_per_proc
-  value = nenv * timed_steps / dt
-  sample = (f'{nenv} envs ({nenv_per_proc}/process x {procs} processes) x {timed_steps} env-steps after {warmup_steps} '
-            f'warm-up, seeded humanoid:run states, uniform(-1,1) actions')
-  return value, procs, sample, dt * 1e3 / timed_steps
-
-
-def cpu_sample_sizes(steps, warmup):
-  """The CPU arm's bounded sample of the GPU arm's workload: the same untimed settle (warmup + 1 env-steps from the
-  same family of seeded states, so the timed window sees the same contact load), the same number of timed env-steps
-  (clamped to 20..300), and enough environments per process for a few seconds of work on every core."""
-  warm = min(max(warmup, 3) + 1, 60)
-  timed = max(20, min(steps, 300))
-  nenv = max(4, min(48, 1600 // timed))
-  return warm, timed, nenv
+  cores = physical_cores()
+  cal_env, cal_steps = 16, 30
+  sp = _run_cpu(cores[:1], cal_env, 5, cal_steps, 1)[0][0]
+  us_per_phys = (sp[1] - sp[0]) / (cal_env * cal_steps * NSUB) * 1e6
+  nenv = -(-total_envs // len(cores))
+  per_env_step_s = us_per_phys * NSUB * 1e-6
+  timed = int(max(20, min(400, round(target_s / (nenv * per_env_step_s)))))
+  if nenv * timed * per_env_step_s > 2.5 * target_s:        # few cores: bound the window instead of the env count's share
+    nenv = max(8, int(2.5 * target_s / (timed * per_env_step_s)))
+  spans = _run_cpu(cores, nenv, warmup_steps, timed, reps)
+  rates = []
+  for r in range(reps):
+    dt = max(s[r][1] for s in spans) - min(s[r][0] for s in spans)
+    rates.append(nenv * len(cores) * timed / dt)
+  best = max(rates)
+  single = 1e6 / (us_per_phys * NSUB)                          # env-steps/s of one core alone
+  return dict(value=best, unit=UNIT, cores=len(cores), kind='port',
+              sample=(f'{nenv * len(cores)} envs ({nenv}/process x {len(cores)} processes, one pinned per physical core) x {timed} '
+                      f'env-steps x {reps} windows (best) after {warmup_steps} settle steps, seeded humanoid:run states, uniform(-1,1) actions'),
+              per_core_us_per_physics_step=us_per_phys, parallel_efficiency=best / (single * len(cores)),
+              windows_env_steps_per_s=rates, work_s_per_process=nenv * timed * per_env_step_s,
+              same_config=bool(nenv * len(cores) == total_envs), ms_per_env_step_batch=1e3 * nenv * len(cores) / best)
 
 
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  warm, timed, nenv = cpu_sample_sizes(max(1, args.steps), args.warmup)
   kind, note = 'port', 'restated CPU oracle (oracle/mjoracle.cpp), NOT libmujoco: MuJoCo is absent from this image'
-  value = None
+  cpu = None
   try:
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import time_mujoco_cpu
     if time_mujoco_cpu.available():      # a machine that has the real reference: time that instead
-      value, cores, sample, ms = time_mujoco_cpu.time_reference(warm, timed, max(1, nenv // 4))
+      value, cores, sample, ms = time_mujoco_cpu.time_reference(21, max(20, min(args.steps, 300)), 8)
+      cpu = dict(value=value, unit=UNIT, cores=cores, kind='reference', sample=sample, ms_per_env_step_batch=ms)
       kind, note = 'reference', 'unmodified dm_control suite.load(humanoid, run) on mujoco, Environment.step'
   except Exception as ex:
     sys.stderr.write(f'real-reference arm failed ({ex!r}); timing the oracle port\n')
-    value = None
-  if value is None:
-    value, cores, sample, ms = time_cpu(warm, timed, nenv)
+    cpu = None
+  if cpu is None:
+    cpu = time_cpu()
+  value = cpu['value']
   line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-              ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-              config=dict(workload='suite.humanoid:run, 5 physics substeps per env-step, random actions', note=note),
-              cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample),
-              e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+              ms_per_step=cpu.pop('ms_per_env_step_batch'), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+              data='synthetic',
+              config=dict(workload='suite.humanoid:run', batch_per_gpu=BATCH, n_sub_steps=NSUB, note=note),
+              cpu_baseline=cpu, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
   print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+def _time_env(env, steps, warmup, gen_seed, nu, dev):
+  """Device-resident env-steps/s of one BatchedEnvironment through env.step (used for the other BASELINE configs)."""
+  import torch
+  B = env.physics.batch
+  gen = torch.Generator(device=dev).manual_seed(gen_seed)
+  act = torch.empty(B, nu, dtype=torch.float64, device=dev)
+  env.physics.check_errors = False
+  env.reset()
+  for _ in range(warmup):
+    act.uniform_(-1, 1, generator=gen); env.step(act)
+  torch.cuda.synchronize(dev)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(steps):
+    act.uniform_(-1, 1, generator=gen); env.step(act)
+  e1.record(); torch.cuda.synchronize(dev)
+  ms = e0.elapsed_time(e1) / steps
+  d = env.physics.data
+  return dict(batch=B, n_sub_steps=env.n_sub_steps, ms_per_step=ms, env_steps_per_s=B / ms * 1e3,
+              physics_steps_per_s=B * env.n_sub_steps / ms * 1e3, mean_ncon=float(d.ncon.double().mean()),
+              warnings=[int(x) for x in d.warning.sum(0).tolist()])
+
+
+def _contact_load(snaps, caps):
+  import torch
+  ncon = torch.cat([s[0] for s in snaps]).double(); nefc = torch.cat([s[1] for s in snaps]).double()
+  niter = torch.cat([s[2] for s in snaps]).double()
+  pops, lo = [], -1
+  for c in caps:
+    pops.append(float(((nefc > lo) & (nefc <= c)).double().mean())); lo = c
+  return dict(mean_ncon=float(ncon.mean()), mean_nefc=float(nefc.mean()), p99_nefc=float(torch.quantile(nefc, 0.99)),
+              max_nefc=float(nefc.max()), mean_niter=float(niter.mean()), bucket_caps=list(caps), bucket_populations=pops,
+              note='state after each sampled env-step: ncon / nefc of the trailing mj_step1, solver iterations of its last physics step')
+
+
 def run_gpu(args):
   import torch
   import torch.distributed as dist
   from dm_control_b200 import lib as blib
   from dm_control_b200 import suite
-  from dm_control_b200 import testing_models as tm
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -194,45 +273,52 @@ def run_gpu(args):
     dist.init_process_group('nccl', device_id=dev)
   L = blib.load()
 
-  env = suite.load('humanoid', 'run', batch=BATCH, seed=1000 + rank, device=dev)
-  phys = env.physics
-  phys.check_errors = False          # no device->host sync inside the rollout; warnings are summed at the end
-  model = phys.model
-  # seeded, partly-in-contact start states (same family the parity tests use), then the task's own settle
-  q0, v0 = tm.initial_states(model, 'humanoid', BATCH, seed=rank)
-  phys.data.qpos.copy_(torch.as_tensor(q0, device=dev)); phys.data.qvel.copy_(torch.as_tensor(v0, device=dev))
-  phys.forward()
-  env._reset_next.zero_()
-  # the task's ~80 tiny reward/observation launches replay as one CUDA graph (falls back to eager if capture fails)
-  env._graph_task_ops = not os.environ.get('B200_BENCH_NO_GRAPH')
-  gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-  actions = torch.empty(BATCH, model.nu, dtype=torch.float64, device=dev)
-  packed = torch.empty(BATCH, OBS_DIM + 2, dtype=torch.float64, device=dev)
   from dm_control_b200 import sharding
-  gathered = torch.empty(BATCH * world, OBS_DIM + 2, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
   flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
-
-  def pack(ts):
-    o = ts.observation
-    packed[:, :21] = o['joint_angles']; packed[:, 21] = o['head_height']; packed[:, 22:34] = o['extremities']
-    packed[:, 34:37] = o['torso_vertical']; packed[:, 37:40] = o['com_velocity']; packed[:, 40:67] = o['velocity']
-    packed[:, 67] = ts.reward; packed[:, 68] = ts.discount
-    if world > 1:
-      # NCCL over NVLink: observations/rewards to rank 0, in environment order (north_star)
-      sharding.gather_to_rank0(packed, BATCH * world, out=gathered)
-
-  def one_step():
-    flush.fill_(0.0)                                   # L2 flush between timed iterations (inside the timed region)
-    actions.uniform_(-1, 1, generator=gen)
-    pack(env.step(actions))
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
+  def build(batch, seed):
+    env = suite.load('humanoid', 'run', batch=batch, seed=seed, device=dev)
+    env.physics.check_errors = False   # no device->host sync inside the rollout; warnings are summed at the end
+    # the task's ~80 tiny reward/observation launches replay as one CUDA graph (falls back to eager if capture fails)
+    env._graph_task_ops = not os.environ.get('B200_BENCH_NO_GRAPH')
+    # start states: the task's own initialize_episode (suite/humanoid.py:152-166: random joint configuration, rejected
+    # until contact-free), then the settle below
+    env.reset()
+    return env
+
+  def runner(env, batch, gather_world):
+    model = env.physics.model
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.empty(batch, model.nu, dtype=torch.float64, device=dev)
+    packed = torch.empty(batch, OBS_DIM + 2, dtype=torch.float64, device=dev)
+    gathered = sharding.alloc_gather(packed, gather_world) if gather_world > 1 else None
+
+    def pack(ts):
+      o = ts.observation
+      packed[:, :21] = o['joint_angles']; packed[:, 21] = o['head_height']; packed[:, 22:34] = o['extremities']
+      packed[:, 34:37] = o['torso_vertical']; packed[:, 37:40] = o['com_velocity']; packed[:, 40:67] = o['velocity']
+      packed[:, 67] = ts.reward; packed[:, 68] = ts.discount
+      if gather_world > 1:
+        # NCCL over NVLink: observations/rewards of every rank, in environment order (north_star)
+        sharding.gather_packed(packed, gathered)
+
+    def one_step(timing=None):
+      flush.fill_(0.0)                                   # L2 flush between timed iterations (inside the timed region)
+      actions.uniform_(-1, 1, generator=gen)
+      pack(env.step(actions, timing=timing))
+    return model, actions, packed, gathered, pack, one_step
+
+  env = build(BATCH, 1000 + rank)
+  phys = env.physics
+  model, actions, packed, gathered, pack, one_step = runner(env, BATCH, world)
+
   sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if (rank == 0 and not os.environ.get("B200_BENCH_NO_SAMPLER")) else None
-  # settle to the steady-state contact load the metric is quoted on (20 warm-up env-steps minimum)
+  # settle to the contact load the metric is quoted on (20 warm-up env-steps minimum)
   try:
     one_step()
   except Exception as ex:           # graph capture unsupported for some op: eager task ops
@@ -242,29 +328,25 @@ def run_gpu(args):
     env._graph_task_ops = False; env._graph = None
     torch.cuda.synchronize()
     one_step()
-  for _ in range(max(args.warmup, 3)):
+  settle = max(args.warmup, 20)
+  for _ in range(settle):
     one_step()
   barrier()
 
-  # ---- device-resident arm -------------------------------------------------------------------------------
+  # ---- device-resident arm: the user-facing env.step, inputs generated on the device ------------------------
   launches0 = L.b200mj_launch_count()
   ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
   kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  snaps = []
   barrier()
   ev[0].record()
   every = max(1, args.steps // 8)
   for i in range(args.steps):
     if sampler and i % every == every // 2:
       sampler.sample()                                 # clocks / throttle reasons while the region is running
-    flush.fill_(0.0)
-    actions.uniform_(-1, 1, generator=gen)
-    env._task.before_step(actions, phys)
-    kev[i][0].record()
-    phys.step(env.n_sub_steps)                         # one b200mj_step call: the step's whole kernel group
-    kev[i][1].record()
-    env._task.after_step(phys)
-    reward, obs = env._reward_and_observation()
-    pack(type('TS', (), dict(observation=obs, reward=reward, discount=torch.ones_like(reward))))
+    one_step(timing=kev[i])                            # events around the one b200mj_step call inside env.step
+    if i % every == 0:
+      snaps.append((phys.data.ncon.clone(), phys.data.nefc.clone(), phys.data.solver_niter.clone()))
   ev[1].record()
   barrier()
   ms_total = ev[0].elapsed_time(ev[1])
@@ -276,35 +358,76 @@ def run_gpu(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   ms_total, kernel_ms = float(t[0]), float(t[1])
   value = BATCH * world * args.steps / (ms_total * 1e-3)
+  desc = phys.describe()
+  load = _contact_load(snaps, [b['rows'] for b in desc.get('acc_buckets', [])] or [10, 24, model.njmax])
 
   # ---- end-to-end arm: HOST action buffer in, HOST observation/reward buffer out, every step -----------------
   # host action tape, drawn before the clock starts (drawing 172k doubles on one host core costs ~0.4 ms per step and
   # is the synthetic policy's time, not the path's); 16 pinned blocks, cycled
-  cpu_gen = torch.Generator().manual_seed(77 + rank)
-  act_tape = [torch.empty(BATCH, model.nu, dtype=torch.float64).uniform_(-1, 1, generator=cpu_gen).pin_memory() for _ in range(16)]
-  out_host = torch.empty((BATCH * world if rank == 0 else BATCH), OBS_DIM + 2, dtype=torch.float64).pin_memory()
-  barrier()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
-  for i in range(args.steps):
-    flush.fill_(0.0)
-    actions.copy_(act_tape[i % len(act_tape)], non_blocking=True)     # H2D from pinned host memory
-    pack(env.step(actions))
-    if rank == 0 and world > 1:
-      out_host.copy_(gathered, non_blocking=True)                     # D2H of the gathered block
-    else:
-      out_host[:BATCH].copy_(packed, non_blocking=True)               # D2H
-    torch.cuda.current_stream().synchronize()                         # the user reads obs before the next action
-  e1.record()
-  barrier()
-  e2e_ms = e0.elapsed_time(e1)
-  t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e_value = BATCH * world * args.steps / (float(t[0]) * 1e-3)
+  def e2e(env, batch, actions, packed, gathered, pack, gather_world, steps):
+    cpu_gen = torch.Generator().manual_seed(77 + rank)
+    act_tape = [torch.empty(batch, model.nu, dtype=torch.float64).uniform_(-1, 1, generator=cpu_gen).pin_memory() for _ in range(16)]
+    # every rank reads back its own rows of the gathered block over its own PCIe link into pinned host memory
+    out_host = torch.empty(batch, OBS_DIM + 2, dtype=torch.float64).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+      flush.fill_(0.0)
+      actions.copy_(act_tape[i % len(act_tape)], non_blocking=True)     # H2D from pinned host memory
+      pack(env.step(actions))
+      out_host.copy_(packed, non_blocking=True)                         # D2H of this rank's rows
+      torch.cuda.current_stream().synchronize()                         # the user reads obs before the next action
+    e1.record()
+    barrier()
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return batch * world * steps / (float(tt[0]) * 1e-3)
+
+  e2e_value = e2e(env, BATCH, actions, packed, gathered, pack, world, args.steps)
   warn = phys.data.warning.sum(0)
   if world > 1:
     dist.all_reduce(warn)
+
+  # ---- strong scaling: BASELINE.json "batch 8192, 8xB200 sharded" = the SAME 8192 environments split over N GPUs -----
+  strong = None
+  if world > 1:
+    sb = BATCH // world
+    env_s = build(sb, 5000 + rank)
+    _, actions_s, packed_s, gathered_s, pack_s, one_step_s = runner(env_s, sb, world)
+    for _ in range(settle + 1):
+      one_step_s()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+      one_step_s()
+    s1.record(); barrier()
+    tt = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    strong = dict(global_batch=BATCH, batch_per_gpu=sb, value=BATCH * args.steps / (float(tt[0]) * 1e-3), unit=UNIT,
+                  ms_per_step=float(tt[0]) / args.steps,
+                  e2e=e2e(env_s, sb, actions_s, packed_s, gathered_s, pack_s, world, args.steps))
+
+  # ---- the other BASELINE.json configs on one GPU, same run (device-resident, through env.step) ---------------
+  configs = None
+  if world == 1 and not args.no_configs:
+    configs = {}
+    for dom, task, B in (('cheetah', 'run', 4096), ('quadruped', 'walk', 4096), ('cartpole', 'swingup', 4096)):
+      try:
+        e = suite.load(dom, task, batch=B, seed=3, device=dev)
+        configs[f'suite.{dom}:{task}'] = _time_env(e, 20, 10, 5, e.physics.model.nu, dev)
+        e.physics.free()
+      except Exception as ex:
+        configs[f'suite.{dom}:{task}'] = dict(error=repr(ex))
+    try:
+      from dm_control_b200 import locomotion
+      e = locomotion.load('cmu_humanoid_run_walls', batch=2048, seed=3, device=dev)
+      configs['locomotion.cmu_humanoid run-through-corridor (walls)'] = _time_env(e, 10, 10, 5, e.physics.model.nu, dev)
+      e.physics.free()
+    except Exception as ex:
+      configs['locomotion.cmu_humanoid run-through-corridor (walls)'] = dict(error=repr(ex))
 
   if rank == 0:
     peak, peak_src = _peaks()
@@ -315,31 +438,36 @@ def run_gpu(args):
       prof = json.load(open(pj))
     cpu = None
     if world == 1 and not args.no_cpu:
-      v, cores, sample, _ = time_cpu(*cpu_sample_sizes(args.steps, args.warmup))
-      cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample)
+      cpu = time_cpu()
+      cpu.pop('ms_per_env_step_batch', None)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
         data='synthetic',
         config=dict(workload='suite.humanoid:run', batch_per_gpu=BATCH, global_batch=BATCH * world, n_sub_steps=NSUB,
                     physics_steps_per_s=value * NSUB, parallelism=f'env-sharded x{world}',
+                    start_states=f'task.initialize_episode (suite/humanoid.py:152-166) + {settle + 1} settle env-steps',
+                    call='BatchedEnvironment.step (value and e2e)',
                     actions='uniform(-1,1) generated on device', l2='256 MB flush write between steps, inside the timed region',
                     task_ops='one CUDA-graph replay' if env._graph_task_ops else 'eager torch ops',
-                    obs_gather='NCCL gather of [B,69] f64 to rank 0 each step' if world > 1 else 'n/a (1 GPU)',
-                    kernels=phys.describe(),
-                    nconmax=model.nconmax, njmax=model.njmax),
-        e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * model.nu * 8,
-                 d2h_bytes_per_step=BATCH * (OBS_DIM + 2) * 8 * (world if world > 1 else 1)),
-        gpu_launches=int(launches),
+                    obs_gather='NCCL all_gather_into_tensor of [B,69] f64 each step; every rank copies its own rows to pinned host memory' if world > 1 else 'n/a (1 GPU)',
+                    kernels=desc, nconmax=model.nconmax, njmax=model.njmax),
+        e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * model.nu * 8 * world,
+                 d2h_bytes_per_step=BATCH * (OBS_DIM + 2) * 8 * world),
+        gpu_launches=int(launches), contact_load=load,
         roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                       traffic=prof.get('dram_bytes_per_step', prof.get('dram_bytes_per_launch')), peak_source=peak_src,
-                      kernel='b200mj step group: [pos_kernel, acc_kernel x row-buckets] x (n_sub_steps-1), [pos_kernel, acclast_kernel x row-buckets], posfinal_kernel',
-                      dominant_kernel=prof.get('dominant_kernel', 'b200mj_acc_kernel'),
+                      kernel='b200mj step group: [pos_kernel, acc_tn_kernel x row-buckets] x n_sub_steps (first pos reused from the previous trailing mj_step1), posfinal_kernel',
+                      dominant_kernel=prof.get('dominant_kernel', 'b200mj_acc_tn_kernel'),
                       dominant_kernel_utilisation_pct=prof.get('dominant_kernel_utilisation_pct'),
                       kernel_ms=kernel_ms, kernel_share_of_step=kernel_ms / (ms_total / args.steps),
                       algorithmic_bytes_per_launch=ALGO_BYTES_PER_ENV_STEP * BATCH,
                       note='latency/issue-bound fp64 kernel: compulsory traffic is ~4 kB per env-step, see DESIGN.md'),
         clocks=clocks, warnings=[int(x) for x in warn.tolist()])
+    if strong is not None:
+      line['strong'] = strong
+    if configs is not None:
+      line['configs'] = configs
     if cpu is not None:
       line['cpu_baseline'] = cpu
     print(json.dumps(line))
@@ -354,6 +482,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  ap.add_argument('--no-configs', action='store_true', help='skip the other BASELINE.json configs (N=1 only)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

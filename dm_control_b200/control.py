@@ -96,7 +96,9 @@ class BatchedEnvironment:
     self._graph.replay()
     return self._graph_out
 
-  def step(self, action):
+  def step(self, action, timing=None):
+    """One control step for every environment. `timing`: optional (start, end) CUDA events recorded around the
+    physics call (bench.py times the step's kernel group with them); no effect on the result."""
     if self._auto_reset and self._count_ub >= self._step_limit:
       if bool(self._reset_next.any()):
         mask = self._reset_next
@@ -105,7 +107,11 @@ class BatchedEnvironment:
         self._reset_next = torch.zeros_like(mask)
       self._count_ub = int(self._step_count.max())      # slow path only: one more readback, then exact again
     self._task.before_step(action, self._physics)
+    if timing is not None:
+      timing[0].record()
     self._physics.step(self._n_sub_steps)
+    if timing is not None:
+      timing[1].record()
     self._task.after_step(self._physics)
     reward, obs = self._reward_and_observation()
     self._step_count += 1

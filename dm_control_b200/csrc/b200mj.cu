@@ -29,6 +29,7 @@
 
 #include "../../include/b200mj.h"
 #include "../../include/b200mj_model_fields.h"
+#include "../../include/b200mj_convex.h"
 
 #define FULL 0xffffffffu
 #define FOR_LANES(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
@@ -43,6 +44,9 @@ struct DevModel {
 #undef DECL_I
 #undef DECL_R
   int nq, nv, nu, na, nbody, njnt, ngeom, nsite, ntendon, neq, nsensor, nsensordata, npair, nlevel, nconmax, njmax;
+  // actuator moments by dof (CSR, built by b200mj_model_create): joint and fixed-tendon transmissions have constant
+  // moment arms, so qfrc_actuator[i] = sum over dof_act_id[dof_act_adr[i] .. dof_act_adr[i+1]) of coef * force
+  const int* dof_act_adr; const int* dof_act_id; const double* dof_act_coef;
   int ldv;          // padded row length of nv-wide matrices (odd => conflict-free column walks)
   int integrator, iterations, ls_iterations, disableflags;
   int any_damping, acc_sensors;
@@ -90,6 +94,7 @@ struct b200mj_model {
   size_t smem_pos, smem_acc;
   int* d_idata;
   double* d_rdata;
+  int* d_xi; double* d_xr;      // derived tables (dof_act_*)
   int envs_per_block;
   size_t smem_per_env;
   int tn_nv;                  // nv when a compile-time-size acceleration kernel exists for this model, else 0
@@ -427,6 +432,9 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
 //     the diagonal zeroed: one shuffle + one DFMA per unknown, nothing else.
 // ------------------------------------------------------------------------------------------------
 #define TN_COLBUF_DOUBLES 64
+#ifndef TN_FACTOR_VARIANT
+#define TN_FACTOR_VARIANT 0
+#endif
 
 // 1/sqrt(x) for x in [mjMINVAL, huge): hardware seed + one cubic step, no special-case slow path (the library
 // rsqrt() carries a subroutine call for denormals / infinities, and a call inside the unrolled factorisation makes
@@ -475,6 +483,29 @@ __device__ __noinline__ void tn_factor(const double* Msrc, double* Lm, double* d
 #pragma unroll
     for (int k = 0; k < N; k++) a[k] += sj * Jr[k];
   }
+#if TN_FACTOR_VARIANT == 0
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    double* cb = colbuf + (j & 1) * 32;      // double-buffered: one __syncwarp per column is enough
+    cb[lane] = a[j];                         // raw column j (lanes < j hold upper-triangle junk that nobody reads)
+    __syncwarp();
+    double piv = cb[j];
+    if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+    const double inv = pos_rsqrt(piv);
+    const double lj = (lane == j ? piv : a[j]) * inv;      // L[i][j]; the diagonal is sqrt(piv)
+    a[j] = lj;
+    if (lane == j) dinv[j] = inv;
+    const double cc = lj * inv;                            // raw_i / piv : a[i][k] -= raw_i raw_k / piv
+    int k = j + 1;
+    if (k < N && (k & 1)) { a[k] -= cc * cb[k]; k++; }
+#pragma unroll
+    for (; k + 1 < N; k += 2) {
+      const double2 s2 = *reinterpret_cast<const double2*>(cb + k);
+      a[k] -= cc * s2.x; a[k + 1] -= cc * s2.y;
+    }
+    if (k < N) a[k] -= cc * cb[k];
+  }
+#else
   // Software-pipelined right-looking elimination. The dependent chain of a column is
   //   a[j] update -> pivot broadcast (shuffle) -> 1/sqrt -> scale -> first update of column j+1,
   // and a warp issues in order: so the chain of column j+1 is started BEFORE the remaining N-j-2 independent updates
@@ -508,6 +539,7 @@ __device__ __noinline__ void tn_factor(const double* Msrc, double* Lm, double* d
     if (k < N) a[k] -= cc * cb[k];
     __syncwarp();
   }
+#endif
   if (isrow) {
 #pragma unroll
     for (int k = 0; k < N; k++) if (k <= lane) Lm[ti + k] = a[k];
@@ -609,6 +641,15 @@ __device__ __forceinline__ void kinematics(const Ctx& c) {
     int t = m.jnt_type[j];
     if (t == BMJ_JNT_FREE) normalize4(qpos + m.jnt_qposadr[j] + 3);
     else if (t == BMJ_JNT_BALL) normalize4(qpos + m.jnt_qposadr[j]);
+    else if (t == BMJ_JNT_HINGE) {
+      // sin / cos of every hinge's half angle, all joints at once (lanes = joints): inside the level loop below only a
+      // few lanes are busy, and sincos was a third of its serial chain. Parked in this joint's xanchor slot, which the
+      // level loop overwrites after it has read them.
+      const double angle = qpos[m.jnt_qposadr[j]] - m.qpos0[m.jnt_qposadr[j]];
+      double sn = 0, cs = 1;
+      if (angle != 0) sincos(angle * 0.5, &sn, &cs);
+      W(xanchor)[3 * j] = sn; W(xanchor)[3 * j + 1] = cs;
+    }
   }
   __syncwarp();
   _Pragma("unroll 1") for (int l = 1; l < m.nlevel; l++) {
@@ -626,6 +667,7 @@ __device__ __forceinline__ void kinematics(const Ctx& c) {
         double* anchor = W(xanchor) + 3 * j; double* axis = W(xaxis) + 3 * j;
         double jax[3] = {m.jnt_axis[3*j], m.jnt_axis[3*j+1], m.jnt_axis[3*j+2]};
         double jp[3] = {m.jnt_pos[3*j], m.jnt_pos[3*j+1], m.jnt_pos[3*j+2]};
+        const double hs = anchor[0], hc = anchor[1];       // hinge: sin, cos of the half angle (pre-pass above)
         if (t == BMJ_JNT_FREE) {
           for (int i = 0; i < 3; i++) pos[i] = qpos[qa + i];
           for (int i = 0; i < 4; i++) quat[i] = qpos[qa + 3 + i];
@@ -642,8 +684,10 @@ __device__ __forceinline__ void kinematics(const Ctx& c) {
           for (int i = 0; i < 3; i++) pos[i] += ax[i] * q;
         } else {
           double ql[4], r[4];
-          if (t == BMJ_JNT_HINGE) axis_angle2quat(ql, jax, qpos[qa] - m.qpos0[qa]);
-          else for (int i = 0; i < 4; i++) ql[i] = qpos[qa + i];
+          if (t == BMJ_JNT_HINGE) {     // axis_angle2quat with the precomputed sin / cos (hs == 0 <=> angle == 0)
+            if (hs == 0) { ql[0] = 1; ql[1] = ql[2] = ql[3] = 0; }
+            else { ql[0] = hc; ql[1] = jax[0] * hs; ql[2] = jax[1] * hs; ql[3] = jax[2] * hs; }
+          } else for (int i = 0; i < 4; i++) ql[i] = qpos[qa + i];
           mul_quat(r, quat, ql);
           for (int i = 0; i < 4; i++) quat[i] = r[i];
           rot_vec_quat(tmp, jp, quat);
@@ -945,7 +989,21 @@ __device__ __noinline__ int narrowphase(double* stg, int t1, int t2, double marg
       stage_contact(stg, n, dist, pos, nw);
       return n;
     }
-    return 0;
+  }
+  if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_BOX) {
+    double out[14];
+    const int nc = cvx_capsule_box(p1, m1, s1, p2, m2, s2, margin, out);
+    if (nc > 0) stage_contact(stg, n, out[0], out + 1, out + 4);
+    if (nc > 1) stage_contact(stg, n, out[7], out + 8, out + 11);
+    return n;
+  }
+  if (!(t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE)) {
+    // every remaining pair of convex primitives (an ellipsoid, a cylinder or two boxes involved): MPR, one contact
+    if (t1 >= BMJ_GEOM_SPHERE && t2 <= BMJ_GEOM_BOX) {
+      double dist, pos[3], nrm[3];
+      if (cvx_pair(t1, p1, m1, s1, t2, p2, m2, s2, margin, &dist, pos, nrm)) stage_contact(stg, n, dist, pos, nrm);
+    }
+    return n;
   }
   if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE) {
     double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
@@ -1303,14 +1361,20 @@ __device__ __forceinline__ void fwd_velocity(const Ctx& c) {
       }
       int d0 = m.body_dofadr[b], dn = m.body_dofnum[b];
       _Pragma("unroll 1") for (int q = d0; q < d0 + dn; q++) for (int i = 0; i < 6; i++) ca[i] += W(cdofdot)[6 * q + i] * qvel[q];
-      double t1[6], t2[6], t3[6];
-      mul_inert_vec(t1, W(cinert) + 10 * b, ca);
-      mul_inert_vec(t2, W(cinert) + 10 * b, cv);
-      cross_force(t3, cv, t2);
-      for (int i = 0; i < 6; i++) { cvel[6 * b + i] = cv[i]; cacc[6 * b + i] = ca[i]; cfrc[6 * b + i] = t1[i] + t3[i]; }
+      for (int i = 0; i < 6; i++) { cvel[6 * b + i] = cv[i]; cacc[6 * b + i] = ca[i]; }
     }
     __syncwarp();
   }
+  // body forces for all bodies at once (lanes = bodies) rather than inside the level loop, where few lanes are busy
+  FOR_LANES(b, m.nbody) {
+    if (b == 0) continue;
+    double t1[6], t2[6], t3[6];
+    mul_inert_vec(t1, W(cinert) + 10 * b, cacc + 6 * b);
+    mul_inert_vec(t2, W(cinert) + 10 * b, cvel + 6 * b);
+    cross_force(t3, cvel + 6 * b, t2);
+    for (int i = 0; i < 6; i++) cfrc[6 * b + i] = t1[i] + t3[i];
+  }
+  __syncwarp();
   tree_accumulate(c, cfrc, 6, false);
   FOR_LANES(k, m.nv) {
     int b = m.dof_bodyid[k];
@@ -1386,14 +1450,12 @@ __device__ __forceinline__ void fwd_actuation(const Ctx& c) {
     W(actforce)[a] = force;
   }
   __syncwarp();
+  // qfrc_actuator = moment^T force: the nonzero moment arms of every dof in actuator order (same summation order
+  // as the dense nu-loop this replaces; the skipped terms are exact zeros)
   FOR_LANES(i, nv) {
     double s = 0;
-    _Pragma("unroll 1") for (int a = 0; a < m.nu; a++) {
-      double gear = m.actuator_gear[a], mom;
-      if (m.actuator_trntype[a] == BMJ_TRN_JOINT) mom = (m.jnt_dofadr[m.actuator_trnid[a]] == i) ? gear : 0.0;
-      else mom = gear * W(tenJ)[m.actuator_trnid[a] * ld + i];
-      s += mom * W(actforce)[a];
-    }
+    const int a0 = m.dof_act_adr[i], a1 = m.dof_act_adr[i + 1];
+    _Pragma("unroll 1") for (int k = a0; k < a1; k++) s += m.dof_act_coef[k] * W(actforce)[m.dof_act_id[k]];
     W(qfact)[i] = s;
   }
   __syncwarp();
@@ -2537,8 +2599,62 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   bool unsupported = m.nv > 64 || h_opti[BMJ_OPT_SOLVER] != BMJ_SOL_NEWTON || h_opti[BMJ_OPT_CONE] != 0 ||
                      (m.integrator != BMJ_INT_EULER && m.integrator != BMJ_INT_RK4);
   for (int i = 0; i < n_condim; i++) if (h_condim[i] != 1 && h_condim[i] != 3) unsupported = true;
+  {   // geom types without a narrow-phase function here (height fields, meshes) must not slip through as contact-free geoms
+    int kk = 0; const int* h_gt = nullptr; int n_gt = 0;
+#define GT_I(name) if (!strcmp(#name, "geom_type")) { h_gt = idata + idata[2 * kk]; n_gt = idata[2 * kk + 1]; } kk++;
+#define GT_R(name) kk++;
+    B200MJ_MODEL_FIELDS(GT_I, GT_R)
+#undef GT_I
+#undef GT_R
+    for (int i = 0; i < n_gt; i++) if (h_gt[i] == BMJ_GEOM_HFIELD || h_gt[i] >= BMJ_GEOM_MESH) unsupported = true;
+  }
   for (int i = 0; i < n_fl; i++) if (h_fl[i] != 0) unsupported = true;
   if (unsupported) { b200mj_model_destroy(M); return -3; }
+  {   // actuator moment arms by dof (constant for joint and fixed-tendon transmissions)
+    struct HF {
+#define HF_I(name) const int* name;
+#define HF_R(name) const double* name;
+      B200MJ_MODEL_FIELDS(HF_I, HF_R)
+#undef HF_I
+#undef HF_R
+    } hf;
+    int kk = 0;
+#define HS_I(name) hf.name = idata + idata[2 * kk]; kk++;
+#define HS_R(name) hf.name = rdata + idata[2 * kk]; kk++;
+    B200MJ_MODEL_FIELDS(HS_I, HS_R)
+#undef HS_I
+#undef HS_R
+    const int nv = m.nv, nu = m.nu;
+    int* adr = new int[nv + 1];
+    int* ids = new int[(size_t)nv * (nu > 0 ? nu : 1)];
+    double* coef = new double[(size_t)nv * (nu > 0 ? nu : 1)];
+    int n = 0;
+    for (int i = 0; i < nv; i++) {
+      adr[i] = n;
+      for (int a = 0; a < nu; a++) {
+        double mom = 0; bool any = false;
+        const double gear = hf.actuator_gear[a];
+        if (hf.actuator_trntype[a] == BMJ_TRN_JOINT) { if (hf.jnt_dofadr[hf.actuator_trnid[a]] == i) { mom = gear; any = true; } }
+        else {
+          const int t = hf.actuator_trnid[a];
+          double tj = 0;
+          for (int w = hf.tendon_adr[t]; w < hf.tendon_adr[t] + hf.tendon_num[t]; w++)
+            if (hf.jnt_dofadr[hf.wrap_objid[w]] == i) { tj += hf.wrap_prm[w]; any = true; }
+          mom = gear * tj;
+        }
+        if (any) { ids[n] = a; coef[n] = mom; n++; }
+      }
+    }
+    adr[nv] = n;
+    const int nn = n > 0 ? n : 1;
+    bool ok = cudaMalloc(&M->d_xi, (size_t)(nv + 1 + nn) * sizeof(int)) == cudaSuccess && cudaMalloc(&M->d_xr, (size_t)nn * sizeof(double)) == cudaSuccess;
+    if (ok) ok = cudaMemcpy(M->d_xi, adr, (size_t)(nv + 1) * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(M->d_xi + nv + 1, ids, (size_t)nn * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(M->d_xr, coef, (size_t)nn * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    delete[] adr; delete[] ids; delete[] coef;
+    if (!ok) { b200mj_model_destroy(M); return -2; }
+    m.dof_act_adr = M->d_xi; m.dof_act_id = M->d_xi + nv + 1; m.dof_act_coef = M->d_xr;
+  }
   M->tn_nv = tn_kernel(m.nv, false) ? m.nv : 0;
   build_layout(M);
   if (M->envs_per_block < 1) { b200mj_model_destroy(M); return -4; }
@@ -2565,6 +2681,8 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
 void b200mj_model_destroy(b200mj_model* M) {
   if (!M) return;
   cudaFree(M->d_idata); cudaFree(M->d_rdata);
+  if (M->d_xi) cudaFree(M->d_xi);
+  if (M->d_xr) cudaFree(M->d_xr);
   if (M->d_hand) cudaFree(M->d_hand);
   if (M->d_hand2) cudaFree(M->d_hand2);
   if (M->streams_ok) {

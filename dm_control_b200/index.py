@@ -59,8 +59,8 @@ def _ragged(model, kind):
 class FieldIndexer:
   """One field with name-aware `__getitem__` / `__setitem__` (index.py:455-600)."""
 
-  def __init__(self, name, array, model, batched):
-    self._name, self._a, self._batched = name, array, batched
+  def __init__(self, name, array, model, batched, on_write=None):
+    self._name, self._a, self._batched, self._on_write = name, array, batched, on_write
     kind = _ROW_KIND.get(name)
     self._ragged = kind in ('nq', 'nv', 'na', 'nsensordata')
     if kind is None:
@@ -111,6 +111,8 @@ class FieldIndexer:
       self._a[k] = torch.as_tensor(value, dtype=self._a.dtype, device=self._a.device)
     else:
       self._a[k] = value
+      if self._on_write is not None:
+        self._on_write()          # model field: the device copy must be refreshed before the next step
 
   @property
   def row_names(self):
@@ -133,7 +135,7 @@ class _Struct:
       raise AttributeError(name)
     c = self._cache.get(name)
     if c is None or c._a is not arr:
-      c = FieldIndexer(name, arr, self._m, self._b)
+      c = FieldIndexer(name, arr, self._m, self._b, on_write=None if self._b else self._m.touch)
       self._cache[name] = c
     return c
 

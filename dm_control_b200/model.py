@@ -101,13 +101,28 @@ class Model:
     if fields is None:
       raise AttributeError(name)
     if name in fields:
-      return fields[name]
+      # read-only view: the device copy of the model is refreshed when `_version` changes, which a write through a raw
+      # array could not signal. Write with `model.set(field, value)` or `physics.named.model.<field>[...] = v`.
+      v = fields[name].view()
+      v.flags.writeable = False
+      return v
     key = name.upper()
     if key in SIZE:
       return int(fields['sizes'][SIZE[key]])
     if name == 'stat':
       return types.SimpleNamespace(meaninertia=float(fields['opt_real'][OPTR['MEANINERTIA']]))
     raise AttributeError(name)
+
+  def set(self, field, value, index=slice(None)):
+    """`model.<field>[index] = value` with the bookkeeping the device copy needs (the next step / forward re-uploads
+    the model). The reference edits `physics.model.<field>` in place (e.g. domain randomisation); here the arrays
+    handed out by attribute access are read-only so that such an edit cannot be silently ignored."""
+    self.fields[field][index] = value
+    self._version += 1
+
+  def touch(self):
+    """Mark the model as modified (after writing `model.fields[...]` directly)."""
+    self._version += 1
 
   def name2id(self, name, object_type):
     """Mirror of `MjModel.name2id` (dm_control/mujoco/wrapper/core.py:334-362): -> id or raises."""

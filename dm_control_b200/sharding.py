@@ -63,3 +63,23 @@ def gather_to_rank0(block, global_batch, out=None):
     return res
   dist.gather(send, None, dst=0)
   return None
+
+
+def alloc_gather(block, world_size=None):
+  """Preallocated `[world * n_local, k]` destination of `gather_packed` (equal shards)."""
+  world = world_size or (dist.get_world_size() if dist.is_initialized() else 1)
+  return block.new_empty(block.shape[0] * world, block.shape[1])
+
+
+def gather_packed(block, out):
+  """One collective per control step: every rank's `[n_local, k]` block lands in `out[rank * n_local : ...]` on every
+  rank (rank 0 included — the north_star's "gather observations / rewards to rank 0"), in environment order, with no
+  temporary buffers and no slice copies (`all_gather_into_tensor`: NCCL ring / NVLS over NVSwitch on GPUs, gloo in the
+  CPU tests). Equal shard sizes only; ragged shards go through `gather_to_rank0`."""
+  if not dist.is_initialized() or dist.get_world_size() == 1:
+    out.copy_(block)
+    return out
+  if out.shape[0] != block.shape[0] * dist.get_world_size():
+    raise ValueError(f'gather_packed needs equal shards: out has {out.shape[0]} rows, block {block.shape[0]} x world {dist.get_world_size()}')
+  dist.all_gather_into_tensor(out, block.contiguous())
+  return out

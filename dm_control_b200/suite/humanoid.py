@@ -74,6 +74,9 @@ class Humanoid(base.Task):
       todo = todo & (physics.data.ncon > 0)
       if not bool(todo.any()):
         break
+    else:
+      # the reference loops until the pose is contact-free (humanoid.py:160-166); a batch cannot loop forever
+      raise RuntimeError(f'humanoid reset: {int(todo.sum())} environments still in contact after 200 re-draws')
 
   def get_observation(self, physics):
     obs = collections.OrderedDict()

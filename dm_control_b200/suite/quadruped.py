@@ -101,6 +101,9 @@ class Move(base.Task):
       z = z + 0.01
       if not bool(todo.any()):
         break
+    else:
+      # quadruped.py:271-276: 'Failed to find a non-contacting configuration.' after its attempt budget
+      raise RuntimeError('Failed to find a non-contacting configuration.')
 
   def get_observation(self, physics):
     obs = collections.OrderedDict()

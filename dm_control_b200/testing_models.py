@@ -54,6 +54,23 @@ XML = {
 </mujoco>""",
 }
 
+# every convex primitive against every other and against a static box platform: ellipsoid / cylinder / box / capsule /
+# sphere free bodies dropped in a heap (pairs resolved by include/b200mj_convex.h: MPR and capsule-box)
+XML['convex_zoo'] = """
+<mujoco><option timestep="0.004"/>
+<default><geom friction=".7" solref=".02 1"/></default>
+<worldbody>
+  <geom name="floor" type="plane" size="5 5 .1"/>
+  <geom name="platform" type="box" pos="0 0 .15" size=".6 .5 .15"/>
+  <body name="e" pos="0 0 .55"><freejoint/><geom name="e" type="ellipsoid" size=".18 .12 .08" euler="20 30 0"/></body>
+  <body name="c" pos=".05 .05 .85"><freejoint/><geom name="c" type="cylinder" size=".09 .12" euler="70 10 0"/></body>
+  <body name="b" pos="-.05 .02 1.15"><freejoint/><geom name="b" type="box" size=".1 .08 .06" euler="10 40 25"/></body>
+  <body name="k" pos=".02 -.04 1.45"><freejoint/><geom name="k" type="capsule" size=".05 .14" euler="80 0 30"/></body>
+  <body name="s" pos="0 .03 1.7"><freejoint/><geom name="s" type="sphere" size=".09"/></body>
+  <body name="k2" pos=".45 .3 .6"><freejoint/><geom name="k2" type="capsule" size=".04 .2" euler="90 0 60"/></body>
+</worldbody>
+</mujoco>"""
+
 _CACHE = {}
 
 

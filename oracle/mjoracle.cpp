@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "../include/b200mj_model_fields.h"
+#include "../include/b200mj_convex.h"   // MPR / capsule-box: the one narrow-phase source shared with the engine (see its header)
 
 typedef double real;
 typedef std::vector<real> vec;
@@ -644,11 +645,22 @@ static int narrowphase(RawCon* c, int t1, int t2, real margin, const real* p1, c
       c->dist = dist;
       return 1;
     }
-    return -1;
   }
-  if (t1 == BMJ_GEOM_CAPSULE) {
-    if (t2 == BMJ_GEOM_CAPSULE) return collide_capsule_capsule(c, margin, p1, m1, s1, p2, m2, s2);
-    return -1;
+  if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE) return collide_capsule_capsule(c, margin, p1, m1, s1, p2, m2, s2);
+  if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_BOX) {
+    real out[14];
+    int n = cvx_capsule_box(p1, m1, s1, p2, m2, s2, margin, out);
+    for (int k = 0; k < n; k++) {
+      c[k].dist = out[7 * k];
+      for (int i = 0; i < 3; i++) { c[k].pos[i] = out[7 * k + 1 + i]; c[k].normal[i] = out[7 * k + 4 + i]; c[k].tangent[i] = 0; }
+    }
+    return n;
+  }
+  if (t1 >= BMJ_GEOM_SPHERE && t2 <= BMJ_GEOM_BOX) {
+    // every remaining pair of convex primitives (an ellipsoid, a cylinder or two boxes involved): MPR, one contact
+    int n = cvx_pair(t1, p1, m1, s1, t2, p2, m2, s2, margin, &c->dist, c->pos, c->normal);
+    if (n) for (int i = 0; i < 3; i++) c->tangent[i] = 0;
+    return n;
   }
   return -1;
 }
@@ -1601,6 +1613,20 @@ void bmjo_contact(void* dv, int i, double* out) {
   for (int j = 0; j < 2; j++) out[k++] = c->solref[j];
   for (int j = 0; j < 5; j++) out[k++] = c->solimp[j];
   out[k++] = c->dim; out[k++] = c->geom1; out[k++] = c->geom2; out[k++] = c->efc_address;
+}
+
+// One geom pair through the narrow phase (test hook, tests/test_convex_pairs.py): geoms given as type, pos[3], mat[9]
+// (row-major), size[3]; the pair is type-sorted as the compiler would emit it. out[k*10 ..] = dist, pos[3], normal[3],
+// tangent hint[3]. Returns the contact count (-1: unsupported pair).
+int bmjo_narrowphase(int t1, const double* p1, const double* m1, const double* s1, int t2, const double* p2, const double* m2,
+                     const double* s2, double margin, double* out) {
+  RawCon raw[8];
+  int n = narrowphase(raw, t1, t2, margin, p1, m1, s1, p2, m2, s2);
+  for (int k = 0; k < n; k++) {
+    out[10 * k] = raw[k].dist;
+    for (int i = 0; i < 3; i++) { out[10 * k + 1 + i] = raw[k].pos[i]; out[10 * k + 4 + i] = raw[k].normal[i]; out[10 * k + 7 + i] = raw[k].tangent[i]; }
+  }
+  return n;
 }
 
 // Batched rollout helper for the CPU baseline: env e uses state rows e of the [B, n] arrays.

@@ -18,8 +18,9 @@ _lib = None
 
 def build(force=False):
   src = os.path.join(_HERE, 'mjoracle.cpp')
-  hdr = os.path.join(os.path.dirname(_HERE), 'include', 'b200mj_model_fields.h')
-  if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+  inc = os.path.join(os.path.dirname(_HERE), 'include')
+  deps = [src, os.path.join(inc, 'b200mj_model_fields.h'), os.path.join(inc, 'b200mj_convex.h')]
+  if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
     subprocess.check_call(['make', '-C', _HERE, '-s'])
   return _SO
 
@@ -55,6 +56,8 @@ def lib():
     L.bmjo_warning.restype = ip
     L.bmjo_warning.argtypes = [vp]
     L.bmjo_contact.argtypes = [vp, ctypes.c_int, dp]
+    L.bmjo_narrowphase.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_int, dp, dp, dp, ctypes.c_double, dp]
+    L.bmjo_narrowphase.restype = ctypes.c_int
     _lib = L
   return _lib
 
@@ -215,3 +218,14 @@ class OraclePhysics:
         out[0] += fp + fn
         out[k] = (fp - fn) * c.friction[k - 1]
     return out
+
+
+def narrowphase(t1, p1, m1, s1, t2, p2, m2, s2, margin=0.0):
+  """One geom pair through the oracle's narrow phase (types must satisfy t1 <= t2). Returns [(dist, pos, normal)]."""
+  dp = ctypes.POINTER(ctypes.c_double)
+  arrs = [np.ascontiguousarray(a, dtype=np.float64).ravel() for a in (p1, m1, s1, p2, m2, s2)]
+  out = np.zeros(80)
+  n = lib().bmjo_narrowphase(int(t1), arrs[0].ctypes.data_as(dp), arrs[1].ctypes.data_as(dp), arrs[2].ctypes.data_as(dp), int(t2),
+                             arrs[3].ctypes.data_as(dp), arrs[4].ctypes.data_as(dp), arrs[5].ctypes.data_as(dp), float(margin),
+                             out.ctypes.data_as(dp))
+  return [(out[10 * k], out[10 * k + 1:10 * k + 4].copy(), out[10 * k + 4:10 * k + 7].copy()) for k in range(max(n, 0))]

@@ -56,7 +56,7 @@ def test_oracle_reproduces_goldens(name, nsub, nsteps, oracle_mod):
 
 def test_goldens_end_in_contact():
   """The contact-pair assertion must bite: every contact-capable model ends with contacts in at least one environment."""
-  for name in ('cheetah', 'humanoid', 'quadruped_floor', 'pendulum_free', 'cmu_humanoid'):
+  for name in ('cheetah', 'humanoid', 'quadruped_floor', 'pendulum_free', 'convex_zoo_floor', 'cmu_humanoid'):
     assert len(GOLD[f'{name}_pairs']) > 0, name
 
 

@@ -60,3 +60,22 @@ def test_model_side_and_errors():
     n.data.xpos['torso', 'w']
   with pytest.raises(AttributeError):
     n.data.not_a_field
+
+
+def test_model_writes_are_tracked_or_refused():
+  """Editing the model must reach the device copy: named writes and model.set() bump the version that triggers the
+  re-upload; a raw `model.<field>[i] = v` is refused (read-only view) instead of being silently ignored."""
+  import types
+  import numpy as np
+  import pytest
+  from dm_control_b200 import index, testing_models as tm
+  m = tm.load('cheetah').copy()
+  phys = types.SimpleNamespace(model=m, data=types.SimpleNamespace())
+  named = index.NamedIndexStructs(phys)
+  v0 = m._version
+  named.model.geom_size['ground', 0] = 3.5
+  assert m._version == v0 + 1 and m.fields['geom_size'].reshape(-1, 3)[m.name2id('ground', 'geom'), 0] == 3.5
+  m.set('body_mass', 2.0, 1)
+  assert m._version == v0 + 2 and m.body_mass[1] == 2.0
+  with pytest.raises(ValueError):
+    m.body_mass[1] = 3.0

@@ -61,3 +61,39 @@ def test_gather_to_rank0_world2_gloo(global_batch):
     p.join(120)
     assert p.exitcode == 0
   assert dict(ret) == {0: True, 1: True, 2: True}
+
+
+def _worker_allgather(rank, world, port, n_local, ret):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+  r, w, _ = sharding.init_from_env(backend='gloo')
+  idx = torch.arange(r * n_local, (r + 1) * n_local, dtype=torch.float64)
+  block = idx[:, None] * 1000 + torch.arange(69, dtype=torch.float64)[None, :]
+  out = sharding.alloc_gather(block, w)
+  ok = True
+  for step in range(3):
+    sharding.gather_packed(block + step, out)       # same preallocated destination every step
+    want = torch.arange(w * n_local, dtype=torch.float64)[:, None] * 1000 + torch.arange(69, dtype=torch.float64)[None, :] + step
+    ok = ok and bool(torch.equal(out, want))
+  ret[r] = ok
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_gather_packed_world2_gloo():
+  """bench.py's per-step exchange: one all_gather_into_tensor into a preallocated block, environment order on every rank."""
+  ctx = mp.get_context('spawn')
+  ret = ctx.Manager().dict()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker_allgather, args=(r, 2, port, 32, ret)) for r in range(2)]
+  for p in procs:
+    p.start()
+  for p in procs:
+    p.join(120)
+    assert p.exitcode == 0
+  assert dict(ret) == {0: True, 1: True}
+
+
+def test_gather_packed_single_process_is_a_copy():
+  block = torch.arange(12, dtype=torch.float64).reshape(4, 3)
+  out = sharding.alloc_gather(block, 1)
+  assert torch.equal(sharding.gather_packed(block, out), block)

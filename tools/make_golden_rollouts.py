@@ -18,7 +18,7 @@ from dm_control_b200 import testing_models as tm
 from oracle import oracle as om
 
 # (model, physics steps per control step, control steps)
-CASES = (('cartpole', 1, 40), ('cheetah', 1, 60), ('humanoid', 5, 16), ('quadruped', 4, 12), ('quadruped_floor', 4, 30), ('pendulum_free', 2, 30),
+CASES = (('cartpole', 1, 40), ('cheetah', 1, 60), ('humanoid', 5, 16), ('quadruped', 4, 12), ('quadruped_floor', 4, 30), ('pendulum_free', 2, 30), ('convex_zoo_floor', 5, 14),
          ('cmu_humanoid', 6, 24))
 B, SEED = 3, 21
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'oracle_rollouts.npz')
