@@ -286,6 +286,8 @@ def run_gpu(args):
     env.physics.check_errors = False   # no device->host sync inside the rollout; warnings are summed at the end
     # the task's ~80 tiny reward/observation launches replay as one CUDA graph (falls back to eager if capture fails)
     env._graph_task_ops = not os.environ.get('B200_BENCH_NO_GRAPH')
+    # ... and, where no events are recorded inside the step (the e2e arm), the whole control step as ONE graph
+    env._graph_step = not os.environ.get('B200_BENCH_NO_GRAPH')
     # start states: the task's own initialize_episode (suite/humanoid.py:152-166: random joint configuration, rejected
     # until contact-free), then the settle below
     env.reset()
@@ -447,7 +449,7 @@ def run_gpu(args):
         config=dict(workload='suite.humanoid:run', batch_per_gpu=BATCH, global_batch=BATCH * world, n_sub_steps=NSUB,
                     physics_steps_per_s=value * NSUB, parallelism=f'env-sharded x{world}',
                     start_states=f'task.initialize_episode (suite/humanoid.py:152-166) + {settle + 1} settle env-steps',
-                    call='BatchedEnvironment.step (value and e2e)',
+                    call='BatchedEnvironment.step (value: eager launches with CUDA events around the physics call; e2e: the same step replayed as one CUDA graph)',
                     actions='uniform(-1,1) generated on device', l2='256 MB flush write between steps, inside the timed region',
                     task_ops='one CUDA-graph replay' if env._graph_task_ops else 'eager torch ops',
                     obs_gather='NCCL all_gather_into_tensor of [B,69] f64 each step; every rank copies its own rows to pinned host memory' if world > 1 else 'n/a (1 GPU)',

@@ -30,7 +30,7 @@ FIRST, MID, LAST = 0, 1, 2
 class BatchedEnvironment:
 
   def __init__(self, physics, task, time_limit=float('inf'), control_timestep=None, n_sub_steps=None,
-               legacy_step=True, auto_reset=True, graph_task_ops=False):
+               legacy_step=True, auto_reset=True, graph_task_ops=False, graph_step=False):
     self._physics, self._task = physics, task
     physics.legacy_step = legacy_step
     if n_sub_steps is not None and control_timestep is not None:
@@ -53,6 +53,13 @@ class BatchedEnvironment:
     self._graph_task_ops = graph_task_ops
     self._graph = None
     self._graph_out = None
+    # Optional: the WHOLE control step — before_step, the physics call (its ~40 kernel launches on the engine's
+    # streams), after_step, reward, observation, step counters — captured once per physics-flag combination and
+    # replayed as one CUDA graph: one launch per step from the host, so a busy host cannot starve the GPU. Needs
+    # `physics.check_errors = False` (the warning check is a device->host sync); the action is copied into a static
+    # buffer; returned tensors are static buffers that the next step overwrites.
+    self._graph_step = graph_step
+    self._step_graphs = {}
 
   @property
   def physics(self):
@@ -96,16 +103,8 @@ class BatchedEnvironment:
     self._graph.replay()
     return self._graph_out
 
-  def step(self, action, timing=None):
-    """One control step for every environment. `timing`: optional (start, end) CUDA events recorded around the
-    physics call (bench.py times the step's kernel group with them); no effect on the result."""
-    if self._auto_reset and self._count_ub >= self._step_limit:
-      if bool(self._reset_next.any()):
-        mask = self._reset_next
-        self._task.initialize_episode(self._physics, mask)
-        self._step_count[mask] = 0
-        self._reset_next = torch.zeros_like(mask)
-      self._count_ub = int(self._step_count.max())      # slow path only: one more readback, then exact again
+  def _device_step(self, action, timing=None, eager_task_ops=False):
+    """Everything of a control step that runs on the device (capturable: no host reads)."""
     self._task.before_step(action, self._physics)
     if timing is not None:
       timing[0].record()
@@ -113,9 +112,11 @@ class BatchedEnvironment:
     if timing is not None:
       timing[1].record()
     self._task.after_step(self._physics)
-    reward, obs = self._reward_and_observation()
+    if eager_task_ops:
+      reward, obs = self._task.get_reward(self._physics), self._task.get_observation(self._physics)
+    else:
+      reward, obs = self._reward_and_observation()
     self._step_count += 1
-    self._count_ub += 1
     last = self._step_count >= self._step_limit
     discount = torch.ones_like(reward)
     # task termination (control.py:113-118): None = the task never terminates; otherwise a [B] tensor holding the
@@ -126,7 +127,51 @@ class BatchedEnvironment:
       ended = ~torch.isnan(term)
       discount = torch.where(ended & ~last, term, discount)
       last = last | ended
+    step_type = torch.where(last, LAST, MID)
+    return reward, obs, discount, last, step_type, term is not None
+
+  def _graphed_step(self, action):
+    phys = self._physics
+    key = phys._flags()
+    entry = self._step_graphs.get(key)
+    if entry is None:
+      # first call with this flag combination: run eagerly (allocations, lazy module loads), capture on the next one
+      self._step_graphs[key] = 'warm'
+      return self._device_step(action, eager_task_ops=True)
+    if entry == 'warm':
+      static_action = torch.empty_like(action)
+      static_action.copy_(action)
+      pos_current = phys._pos_current
+      g = torch.cuda.CUDAGraph()
+      torch.cuda.synchronize(phys.device)
+      with torch.cuda.graph(g):
+        out = self._device_step(static_action, eager_task_ops=True)
+      # the capture did not execute anything: restore the facade's bookkeeping and the step counter's value, then replay
+      after = phys._pos_current
+      phys._pos_current = pos_current
+      entry = self._step_graphs[key] = (g, static_action, out, after)
+    g, static_action, out, after = entry
+    static_action.copy_(action)
+    g.replay()
+    phys._pos_current = after
+    return out
+
+  def step(self, action, timing=None):
+    """One control step for every environment. `timing`: optional (start, end) CUDA events recorded around the
+    physics call (bench.py times the step's kernel group with them); no effect on the result."""
+    if self._auto_reset and self._count_ub >= self._step_limit:
+      if bool(self._reset_next.any()):
+        mask = self._reset_next
+        self._task.initialize_episode(self._physics, mask)
+        self._step_count[mask] = 0
+        self._reset_next = torch.zeros_like(mask)
+      self._count_ub = int(self._step_count.max())      # slow path only: one more readback, then exact again
+    if self._graph_step and timing is None and not self._physics.check_errors:
+      reward, obs, discount, last, step_type, may_end = self._graphed_step(action)
+    else:
+      reward, obs, discount, last, step_type, may_end = self._device_step(action, timing)
+    self._count_ub += 1
+    if may_end:
       self._count_ub = float('inf')       # episodes may end at any step: check the flags on the next call
     self._reset_next = last
-    step_type = torch.where(last, LAST, MID)
     return TimeStep(step_type, reward, discount, obs)

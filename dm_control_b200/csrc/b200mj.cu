@@ -47,6 +47,8 @@ struct DevModel {
   // actuator moments by dof (CSR, built by b200mj_model_create): joint and fixed-tendon transmissions have constant
   // moment arms, so qfrc_actuator[i] = sum over dof_act_id[dof_act_adr[i] .. dof_act_adr[i+1]) of coef * force
   const int* dof_act_adr; const int* dof_act_id; const double* dof_act_coef;
+  // per-environment geoms (b200mj_model_set_variable_geoms): geom_varid[g] = slot k of io.var_geom_pos / var_geom_size, or -1
+  const int* geom_varid; int nvargeom;
   int ldv;          // padded row length of nv-wide matrices (odd => conflict-free column walks)
   int integrator, iterations, ls_iterations, disableflags;
   int any_damping, acc_sensors;
@@ -95,9 +97,11 @@ struct b200mj_model {
   int* d_idata;
   double* d_rdata;
   int* d_xi; double* d_xr;      // derived tables (dof_act_*)
+  int* d_varid;                 // geom -> variable-geom slot
   int envs_per_block;
   size_t smem_per_env;
   int tn_nv;                  // nv when a compile-time-size acceleration kernel exists for this model, else 0
+  int nkey;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -209,7 +213,9 @@ struct Ctx {
   // where the position/velocity stage deposits what the acceleration stage consumes: the workspace itself in the
   // fused kernel, this environment's row of the L2-resident handover buffer in the split position kernel
   double *pM, *pJ, *pD, *pAref, *pBias, *pPassive; int* pEq; double* stage;
-  __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df, int sl) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df), sync_level(sl) {
+  int env; const double* var_pos; const double* var_size;      // per-environment geoms (set_env)
+  __device__ void set_env(int e, const b200mj_io& io) { env = e; var_pos = io.var_geom_pos; var_size = io.var_geom_size; }
+  __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df, int sl) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df), sync_level(sl), env(0), var_pos(nullptr), var_size(nullptr) {
     pM = ws_ + L_.M; pJ = ws_ + L_.J; pD = ws_ + L_.efcD; pAref = ws_ + L_.aref; pBias = ws_ + L_.bias; pPassive = ws_ + L_.passive;
     pEq = reinterpret_cast<int*>(ws_ + L_.eqflag); stage = ws_ + L_.J;
   }
@@ -630,6 +636,29 @@ __device__ __noinline__ void tree_accumulate_raw(const int* parentid, int nbody,
 // ------------------------------------------------------------------------------------------------
 // position stage
 // ------------------------------------------------------------------------------------------------
+// geom_pos / geom_size / bounding radius of geom g in environment `env`: the model's, or this environment's own
+// (corridor walls and platforms differ per environment while the topology is shared; arenas/corridors.py:394-440)
+__device__ __forceinline__ void geom_pos_of(const Ctx& c, int g, double* gp) {
+  const DevModel& m = c.m;
+  const int k = (m.nvargeom > 0 && c.var_pos) ? m.geom_varid[g] : -1;
+  const double* src = k >= 0 ? c.var_pos + ((size_t)c.env * m.nvargeom + k) * 3 : m.geom_pos + 3 * g;
+  gp[0] = src[0]; gp[1] = src[1]; gp[2] = src[2];
+}
+__device__ __forceinline__ double geom_size_of(const Ctx& c, int g, double* sz) {
+  const DevModel& m = c.m;
+  const int k = (m.nvargeom > 0 && c.var_size) ? m.geom_varid[g] : -1;
+  if (k < 0) { sz[0] = m.geom_size[3 * g]; sz[1] = m.geom_size[3 * g + 1]; sz[2] = m.geom_size[3 * g + 2]; return m.geom_rbound[g]; }
+  const double* src = c.var_size + ((size_t)c.env * m.nvargeom + k) * 3;
+  sz[0] = src[0]; sz[1] = src[1]; sz[2] = src[2];
+  const int t = m.geom_type[g];
+  if (t == BMJ_GEOM_SPHERE) return sz[0];
+  if (t == BMJ_GEOM_CAPSULE) return sz[0] + sz[1];
+  if (t == BMJ_GEOM_CYLINDER) return sqrt(sz[0] * sz[0] + sz[1] * sz[1]);
+  if (t == BMJ_GEOM_ELLIPSOID) return fmax(sz[0], fmax(sz[1], sz[2]));
+  if (t == BMJ_GEOM_BOX) return sqrt(sz[0] * sz[0] + sz[1] * sz[1] + sz[2] * sz[2]);
+  return m.geom_rbound[g];
+}
+
 __device__ __forceinline__ void kinematics(const Ctx& c) {
   const DevModel& m = c.m; int lane = c.lane;
   double* qpos = W(qpos); double* xpos = W(xpos); double* xquat = W(xquat); double* xmat = W(xmat);
@@ -709,7 +738,8 @@ __device__ __forceinline__ void kinematics(const Ctx& c) {
   }
   FOR_LANES(g, m.ngeom) {
     int b = m.geom_bodyid[g];
-    double tmp[3], q[4], gp[3] = {m.geom_pos[3*g], m.geom_pos[3*g+1], m.geom_pos[3*g+2]};
+    double tmp[3], q[4], gp[3];
+    geom_pos_of(c, g, gp);
     double gq[4] = {m.geom_quat[4*g], m.geom_quat[4*g+1], m.geom_quat[4*g+2], m.geom_quat[4*g+3]};
     mat_vec(tmp, xmat + 9 * b, gp);
     for (int i = 0; i < 3; i++) W(gxpos)[3 * g + i] = xpos[3 * b + i] + tmp[i];
@@ -733,7 +763,8 @@ __device__ __forceinline__ void site_frame(const Ctx& c, int s, double* pos, dou
 __device__ __forceinline__ void geom_frame(const Ctx& c, int g, double* pos, double* mat) {
   const DevModel& m = c.m;
   int b = m.geom_bodyid[g];
-  double tmp[3], q[4], gp[3] = {m.geom_pos[3*g], m.geom_pos[3*g+1], m.geom_pos[3*g+2]};
+  double tmp[3], q[4], gp[3];
+  geom_pos_of(c, g, gp);
   double gq[4] = {m.geom_quat[4*g], m.geom_quat[4*g+1], m.geom_quat[4*g+2], m.geom_quat[4*g+3]};
   mat_vec(tmp, W(xmat) + 9 * b, gp);
   for (int i = 0; i < 3; i++) pos[i] = W(xpos)[3 * b + i] + tmp[i];
@@ -1088,18 +1119,16 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
       const double* m1 = W(gxmat) + 9 * g1; const double* m2 = W(gxmat) + 9 * g2;
       bool keep;
       double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      double s1[3], s2[3];
+      const double rb1 = geom_size_of(c, g1, s1), rb2 = geom_size_of(c, g2, s2);
       if (t1 == BMJ_GEOM_PLANE) {
         double nr[3] = {m1[2], m1[5], m1[8]};
-        keep = dot3(dif, nr) <= m.geom_rbound[g2] + margin;
+        keep = dot3(dif, nr) <= rb2 + margin;
       } else {
-        double bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
+        double bound = rb1 + rb2 + margin;
         keep = dot3(dif, dif) <= bound * bound;
       }
-      if (keep) {
-        double s1[3] = {m.geom_size[3*g1], m.geom_size[3*g1+1], m.geom_size[3*g1+2]};
-        double s2[3] = {m.geom_size[3*g2], m.geom_size[3*g2+1], m.geom_size[3*g2+2]};
-        n = narrowphase(stg, t1, t2, margin, p1, m1, s1, p2, m2, s2);
-      }
+      if (keep) n = narrowphase(stg, t1, t2, margin, p1, m1, s1, p2, m2, s2);
     }
     int total;
     int off = warp_excl_scan(n, lane, &total);
@@ -2050,15 +2079,16 @@ enum { MODE_STEP = 0, MODE_FORWARD = 1 };
 //   ordering one trailing [posvel] pass (= mj_step1 on the new state); MODE_FORWARD = one [posvel + acc] pass.
 extern "C" __global__ void __launch_bounds__(256)
 b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ b200mj_io io,
-                   int batch, int nstep, int flags, int mode, int extra_disable, int sync_level) {
+                   int batch, int nstep, int flags, int mode, int extra_disable, int sync_level, const uint8_t* env_mask) {
   extern __shared__ double smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env = blockIdx.x * (blockDim.x >> 5) + warp;
   // warps past the end of the batch shadow the last environment (same control flow => same barrier count)
-  // and never store
-  const bool live = env < batch;
-  if (!live) env = batch - 1;
+  // and never store; so do the warps of environments outside env_mask (masked reset / forward)
+  const bool live = env < batch && (env_mask == nullptr || env_mask[env < batch ? env : 0] != 0);
+  if (env >= batch) env = batch - 1;
   Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, blockDim.x > 32 ? sync_level : 0);
+  c.set_env(env, io);
   size_t e = (size_t)env;
   // ---- load state ----
   FOR_LANES(i, m.nq) W(qpos)[i] = io.qpos[e * m.nq + i];
@@ -2195,6 +2225,7 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   const bool live = env < batch;
   if (!live) env = batch - 1;
   Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, blockDim.x > 32 ? 1 : 0);
+  c.set_env(env, io);
   size_t e = (size_t)env;
   double* hrow = hand + e * H.total;
   c.pM = hrow + H.M; c.pJ = hrow + H.J; c.pD = hrow + H.efcD; c.pAref = hrow + H.aref; c.pBias = hrow + H.bias;
@@ -2289,6 +2320,7 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   // fewer than rows_gt+1) rows are served by the launch with the matching workspace and leave at once here
   if (nefc <= rows_gt || nefc > rows_le) return;
   Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, 0);
+  c.set_env(env, io);
   const int nv = NVT > 0 ? NVT : m.nv, ld = NVT > 0 ? (NVT | 1) : m.ldv;
   // ---- load state + handover ----
   FOR_LANES(i, m.nq) W(qpos)[i] = io.qpos[e * m.nq + i];
@@ -2655,6 +2687,7 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
     if (!ok) { b200mj_model_destroy(M); return -2; }
     m.dof_act_adr = M->d_xi; m.dof_act_id = M->d_xi + nv + 1; m.dof_act_coef = M->d_xr;
   }
+  M->nkey = h_sizes[BMJ_NKEY];
   M->tn_nv = tn_kernel(m.nv, false) ? m.nv : 0;
   build_layout(M);
   if (M->envs_per_block < 1) { b200mj_model_destroy(M); return -4; }
@@ -2683,6 +2716,7 @@ void b200mj_model_destroy(b200mj_model* M) {
   cudaFree(M->d_idata); cudaFree(M->d_rdata);
   if (M->d_xi) cudaFree(M->d_xi);
   if (M->d_xr) cudaFree(M->d_xr);
+  if (M->d_varid) cudaFree(M->d_varid);
   if (M->d_hand) cudaFree(M->d_hand);
   if (M->d_hand2) cudaFree(M->d_hand2);
   if (M->streams_ok) {
@@ -2713,7 +2747,56 @@ int b200mj_model_set_capacity(b200mj_model* M, int nconmax, int njmax) {
   return M->envs_per_block < 1 ? -4 : 0;
 }
 
-static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, int mode, int extra, void* stream) {
+// masked state reset (b200mj_reset): one thread per (environment, state element)
+extern "C" __global__ void b200mj_reset_kernel(const __grid_constant__ DevModel m, const __grid_constant__ b200mj_io io, int batch,
+                                               const uint8_t* env_mask, const double* key_qpos) {
+  const int per = m.nq + 2 * m.nv + m.na + m.nu + 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)batch * per) return;
+  const int e = (int)(idx / per); int k = (int)(idx % per);
+  if (env_mask && !env_mask[e]) return;
+  if (k < m.nq) { io.qpos[(size_t)e * m.nq + k] = key_qpos ? key_qpos[k] : m.qpos0[k]; return; }
+  k -= m.nq;
+  if (k < m.nv) { io.qvel[(size_t)e * m.nv + k] = 0; return; }
+  k -= m.nv;
+  if (k < m.nv) { if (io.qacc_warmstart) io.qacc_warmstart[(size_t)e * m.nv + k] = 0; return; }
+  k -= m.nv;
+  if (k < m.na) { io.act[(size_t)e * m.na + k] = 0; return; }
+  k -= m.na;
+  if (k < m.nu) { if (io.ctrl) const_cast<double*>(io.ctrl)[(size_t)e * m.nu + k] = 0; return; }
+  if (io.time) io.time[e] = 0;
+}
+
+// mj_contactForce for one contact id of every environment (one thread per environment)
+extern "C" __global__ void b200mj_contact_force_kernel(const __grid_constant__ DevModel m, const __grid_constant__ b200mj_io io,
+                                                       int batch, int cid, double* out6) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch) return;
+  double f[6] = {0, 0, 0, 0, 0, 0};
+  const int ncon = io.ncon ? io.ncon[e] : 0;
+  if (cid >= 0 && cid < ncon && io.contact_efc_address && io.contact_geom && io.efc_force) {
+    const size_t o = (size_t)e * m.nconmax + cid;
+    const int adr = io.contact_efc_address[o];
+    if (adr >= 0) {
+      const int g1 = io.contact_geom[2 * o], g2 = io.contact_geom[2 * o + 1];
+      const int pr1 = m.geom_priority[g1], pr2 = m.geom_priority[g2];
+      int condim; double mu;
+      if (pr1 != pr2) { const int gp = pr1 > pr2 ? g1 : g2; condim = m.geom_condim[gp]; mu = m.geom_friction[3 * gp]; }
+      else { condim = max(m.geom_condim[g1], m.geom_condim[g2]); mu = fmax(m.geom_friction[3 * g1], m.geom_friction[3 * g2]); }
+      const double* ef = io.efc_force + (size_t)e * m.njmax + adr;
+      if (condim == 1) f[0] = ef[0];
+      else {   // pyramid edges (+t1, -t1, +t2, -t2): mju_decodePyramid
+        f[0] = ef[0] + ef[1] + ef[2] + ef[3];
+        f[1] = (ef[0] - ef[1]) * mu;
+        f[2] = (ef[2] - ef[3]) * mu;
+      }
+    }
+  }
+  for (int i = 0; i < 6; i++) out6[(size_t)e * 6 + i] = f[i];
+}
+
+static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, int mode, int extra, void* stream,
+                  const uint8_t* env_mask = nullptr) {
   if (!M || !io || batch <= 0 || nstep < 0) return -1;
   const_cast<b200mj_model*>(M)->reuse_ok = 0;      // the fused kernel leaves no handover behind
   if (!io->qpos || !io->qvel || (M->dm.na > 0 && !io->act)) return -1;
@@ -2723,7 +2806,7 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
   if (const char* pad = getenv("B200MJ_EXTRA_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
   static int sync_level = -1;
   if (sync_level < 0) { const char* sl = getenv("B200MJ_SYNC_LEVEL"); sync_level = sl ? atoi(sl) : 1; }
-  B200MJ_LAUNCH(b200mj_step_kernel, grid, 32 * epb, smem, (cudaStream_t)stream, M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level);
+  B200MJ_LAUNCH(b200mj_step_kernel, grid, 32 * epb, smem, (cudaStream_t)stream, M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level, env_mask);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
@@ -2825,6 +2908,54 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
 
 int b200mj_forward(const b200mj_model* M, const b200mj_io* io, int batch, int extra_disableflags, int flags, void* stream) {
   return launch(M, io, batch, 0, flags, MODE_FORWARD, extra_disableflags, stream);
+}
+
+int b200mj_forward_masked(const b200mj_model* M, const b200mj_io* io, int batch, const uint8_t* env_mask, int extra_disableflags,
+                          int flags, void* stream) {
+  return launch(M, io, batch, 0, flags, MODE_FORWARD, extra_disableflags, stream, env_mask);
+}
+
+int b200mj_reset(const b200mj_model* M, const b200mj_io* io, int batch, const uint8_t* env_mask, int keyframe, void* stream) {
+  if (!M || !io || batch <= 0 || !io->qpos || !io->qvel || (M->dm.na > 0 && !io->act)) return -1;
+  const DevModel& m = M->dm;
+  const double* key = nullptr;
+  if (keyframe >= 0) {
+    if (keyframe >= M->nkey) return -1;
+    key = m.key_qpos + (size_t)keyframe * m.nq;
+  }
+  const long long total = (long long)batch * (m.nq + 2 * m.nv + m.na + m.nu + 1);
+  B200MJ_LAUNCH(b200mj_reset_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, M->dm, *io, batch, env_mask, key);
+  g_launches++;
+  if (cudaGetLastError() != cudaSuccess) return -5;
+  // mj_forward with actuation disabled (engine.py:325-327), sensors on, for the environments just reset
+  return launch(M, io, batch, 0, B200MJ_STEP_SENSORS, MODE_FORWARD, BMJ_DSBL_ACTUATION, stream, env_mask);
+}
+
+int b200mj_contact_force(const b200mj_model* M, const b200mj_io* io, int batch, int contact_id, double* out6, void* stream) {
+  if (!M || !io || !out6 || batch <= 0) return -1;
+  B200MJ_LAUNCH(b200mj_contact_force_kernel, (batch + 127) / 128, 128, 0, (cudaStream_t)stream, M->dm, *io, batch, contact_id, out6);
+  g_launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int b200mj_subtree_vel(const b200mj_model* M, const b200mj_io* io, int batch, int flags, void* stream) {
+  // zero physics steps in the legacy ordering = the trailing mj_step1 alone: position / velocity stage (with collision
+  // when B200MJ_STEP_FULL_FINAL), mj_subtreeVel, position- and velocity-stage sensors, outputs; the state is unchanged
+  return launch(M, io, batch, 0, flags | B200MJ_STEP_LEGACY, MODE_STEP, 0, stream);
+}
+
+int b200mj_model_set_variable_geoms(b200mj_model* M, const int32_t* geom_ids, int n) {
+  if (!M || n < 0 || (n > 0 && !geom_ids)) return -1;
+  const int ng = M->dm.ngeom;
+  int* varid = new int[ng > 0 ? ng : 1];
+  for (int g = 0; g < ng; g++) varid[g] = -1;
+  for (int k = 0; k < n; k++) { if (geom_ids[k] < 0 || geom_ids[k] >= ng) { delete[] varid; return -1; } varid[geom_ids[k]] = k; }
+  if (!M->d_varid && cudaMalloc(&M->d_varid, (size_t)(ng > 0 ? ng : 1) * sizeof(int)) != cudaSuccess) { delete[] varid; return -2; }
+  const bool ok = cudaMemcpy(M->d_varid, varid, (size_t)ng * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+  delete[] varid;
+  if (!ok) return -2;
+  M->dm.geom_varid = M->d_varid; M->dm.nvargeom = n; M->reuse_ok = 0;
+  return 0;
 }
 
 int b200mj_step_host(const b200mj_model* M, const b200mj_io* io, int batch, int nstep, int flags, const double* ctrl_host,

@@ -39,7 +39,8 @@ STEP_LEGACY, STEP_FULL_FINAL, STEP_SENSORS, STEP_REUSE_POS = 1, 2, 4, 8
 # every symbol include/b200mj.h declares
 SYMBOLS = ('b200mj_model_create', 'b200mj_model_destroy', 'b200mj_model_set_disableflags', 'b200mj_model_set_capacity',
            'b200mj_step', 'b200mj_forward', 'b200mj_step_host', 'b200mj_workspace_bytes', 'b200mj_envs_per_block', 'b200mj_describe',
-           'b200mj_launch_count', 'b200mj_error_string', 'b200mj_version')
+           'b200mj_launch_count', 'b200mj_error_string', 'b200mj_version', 'b200mj_reset', 'b200mj_forward_masked',
+           'b200mj_contact_force', 'b200mj_subtree_vel', 'b200mj_model_set_variable_geoms')
 
 _lib = None
 
@@ -68,8 +69,14 @@ def load():
   L.b200mj_forward.argtypes = [vp, ctypes.POINTER(IO), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
   L.b200mj_step_host.argtypes = [vp, ctypes.POINTER(IO), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp,
                                  ctypes.c_int, vp]
+  L.b200mj_reset.argtypes = [vp, ctypes.POINTER(IO), ctypes.c_int, vp, ctypes.c_int, vp]
+  L.b200mj_forward_masked.argtypes = [vp, ctypes.POINTER(IO), ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+  L.b200mj_contact_force.argtypes = [vp, ctypes.POINTER(IO), ctypes.c_int, ctypes.c_int, vp, vp]
+  L.b200mj_subtree_vel.argtypes = [vp, ctypes.POINTER(IO), ctypes.c_int, ctypes.c_int, vp]
+  L.b200mj_model_set_variable_geoms.argtypes = [vp, _c_int_p, ctypes.c_int]
   for f in ('b200mj_step', 'b200mj_forward', 'b200mj_step_host', 'b200mj_model_set_disableflags',
-            'b200mj_model_set_capacity', 'b200mj_envs_per_block'):
+            'b200mj_model_set_capacity', 'b200mj_envs_per_block', 'b200mj_reset', 'b200mj_forward_masked', 'b200mj_contact_force',
+            'b200mj_subtree_vel', 'b200mj_model_set_variable_geoms'):
     getattr(L, f).restype = ctypes.c_int
   L.b200mj_workspace_bytes.argtypes = [vp]
   L.b200mj_workspace_bytes.restype = ctypes.c_int64

@@ -152,6 +152,7 @@ class BatchedPhysics:
           rdata.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), rdata.size, ctypes.byref(self._handle)))
     self._model_version = self.model._version
     self._model_flags_version = self.model._flags_version
+    self._apply_variable_geoms()       # a re-uploaded model forgets its per-environment geom list
 
   def _bind_io(self):
     for name, ctype in _lib.IO_FIELDS:
@@ -257,19 +258,25 @@ class BatchedPhysics:
     c = torch.as_tensor(control, dtype=torch.float64, device=self.device)
     self.data.ctrl.copy_(c.expand_as(self.data.ctrl))
 
-  def reset(self, keyframe_id=None, env_mask=None):
-    """mj_resetData[Keyframe] + mj_forward with actuation disabled (reference: engine.py:306-327)."""
-    m, d = self.model, self.data
-    if keyframe_id is None:
-      q0 = torch.as_tensor(m.qpos0, device=self.device)
-    else:
-      if not 0 <= keyframe_id < m.nkey:
-        raise ValueError(f'`keyframe_id` must be between 0 and {m.nkey}, got: {keyframe_id}')
-      q0 = torch.as_tensor(m.key_qpos.reshape(m.nkey, m.nq)[keyframe_id], device=self.device)
+  def _mask_ptr(self, env_mask):
+    """Device pointer of a [B] uint8 mask (None -> NULL = every environment); keeps the tensor alive on `self`."""
     if env_mask is None:
-      d.qpos.copy_(q0.expand_as(d.qpos))
-      for name in ('qvel', 'act', 'qacc_warmstart', 'time', 'ctrl', 'qfrc_applied', 'xfrc_applied', 'sensordata',
-                   'actuator_force', 'qacc'):
+      self._mask_keep = None
+      return ctypes.c_void_p(None)
+    self._mask_keep = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+    return ctypes.c_void_p(self._mask_keep.data_ptr())
+
+  def reset(self, keyframe_id=None, env_mask=None):
+    """mj_resetData[Keyframe] + mj_forward with actuation disabled (reference: engine.py:306-327), for every
+    environment or for those of `env_mask`; one b200mj_reset call (a state-reset launch + a masked forward launch):
+    the environments outside the mask keep their state AND their outputs."""
+    m, d = self.model, self.data
+    if keyframe_id is not None and not 0 <= keyframe_id < m.nkey:
+      raise ValueError(f'`keyframe_id` must be between 0 and {m.nkey}, got: {keyframe_id}')
+    self._pos_current = False
+    self._sync_model()
+    if env_mask is None:
+      for name in ('qfrc_applied', 'xfrc_applied', 'sensordata', 'actuator_force', 'qacc'):
         t = getattr(d, name, None)
         if t is not None:
           t.zero_()
@@ -278,16 +285,66 @@ class BatchedPhysics:
         self._warn_seen.zero_()
     else:
       mask = torch.as_tensor(env_mask, dtype=torch.bool, device=self.device)
-      d.qpos[mask] = q0
-      for name in ('qvel', 'act', 'qacc_warmstart', 'time', 'ctrl'):
-        t = getattr(d, name)
-        t[mask] = 0
+      for name in ('qfrc_applied', 'xfrc_applied'):      # mj_resetData clears the applied forces of the reset environments too
+        t = getattr(d, name, None)
+        if t is not None:
+          t[mask] = 0
     with self.suppress_physics_errors():   # reference swallows errors here too (control.py:248-251)
-      self.forward(extra_disableflags=DSBL_ACTUATION)
+      with self.check_invalid_state():
+        with torch.cuda.device(self.device):
+          _lib.check(self._L.b200mj_reset(self._handle, ctypes.byref(self._io), self.batch, self._mask_ptr(env_mask),
+                                          -1 if keyframe_id is None else int(keyframe_id), self._stream()))
 
-  def after_reset(self):
-    """Reference: engine.py:329-333."""
-    self.forward(extra_disableflags=DSBL_ACTUATION)
+  def after_reset(self, env_mask=None):
+    """Reference: engine.py:329-333 (mj_forward with actuation disabled); `env_mask` restricts it to the environments
+    being reset, leaving the others' outputs untouched."""
+    if env_mask is None:
+      return self.forward(extra_disableflags=DSBL_ACTUATION)
+    self._pos_current = False
+    self._sync_model()
+    with self.check_invalid_state():
+      with torch.cuda.device(self.device):
+        _lib.check(self._L.b200mj_forward_masked(self._handle, ctypes.byref(self._io), self.batch, self._mask_ptr(env_mask),
+                                                 DSBL_ACTUATION, _lib.STEP_SENSORS if self._sensors else 0, self._stream()))
+
+  def contact_force(self, contact_id):
+    """`mj_contactForce` (reference: mujoco/wrapper/core.py:546-551) for contact `contact_id` of every environment:
+    [B, 6] force and torque in the contact frame (zeros where an environment has fewer contacts)."""
+    out = torch.zeros(self.batch, 6, dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+      _lib.check(self._L.b200mj_contact_force(self._handle, ctypes.byref(self._io), self.batch, int(contact_id),
+                                              ctypes.c_void_p(out.data_ptr()), self._stream()))
+    return out
+
+  def subtree_vel(self):
+    """`mj_subtreeVel` on the current state (reference: locomotion/walkers/legacy_base.py:179-186): refreshes
+    `data.subtree_linvel` (and the other position / velocity-stage outputs) without integrating. After `step()` in the
+    legacy ordering they are current already — this is for states written by hand."""
+    self._sync_model()
+    with torch.cuda.device(self.device):
+      _lib.check(self._L.b200mj_subtree_vel(self._handle, ctypes.byref(self._io), self.batch, self._flags() & ~_lib.STEP_REUSE_POS,
+                                            self._stream()))
+    self._pos_current = False
+
+  def set_variable_geoms(self, geom_ids):
+    """Per-environment geoms: `data.var_geom_pos / var_geom_size` [B, n, 3] replace `model.geom_pos / geom_size` of the
+    listed geoms (initialised from the model). The composer corridor arenas re-draw their wall / platform boxes every
+    episode and the reference recompiles (composer/environment.py:378-383); here the environments share one topology."""
+    ids = np.ascontiguousarray(geom_ids, dtype=np.int32)
+    m, B = self.model, self.batch
+    self._var_geom_ids = ids
+    gp = torch.as_tensor(np.array(m.geom_pos, dtype=np.float64).reshape(-1, 3)[ids], device=self.device)
+    gs = torch.as_tensor(np.array(m.geom_size, dtype=np.float64).reshape(-1, 3)[ids], device=self.device)
+    self.data.var_geom_pos = gp[None].repeat(B, 1, 1).contiguous()
+    self.data.var_geom_size = gs[None].repeat(B, 1, 1).contiguous()
+    self._apply_variable_geoms()
+    self._bind_io()
+    self._pos_current = False
+
+  def _apply_variable_geoms(self):
+    ids = getattr(self, '_var_geom_ids', None)
+    if ids is not None:
+      _lib.check(self._L.b200mj_model_set_variable_geoms(self._handle, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(ids.size)))
 
   @contextlib.contextmanager
   def reset_context(self):

@@ -58,7 +58,7 @@ class Balance(base.Task):
       physics.data.qpos.copy_(q); physics.data.qvel.copy_(v)
     else:
       physics.data.qpos[env_mask] = q[env_mask]; physics.data.qvel[env_mask] = v[env_mask]
-    physics.after_reset()
+    physics.after_reset(env_mask)
 
   def get_observation(self, physics):
     obs = collections.OrderedDict()

@@ -70,7 +70,7 @@ class Humanoid(base.Task):
     physics.reset(env_mask=None if env_mask is None else env_mask)
     for _ in range(200):
       base.randomize_limited_and_rotational_joints(physics, gen, todo)
-      physics.after_reset()
+      physics.after_reset(todo)      # only the environments still being drawn: the others keep their outputs
       todo = todo & (physics.data.ncon > 0)
       if not bool(todo.any()):
         break

@@ -96,7 +96,7 @@ class Move(base.Task):
       q[todo, 2] = z[todo]
       q[todo, 3:7] = quat[todo]
       with physics.suppress_physics_errors():      # a full contact buffer while embedded is expected (quadruped.py:266-270)
-        physics.after_reset()
+        physics.after_reset(todo)
       todo = todo & (physics.data.ncon > 0)
       z = z + 0.01
       if not bool(todo.any()):

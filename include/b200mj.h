@@ -10,7 +10,15 @@
  *   b200mj_forward        <- mujoco.mj_forward (+ actuation-disabled form)  mujoco/engine.py:306-343
  *   b200mj_step_host      <- the same step as seen by rl/control.py:99-127 with HOST action/observation
  *                            buffers (host<->device copies inside the call)
+ *   b200mj_reset          <- Physics.reset(keyframe_id): mj_resetData[Keyframe] + mj_forward   mujoco/engine.py:306-327
+ *   b200mj_forward_masked <- Physics.after_reset() for the environments being reset           mujoco/engine.py:329-333
+ *   b200mj_contact_force  <- mujoco.mj_contactForce                                           mujoco/wrapper/core.py:546-551
+ *   b200mj_subtree_vel    <- mujoco.mj_subtreeVel (after a position/velocity stage)           locomotion/walkers/legacy_base.py:179-186
+ *   b200mj_model_set_variable_geoms <- the per-episode recompile of the composer arenas       composer/environment.py:378-383
  *   b200mj_workspace_bytes / b200mj_envs_per_block / b200mj_describe / b200mj_launch_count : instrumentation
+ *
+ * Threading: a b200mj_model handle owns streams, events and the handover buffers of its last call — like a reference
+ * Physics instance it must be driven by one host thread at a time (the reference's contract: one Physics per thread).
  *
  * Conventions: all `*_dev` pointers are device pointers on the current CUDA device; batched arrays are
  * row-major [batch, n] (one environment's values contiguous: one warp owns one environment and reads its
@@ -43,6 +51,12 @@ typedef struct b200mj_io {
   const double* ctrl;          /* nu  */
   const double* qfrc_applied;  /* nv, may be NULL */
   const double* xfrc_applied;  /* nbody*6 (force, torque), may be NULL */
+  /* per-environment geoms (b200mj_model_set_variable_geoms names which; NULL = every environment uses the model's):
+   * the composer corridor arenas re-draw wall / platform boxes every episode (locomotion/arenas/corridors.py:394-440)
+   * and the reference recompiles its model for that (composer/environment.py:378-383); here the topology is shared and
+   * only these two tables differ between environments */
+  const double* var_geom_pos;   /* nvargeom*3 */
+  const double* var_geom_size;  /* nvargeom*3 */
   /* ---- position / velocity stage outputs (consistent with the NEW state) ---- */
   double* xpos;            /* nbody*3 */
   double* xquat;           /* nbody*4 */
@@ -108,6 +122,25 @@ int b200mj_forward(const b200mj_model* m, const b200mj_io* io, int batch, int ex
 int b200mj_step_host(const b200mj_model* m, const b200mj_io* io, int batch, int nstep, int flags,
                      const double* ctrl_host, double* ctrl_dev, const double* obs_dev, double* obs_host, int nobs,
                      void* stream);
+
+/* mj_resetData / mj_resetDataKeyframe + mj_forward with actuation disabled (Physics.reset, engine.py:306-327) for the
+ * environments whose env_mask byte is non-zero (env_mask == NULL: all), in two launches: qpos <- qpos0 or key_qpos[keyframe]
+ * (keyframe < 0: qpos0), qvel / act / qacc_warmstart / ctrl / time <- 0, then the forward pass; the other
+ * environments' state and outputs are left untouched. */
+int b200mj_reset(const b200mj_model* m, const b200mj_io* io, int batch, const uint8_t* env_mask_dev, int keyframe, void* stream);
+/* mj_forward restricted to the environments of env_mask (NULL: all): after_reset() of a masked reset (engine.py:329-333) */
+int b200mj_forward_masked(const b200mj_model* m, const b200mj_io* io, int batch, const uint8_t* env_mask_dev,
+                          int extra_disableflags, int flags, void* stream);
+/* mj_contactForce (mujoco/wrapper/core.py:546-551) for contact `contact_id` of every environment, from the contact
+ * and efc_force arrays of `io`: out6_dev [batch, 6] = force (normal, tangent1, tangent2) and torque (zero for condim
+ * 1 / 3) in the contact frame; zeros where contact_id >= ncon or the contact has no constraint rows. */
+int b200mj_contact_force(const b200mj_model* m, const b200mj_io* io, int batch, int contact_id, double* out6_dev, void* stream);
+/* mj_step1-equivalent on the current state without integrating: position / velocity stage, mj_subtreeVel
+ * (io->subtree_linvel; locomotion/walkers/legacy_base.py:179-186 calls it after every substep), position- and
+ * velocity-stage sensors, outputs. */
+int b200mj_subtree_vel(const b200mj_model* m, const b200mj_io* io, int batch, int flags, void* stream);
+/* Name the geoms that take per-environment pos / size from io->var_geom_pos / var_geom_size (slot k <-> geom_ids[k]). */
+int b200mj_model_set_variable_geoms(b200mj_model* m, const int32_t* geom_ids, int n);
 
 /* instrumentation */
 int64_t b200mj_workspace_bytes(const b200mj_model* m);   /* shared memory per environment (bytes) */

@@ -39,11 +39,15 @@ def test_contact_force_equals_weight_on_gpu():
   phys.step(500)
   d = phys.data
   assert d.ncon.tolist() == [4, 4]
-  total = 0.0
-  for i in range(4):
+  # mj_contactForce through the C ABI (b200mj_contact_force), as the reference test calls it per contact
+  forces = torch.stack([phys.contact_force(i) for i in range(4)])          # [4, B, 6]
+  total = forces[:, :, 0].sum(0)
+  assert float((total - 9.81 * phys.model.body_mass[1]).abs().max()) < 5e-8
+  assert float(forces[:, :, 3:].abs().max()) == 0.0                          # condim 3: no contact torque (core_test.py:426-462)
+  assert float(phys.contact_force(7).abs().max()) == 0.0                    # beyond ncon: zeros
+  for i in range(4):      # and it is the pyramid decoding of efc_force
     a = int(d.contact_efc_address[0, i])
-    total += float(d.efc_force[0, a:a + 4].sum())   # pyramid: the normal force is the sum of the four edge forces
-  assert abs(total - 9.81 * phys.model.body_mass[1]) < 5e-8
+    assert abs(float(d.efc_force[0, a:a + 4].sum()) - float(forces[i, 0, 0])) < 1e-15
 
 
 @pytest.mark.parametrize('name', ['cheetah', 'cartpole', 'humanoid'])
@@ -237,3 +241,76 @@ def test_copy_then_lockstep():
   a.step(10); b.step(10)
   assert torch.equal(a.get_state(), b.get_state())
   a.free(); a.free()       # idempotent (engine_test.py:203-205)
+
+
+def test_masked_reset_leaves_the_other_environments_alone():
+  """b200mj_reset with an env_mask (engine.py:306-327 for some environments): masked ones go back to qpos0 with fresh
+  outputs, the others keep state AND outputs (sensordata, actuator_force, xpos) bit for bit."""
+  phys = _phys('cheetah', 6)
+  _seed(phys, 'cheetah', 3)
+  phys.set_control(torch.full((6,), 0.4, dtype=torch.float64)); phys.step(7)
+  before = {k: getattr(phys.data, k).clone() for k in ('qpos', 'qvel', 'time', 'sensordata', 'actuator_force', 'xpos', 'qacc', 'ctrl')}
+  mask = torch.tensor([True, False, False, True, False, False], device=DEV)
+  phys.reset(env_mask=mask)
+  keep = ~mask
+  for k, v in before.items():
+    assert torch.equal(getattr(phys.data, k)[keep], v[keep]), k
+  q0 = torch.as_tensor(np.asarray(phys.model.qpos0), device=DEV)
+  assert torch.equal(phys.data.qpos[mask], q0.expand(2, -1)) and float(phys.data.qvel[mask].abs().max()) == 0.0
+  assert float(phys.data.time[mask].abs().max()) == 0.0 and float(phys.data.ctrl[mask].abs().max()) == 0.0
+  assert float(phys.data.actuator_force[mask].abs().max()) == 0.0          # forward ran with actuation disabled
+  fresh = _phys('cheetah', 2)
+  assert torch.equal(phys.data.xpos[mask], fresh.data.xpos)
+  # keyframes through the same entry point
+  with pytest.raises(ValueError):
+    phys.reset(keyframe_id=5)
+
+
+def test_subtree_vel_entry_point_matches_forward():
+  """b200mj_subtree_vel (mj_subtreeVel after a hand-written state, legacy_base.py:179-186) against mj_forward's output."""
+  a, b = _phys('humanoid', 4), _phys('humanoid', 4)
+  for p in (a, b):
+    _seed(p, 'humanoid', 8)
+  q0, v0 = tm.initial_states(a.model, 'humanoid', 4, 9)
+  for p in (a, b):
+    p.data.qpos.copy_(torch.as_tensor(q0)); p.data.qvel.copy_(torch.as_tensor(v0))
+  a.forward(); b.subtree_vel()
+  assert torch.equal(a.data.subtree_linvel, b.data.subtree_linvel) and torch.equal(a.data.xpos, b.data.xpos)
+  assert torch.equal(a.data.qvel, b.data.qvel)
+
+
+VAR_GEOM = """
+<mujoco><worldbody>
+  <geom name="floor" type="plane" size="5 5 .1"/>
+  <geom name="step" type="box" pos="0 0 .1" size=".3 .3 .1"/>
+  <body name="ball" pos="0 0 .6"><freejoint/><geom name="ball" type="sphere" size=".1"/></body>
+</worldbody></mujoco>"""
+
+
+def test_per_environment_geoms(oracle_mod):
+  """set_variable_geoms: every environment has its own platform box (height / half-size); each must behave like a model
+  COMPILED with that box (what the reference does per episode, composer/environment.py:378-383) — checked against the
+  oracle on per-environment models."""
+  from dm_control_b200 import mjcf_compile
+  from dm_control_b200.physics import BatchedPhysics
+  from oracle import oracle as om
+  model = mjcf_compile.compile_xml(VAR_GEOM)
+  B = 3
+  phys = BatchedPhysics(model, batch=B)
+  gid = model.name2id('step', 'geom')
+  phys.set_variable_geoms([gid])
+  pos = torch.tensor([[0, 0, .1], [0, 0, .25], [.05, 0, .05]], dtype=torch.float64)
+  size = torch.tensor([[.3, .3, .1], [.3, .3, .25], [.2, .2, .05]], dtype=torch.float64)
+  phys.data.var_geom_pos[:, 0] = pos.to(DEV); phys.data.var_geom_size[:, 0] = size.to(DEV)
+  phys.forward()
+  phys.step(400)
+  z = phys.data.qpos[:, 2].cpu().numpy()
+  for e in range(B):
+    m = model.copy()
+    m.fields['geom_pos'].reshape(-1, 3)[gid] = pos[e].numpy(); m.fields['geom_size'].reshape(-1, 3)[gid] = size[e].numpy()
+    m.fields['geom_rbound'].reshape(-1)[gid] = float(np.linalg.norm(size[e].numpy())); m.touch()
+    o = om.OraclePhysics(m); o.forward()
+    for _ in range(400):
+      o.control_step(1)
+    assert abs(z[e] - o.qpos[2]) < 1e-9, (e, z[e], o.qpos[2])
+  assert z[1] - z[0] > 0.29 and z[0] - z[2] > 0.09          # resting on platforms of different heights

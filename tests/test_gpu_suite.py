@@ -88,3 +88,30 @@ def test_time_limit_and_auto_reset():
   after = env2.physics.get_state()
   assert torch.equal(after[~mask], before[~mask])
   assert not torch.equal(after[mask], before[mask])
+
+
+@pytest.mark.skipif(DEV != 'cuda', reason='CUDA graphs: device only')
+@pytest.mark.parametrize('domain,task,nu', [('humanoid', 'run', 21), ('cheetah', 'run', 6)])
+def test_whole_step_graph_equals_eager(domain, task, nu):
+  """BatchedEnvironment(graph_step=True): the control step replayed as one CUDA graph (physics launches on the engine's
+  streams + task ops) gives the same trajectory, bit for bit, as the eager path — across the capture itself, the
+  reuse / no-reuse flag combinations and a reset in the middle."""
+  from dm_control_b200 import suite
+  outs = []
+  for graphed in (False, True):
+    env = suite.load(domain, task, batch=32, seed=4)
+    env.physics.check_errors = False
+    env._graph_step = graphed
+    env.reset()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    rows = []
+    for t in range(14):
+      if t == 8:
+        env.reset()
+      a = torch.rand(32, nu, generator=g, device=DEV, dtype=torch.float64) * 2 - 1
+      ts = env.step(a)
+      rows.append(torch.cat([v.reshape(32, -1) for v in ts.observation.values()] + [ts.reward[:, None]], dim=1).clone())
+    outs.append((torch.stack(rows), env.physics.get_state().clone()))
+    if graphed:
+      assert any(isinstance(v, tuple) for v in env._step_graphs.values())      # a graph was really captured and replayed
+  assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
