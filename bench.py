@@ -223,6 +223,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+def _mean_ncon(d):
+  return float(d.ncon.double().mean()) if hasattr(d, 'ncon') else None
+
+
 def _time_env(env, steps, warmup, gen_seed, nu, dev):
   """Device-resident env-steps/s of one BatchedEnvironment through env.step (used for the other BASELINE configs)."""
   import torch
@@ -242,7 +246,7 @@ def _time_env(env, steps, warmup, gen_seed, nu, dev):
   ms = e0.elapsed_time(e1) / steps
   d = env.physics.data
   return dict(batch=B, n_sub_steps=env.n_sub_steps, ms_per_step=ms, env_steps_per_s=B / ms * 1e3,
-              physics_steps_per_s=B * env.n_sub_steps / ms * 1e3, mean_ncon=float(d.ncon.double().mean()),
+              physics_steps_per_s=B * env.n_sub_steps / ms * 1e3, mean_ncon=_mean_ncon(d),
               warnings=[int(x) for x in d.warning.sum(0).tolist()])
 
 
@@ -348,7 +352,8 @@ def run_gpu(args):
       sampler.sample()                                 # clocks / throttle reasons while the region is running
     one_step(timing=kev[i])                            # events around the one b200mj_step call inside env.step
     if i % every == 0:
-      snaps.append((phys.data.ncon.clone(), phys.data.nefc.clone(), phys.data.solver_niter.clone()))
+      snaps.append(tuple(getattr(phys.data, f).clone() if hasattr(phys.data, f) else torch.zeros(BATCH, dtype=torch.int32, device=dev)
+                         for f in ('ncon', 'nefc', 'solver_niter')))
   ev[1].record()
   barrier()
   ms_total = ev[0].elapsed_time(ev[1])

@@ -2506,6 +2506,7 @@ static void build_layout(b200mj_model* M) {
     // row-count buckets: most environments carry far fewer rows than njmax (humanoid: mean 10, max 43 of 64)
     int caps[4] = {10, 24, nj, nj};
     int ncap = 3;
+    if (nj > 96) { caps[0] = 12; caps[1] = 32; caps[2] = 72; caps[3] = nj; ncap = 4; }   // large capacities (CMU corridor): one more step
     if (const char* ev = getenv("B200MJ_BUCKETS")) {
       int a1 = 0, a2 = 0, a3 = 0;
       int got = sscanf(ev, "%d,%d,%d", &a1, &a2, &a3);

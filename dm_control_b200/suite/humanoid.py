@@ -15,7 +15,7 @@ _STAND_HEIGHT = 1.4
 _WALK_SPEED = 1
 _RUN_SPEED = 10
 
-OUTPUTS = ('xpos', 'xmat', 'subtree_com', 'sensordata', 'ncon')
+OUTPUTS = ('xpos', 'xmat', 'subtree_com', 'sensordata', 'ncon', 'nefc', 'solver_niter')
 
 
 class Physics(BatchedPhysics):

@@ -75,6 +75,49 @@ def cmu_humanoid_flat_xml():
   return ET.tostring(root)
 
 
+N_WALLS = 25      # basic_cmu_2019.py:42-48: wall_gap 4, corridor_length 100, no initial padding -> walls at x = 2, 6, ..., 98
+
+
+def cmu_corridor_walls_xml():
+  """`cmu_humanoid_run_walls` (locomotion/examples/basic_cmu_2019.py:34-63) as ONE model: the WallsCorridor arena
+  (arenas/corridors.py:94-120: ground plane + four side planes; :394-440: wall boxes) with the position-controlled CMU
+  humanoid attached by a free joint, and the four `framepos` end-effector sensors the walker adds when it is built
+  (walkers/legacy_base.py:222-233: objtype xbody, reftype xbody = root). The 25 wall boxes get PLACEHOLDER pos / size:
+  every environment overrides them per episode (BatchedPhysics.set_variable_geoms), which stands where the
+  reference's per-episode recompile stands (composer/environment.py:378-383). The egocentric camera observable is not
+  part of the batched task (rendering is out of scope)."""
+  root = ET.fromstring(cmu_humanoid_flat_xml())
+  world = root.find('worldbody')
+  world.remove([g for g in world.findall('geom') if g.get('name') == 'groundplane'][0])
+  L, W, PAD, SH = 100.0, 10.0, 2.0, 4.0      # corridor_length, corridor_width, _CORRIDOR_X_PADDING, _SIDE_WALL_HEIGHT
+  # the arena's geoms live in the arena's own default scope under composer (MuJoCo built-in defaults), not in the walker's
+  # (`<default><geom condim="1" friction=".7" solref=".015 1" .../>`, humanoid_CMU_V2019.xml:8-9): spell them out
+  builtin = dict(condim='3', friction='1 0.005 0.0001', solref='0.02 1', solimp='0.9 0.95 0.001 0.5 2', contype='1', conaffinity='1')
+  def plane(name, pos, size, xyaxes=None):
+    a = dict(name=name, type='plane', pos=' '.join(map(str, pos)), size=' '.join(map(str, size)), **builtin)
+    if xyaxes:
+      a['xyaxes'] = xyaxes
+    return ET.Element('geom', **a)
+  arena = [plane('ground_plane', (L / 2, 0, 0), (L / 2 + PAD, W / 2, 1)),
+           plane('left_plane', (L / 2, W / 2, SH / 2), (L / 2 + PAD, SH / 2, 1), '1 0 0 0 0 1'),
+           plane('right_plane', (L / 2, -W / 2, SH / 2), (L / 2 + PAD, SH / 2, 1), '-1 0 0 0 0 1'),
+           plane('near_plane', (-PAD, 0, SH / 2), (W / 2, SH / 2, 1), '0 1 0 0 0 1'),
+           plane('far_plane', (L + PAD, 0, SH / 2), (W / 2, SH / 2, 1), '0 -1 0 0 0 1')]
+  for k, g in enumerate(arena):
+    world.insert(k, g)
+  walls = ET.Element('body', name='walls')
+  for k in range(N_WALLS):
+    side = 1 if k % 2 == 0 else -1
+    ET.SubElement(walls, 'geom', name=f'wall_{k}', type='box', pos=f'{2.0 + 4.0 * k} {side * 3.0} 1.5', size='0.08 2.0 1.5', **builtin)
+  world.insert(len(arena), walls)
+  body = [b for b in world.findall('body') if b.get('name') == 'root'][0]
+  body.set('pos', '0.5 0 0.94')          # walker_spawn_position (0.5, 0, 0) on top of the upright pose
+  sensor = root.find('sensor')
+  for eff in ('rradius', 'lradius', 'rfoot', 'lfoot'):     # cmu_humanoid.py:330-335 end_effectors
+    ET.SubElement(sensor, 'framepos', name=f'{eff}_end_effector', objtype='xbody', objname=eff, reftype='xbody', refname='root')
+  return ET.tostring(root)
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   caps = dict(cartpole=dict(nconmax=0, njmax=4), cheetah=dict(nconmax=16, njmax=80),
@@ -89,6 +132,9 @@ def main():
     print('quadruped', 'nq', m.nq, 'nv', m.nv, 'nu', m.nu, 'na', m.na, 'nbody', m.nbody, 'ngeom', m.ngeom, 'npair', m.npair)
   except Exception as ex:
     print('quadruped: not compiled yet:', repr(ex))
+  m = mc.compile_xml(cmu_corridor_walls_xml(), nconmax=48, njmax=200)
+  m.save(os.path.join(OUT, 'cmu_corridor_walls.npz'))
+  print('cmu_corridor_walls', 'nq', m.nq, 'nv', m.nv, 'nu', m.nu, 'nbody', m.nbody, 'ngeom', m.ngeom, 'npair', m.npair, 'nsensordata', m.nsensordata)
   m = mc.compile_xml(cmu_humanoid_flat_xml(), nconmax=40, njmax=112)
   m.save(os.path.join(OUT, 'cmu_humanoid.npz'))
   print('cmu_humanoid', 'nq', m.nq, 'nv', m.nv, 'nu', m.nu, 'nbody', m.nbody, 'ngeom', m.ngeom, 'npair', m.npair, 'nsensordata', m.nsensordata,
