@@ -1,0 +1,128 @@
+"""Import shims that let the UNMODIFIED reference sources under /root/reference/dm_control run on this engine.
+
+`install()` registers, in sys.modules:
+  * `dm_env` (+ `dm_env.specs`): a minimal stand-in for the DeepMind `dm_env` package (absent from this image) — the
+    TimeStep / StepType / specs surface that `dm_control/rl/control.py` uses;
+  * `dm_control`, `dm_control.rl`, `dm_control.suite`, `dm_control.suite.utils`, `dm_control.utils`: EMPTY package objects
+    whose `__path__` points INTO /root/reference, so `import dm_control.rl.control`, `dm_control.suite.humanoid`,
+    `dm_control.suite.base`, `dm_control.suite.common`, `dm_control.suite.utils.randomizers`, `dm_control.utils.rewards`
+    ... execute the reference's own files, unmodified, without running the package `__init__`s that would pull in
+    `mujoco`, `lxml`, OpenGL, ...;
+  * `dm_control.mujoco`: a stand-in module whose `Physics` is `dm_control_b200.refview.SingleEnvPhysics` (the reference's
+    numpy Physics API on a B = 1 view of the batched CUDA engine), plus `action_spec` and the `wrapper.mjbindings.enums`
+    the randomizers read.
+Test infrastructure only; nothing under dm_control_b200/ imports it."""
+import collections
+import enum
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE = os.environ.get('DM_CONTROL_REFERENCE', '/root/reference')
+
+
+def available():
+  return os.path.isdir(os.path.join(REFERENCE, 'dm_control', 'suite'))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dm_env stand-in
+# ---------------------------------------------------------------------------------------------------------------
+def _make_dm_env():
+  m = types.ModuleType('dm_env')
+  specs = types.ModuleType('dm_env.specs')
+
+  class Array:
+    def __init__(self, shape, dtype, name=None):
+      self.shape, self.dtype, self.name = tuple(shape), np.dtype(dtype), name
+
+    def __repr__(self):
+      return f'Array(shape={self.shape}, dtype={self.dtype}, name={self.name!r})'
+
+  class BoundedArray(Array):
+    def __init__(self, shape, dtype, minimum, maximum, name=None):
+      super().__init__(shape, dtype, name)
+      self.minimum, self.maximum = np.asarray(minimum, dtype=dtype), np.asarray(maximum, dtype=dtype)
+
+  specs.Array, specs.BoundedArray = Array, BoundedArray
+
+  class StepType(enum.IntEnum):
+    FIRST = 0
+    MID = 1
+    LAST = 2
+
+  class TimeStep(collections.namedtuple('TimeStep', ['step_type', 'reward', 'discount', 'observation'])):
+    __slots__ = ()
+
+    def first(self):
+      return self.step_type == StepType.FIRST
+
+    def mid(self):
+      return self.step_type == StepType.MID
+
+    def last(self):
+      return self.step_type == StepType.LAST
+
+  class Environment:
+    pass
+
+  m.specs, m.StepType, m.TimeStep, m.Environment = specs, StepType, TimeStep, Environment
+  m.restart = lambda observation: TimeStep(StepType.FIRST, None, None, observation)
+  m.transition = lambda reward, observation, discount=1.0: TimeStep(StepType.MID, reward, discount, observation)
+  m.termination = lambda reward, observation: TimeStep(StepType.LAST, reward, 0.0, observation)
+  m.truncation = lambda reward, observation, discount=1.0: TimeStep(StepType.LAST, reward, discount, observation)
+  return m, specs
+
+
+def _package(name, path):
+  p = types.ModuleType(name)
+  p.__path__ = [path]
+  p.__package__ = name
+  return p
+
+
+def install():
+  if not available():
+    raise RuntimeError(f'{REFERENCE}/dm_control not found')
+  if 'dm_control.mujoco' in sys.modules and getattr(sys.modules['dm_control.mujoco'], '_b200_shim', False):
+    return
+  root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  if root not in sys.path:
+    sys.path.insert(0, root)
+  dm_env, specs = _make_dm_env()
+  sys.modules['dm_env'], sys.modules['dm_env.specs'] = dm_env, specs
+  ref = os.path.join(REFERENCE, 'dm_control')
+  for name, sub in (('dm_control', ''), ('dm_control.rl', 'rl'), ('dm_control.suite', 'suite'), ('dm_control.suite.utils', 'suite/utils'),
+                    ('dm_control.utils', 'utils')):
+    sys.modules[name] = _package(name, os.path.join(ref, sub))
+  from dm_control_b200 import refview
+  from dm_control_b200.physics import PhysicsError
+
+  mj = types.ModuleType('dm_control.mujoco')
+  mj._b200_shim = True
+  mj.Physics = refview.SingleEnvPhysics
+
+  def action_spec(physics):       # dm_control/mujoco/engine.py:948-966
+    m = physics.model
+    nu = m.nu
+    is_limited = np.asarray(m.actuator_ctrllimited).ravel().astype(bool)
+    rng = np.asarray(m.actuator_ctrlrange).reshape(nu, 2)
+    minima = np.full(nu, -np.inf); maxima = np.full(nu, np.inf)
+    minima[is_limited], maxima[is_limited] = rng[is_limited, 0], rng[is_limited, 1]
+    return specs.BoundedArray(shape=(nu,), dtype=float, minimum=minima, maximum=maxima)
+  mj.action_spec = action_spec
+  wrapper = types.ModuleType('dm_control.mujoco.wrapper')
+  mjb = types.ModuleType('dm_control.mujoco.wrapper.mjbindings')
+  enums = types.SimpleNamespace(mjtJoint=types.SimpleNamespace(mjJNT_FREE=0, mjJNT_BALL=1, mjJNT_SLIDE=2, mjJNT_HINGE=3))
+  mjb.enums = enums
+  wrapper.mjbindings = mjb
+  mj.wrapper = wrapper
+  sys.modules['dm_control.mujoco'] = mj
+  sys.modules['dm_control.mujoco.wrapper'] = wrapper
+  sys.modules['dm_control.mujoco.wrapper.mjbindings'] = mjb
+  sys.modules['dm_control'].mujoco = mj
+  # rl/control.py defines its own PhysicsError; the engine raises dm_control_b200's: make them one class once imported
+  import dm_control.rl.control as control
+  control.PhysicsError = PhysicsError

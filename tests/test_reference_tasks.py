@@ -1,0 +1,74 @@
+"""north_star: "suite tasks run unchanged". The UNMODIFIED reference sources — dm_control/rl/control.py (Environment),
+dm_control/suite/humanoid.py (task + Physics subclass), suite/base.py, suite/common, suite/utils/randomizers.py,
+utils/rewards.py, utils/containers.py — are imported from /root/reference (tests/refshim wires the few absent third-party
+modules) and drive a B = 1 view of the batched CUDA engine (dm_control_b200/refview.py) for 100 control steps.
+The trajectory is checked against the CPU oracle stepped from the same post-reset state with the same actions.
+
+/root/reference exists in the build container only: the tests skip where it is absent (GPU box).
+  * `-m gpu` twin: runs on the device (or under B200MJ_EMULATE_GPU=1);
+  * CPU-collectable test: runs the same body in a child process against the CPU emulation build of the kernels."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import refshim   # noqa: E402
+
+needs_reference = pytest.mark.skipif(not refshim.available(), reason='/root/reference is not on this machine')
+
+
+def run_unmodified_humanoid(nsteps=100):
+  refshim.install()
+  import dm_control.suite.humanoid as ref_humanoid            # the reference file itself
+  assert os.path.realpath(ref_humanoid.__file__).startswith(os.path.realpath(refshim.REFERENCE))
+  from oracle import oracle as om
+  env = ref_humanoid.run(random=7)                            # control.Environment(Physics, Humanoid, ...), unmodified
+  spec = env.action_spec()
+  assert spec.shape == (21,) and spec.minimum.min() == -1 and spec.maximum.max() == 1
+  ts = env.reset()
+  assert ts.first() and ts.reward is None
+  assert env.physics.data.ncon == 0                           # humanoid.py:160-166: re-drawn until contact-free
+  assert set(ts.observation) == {'joint_angles', 'head_height', 'extremities', 'torso_vertical', 'com_velocity', 'velocity'}
+  phys = env.physics
+  o = om.OraclePhysics(phys.model)
+  o.qpos[:] = phys.data.qpos; o.qvel[:] = phys.data.qvel; o.forward()
+  rs = np.random.RandomState(3)
+  worst = 0.0
+  for t in range(nsteps):
+    a = rs.uniform(-1, 1, 21)
+    ts = env.step(a)
+    o.ctrl[:] = a; o.control_step(5)                          # control_timestep .025 / timestep .005
+    assert not ts.last() and ts.discount == 1.0
+    assert 0.0 <= ts.reward <= 1.0
+    worst = max(worst, float(np.abs(phys.data.qpos - o.qpos).max()), float(np.abs(phys.data.qvel - o.qvel).max()) * 0.1)
+    assert phys.data.ncon == o.ncon
+    assert [(c.geom1, c.geom2) for c in phys.data.contact] == [(c.geom1, c.geom2) for c in o.contact]
+    # the reference task's own observation code, on the oracle's numbers
+    np.testing.assert_allclose(ts.observation['joint_angles'], o.qpos[7:], atol=1e-6)
+    np.testing.assert_allclose(ts.observation['head_height'], np.asarray(o.xpos).reshape(-1, 3)[phys.model.name2id('head', 'body'), 2], atol=1e-6)
+  assert abs(env.physics.time() - nsteps * 0.025) < 1e-9
+  assert worst < 1e-6, worst
+  return worst
+
+
+@needs_reference
+@pytest.mark.gpu
+def test_unmodified_reference_humanoid_task_on_the_engine():
+  run_unmodified_humanoid(100)
+
+
+@needs_reference
+def test_unmodified_reference_humanoid_task_under_emulation():
+  """CPU-collectable twin: the same body in a child process, kernels from the CPU emulation build (tests/emu)."""
+  code = ("import os, sys; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r);"
+          "import gpu_shim; gpu_shim.install();"
+          "import test_reference_tasks as t; print('worst', t.run_unmodified_humanoid(100))") % (
+              ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'emu'))
+  env = dict(os.environ, B200MJ_EMULATE_GPU='1')
+  r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+  assert 'worst' in r.stdout
