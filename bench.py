@@ -234,7 +234,10 @@ def _time_env(env, steps, warmup, gen_seed, nu, dev):
   gen = torch.Generator(device=dev).manual_seed(gen_seed)
   act = torch.empty(B, nu, dtype=torch.float64, device=dev)
   env.physics.check_errors = False
+  if hasattr(env, '_graph_step') and not os.environ.get('B200_BENCH_NO_GRAPH'):
+    env._graph_step = True             # one CUDA graph per control step: these small models are launch-bound otherwise
   env.reset()
+  env.physics.data.warning.zero_()     # reset procedures embed / re-draw on purpose (quadruped.py:266-270): count the rollout only
   for _ in range(warmup):
     act.uniform_(-1, 1, generator=gen); env.step(act)
   torch.cuda.synchronize(dev)
@@ -295,6 +298,12 @@ def run_gpu(args):
     # start states: the task's own initialize_episode (suite/humanoid.py:152-166: random joint configuration, rejected
     # until contact-free), then the settle below
     env.reset()
+    if os.environ.get('B200_BENCH_START') == 'seeded':
+      # round-1 protocol (A/B continuity only): seeded tumbling starts instead of the task's initialize_episode
+      from dm_control_b200 import testing_models as tm
+      q0, v0 = tm.initial_states(env.physics.model, 'humanoid', batch, seed=rank)
+      env.physics.data.qpos.copy_(torch.as_tensor(q0, device=dev)); env.physics.data.qvel.copy_(torch.as_tensor(v0, device=dev))
+      env.physics.forward()
     return env
 
   def runner(env, batch, gather_world):
@@ -339,10 +348,19 @@ def run_gpu(args):
     one_step()
   barrier()
 
-  # ---- device-resident arm: the user-facing env.step, inputs generated on the device ------------------------
+  # ---- kernel-group time for the roofline: a few eager steps with CUDA events around the one b200mj_step call ------
+  nk = min(8, args.steps)
+  kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nk)]
   launches0 = L.b200mj_launch_count()
+  for i in range(nk):
+    one_step(timing=kev[i])
+  torch.cuda.synchronize()
+  launches_per_step = (L.b200mj_launch_count() - launches0) / nk
+  kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / nk
+  one_step(); one_step()                               # back on the graph path (re-captures nothing: same flags)
+
+  # ---- device-resident arm: the user-facing env.step (one CUDA graph per step), inputs generated on the device ----
   ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-  kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
   snaps = []
   barrier()
   ev[0].record()
@@ -350,15 +368,14 @@ def run_gpu(args):
   for i in range(args.steps):
     if sampler and i % every == every // 2:
       sampler.sample()                                 # clocks / throttle reasons while the region is running
-    one_step(timing=kev[i])                            # events around the one b200mj_step call inside env.step
+    one_step()
     if i % every == 0:
       snaps.append(tuple(getattr(phys.data, f).clone() if hasattr(phys.data, f) else torch.zeros(BATCH, dtype=torch.int32, device=dev)
                          for f in ('ncon', 'nefc', 'solver_niter')))
   ev[1].record()
   barrier()
   ms_total = ev[0].elapsed_time(ev[1])
-  kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-  launches = L.b200mj_launch_count() - launches0
+  launches = int(round(launches_per_step * args.steps))
   clocks = sampler.summary() if sampler else None
   t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=dev)
   if world > 1:
@@ -454,7 +471,7 @@ def run_gpu(args):
         config=dict(workload='suite.humanoid:run', batch_per_gpu=BATCH, global_batch=BATCH * world, n_sub_steps=NSUB,
                     physics_steps_per_s=value * NSUB, parallelism=f'env-sharded x{world}',
                     start_states=f'task.initialize_episode (suite/humanoid.py:152-166) + {settle + 1} settle env-steps',
-                    call='BatchedEnvironment.step (value: eager launches with CUDA events around the physics call; e2e: the same step replayed as one CUDA graph)',
+                    call='BatchedEnvironment.step with graph_step=True: the control step (physics launches on the engine streams + task ops) replayed as one CUDA graph, value and e2e; roofline.kernel_ms from 8 eager steps with CUDA events around the b200mj_step call',
                     actions='uniform(-1,1) generated on device', l2='256 MB flush write between steps, inside the timed region',
                     task_ops='one CUDA-graph replay' if env._graph_task_ops else 'eager torch ops',
                     obs_gather='NCCL all_gather_into_tensor of [B,69] f64 each step; every rank copies its own rows to pinned host memory' if world > 1 else 'n/a (1 GPU)',

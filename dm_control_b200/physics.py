@@ -108,9 +108,12 @@ class BatchedPhysics:
     want = None if outputs == 'all' else set(outputs) | set(state_names) | {'warning'}
     self._io = _lib.IO()
     self._applied_dirty = False
+    self._applied_on = False
     for name, shp in self._FIELDS:
       if want is not None and name not in want:
         continue
+      if name in ('qfrc_applied', 'xfrc_applied'):
+        continue        # allocated by enable_applied_forces(): writing to them before that must fail loudly, not be ignored
       t = torch.zeros((B,) + tuple(shp(m)), dtype=torch.float64, device=self.device)
       setattr(self.data, name, t)
     for name, shp in self._INT_FIELDS:
@@ -157,18 +160,22 @@ class BatchedPhysics:
   def _bind_io(self):
     for name, ctype in _lib.IO_FIELDS:
       t = getattr(self.data, name, None)
-      if t is None or t.numel() == 0 or name in ('qfrc_applied', 'xfrc_applied'):
+      if t is None or t.numel() == 0 or (name in ('qfrc_applied', 'xfrc_applied') and not self._applied_on):
         setattr(self._io, name, ctypes.cast(None, ctype))
       else:
         setattr(self._io, name, ctypes.cast(t.data_ptr(), ctype))
 
   def enable_applied_forces(self, on=True):
-    """Route data.qfrc_applied / data.xfrc_applied into the step (off by default: saves two HBM reads per step)."""
+    """Allocate `data.qfrc_applied` [B, nv] / `data.xfrc_applied` [B, nbody, 6] and route them into every step (the
+    reference's arrays always act; here they are opt-in — two HBM reads per physics step and the fused kernel instead
+    of the split path — and do not exist until enabled, so a write without this call raises AttributeError)."""
     self._pos_current = False
-    for name, ctype in _lib.IO_FIELDS:
-      if name in ('qfrc_applied', 'xfrc_applied'):
-        t = getattr(self.data, name)
-        setattr(self._io, name, ctypes.cast(t.data_ptr() if on else None, ctype))
+    self._applied_on = bool(on)
+    m, B = self.model, self.batch
+    for name, shape in (('qfrc_applied', (B, m.nv)), ('xfrc_applied', (B, m.nbody, 6))):
+      if on and getattr(self.data, name, None) is None:
+        setattr(self.data, name, torch.zeros(shape, dtype=torch.float64, device=self.device))
+    self._bind_io()
 
   def free(self):
     if getattr(self, '_handle', None):
@@ -211,6 +218,10 @@ class BatchedPhysics:
     for name in ('qpos', 'qvel', 'act', 'qacc_warmstart', 'time', 'ctrl'):
       getattr(other.data, name).copy_(getattr(self.data, name))
     other.legacy_step = self.legacy_step
+    other.check_errors = self.check_errors
+    if self._applied_on:
+      other.enable_applied_forces(True)
+      other.data.qfrc_applied.copy_(self.data.qfrc_applied); other.data.xfrc_applied.copy_(self.data.xfrc_applied)
     other.forward()
     return other
 
