@@ -343,7 +343,7 @@ def run_gpu(args):
     env._graph_task_ops = False; env._graph = None
     torch.cuda.synchronize()
     one_step()
-  settle = max(args.warmup, 20)
+  settle = int(os.environ.get('B200_BENCH_SETTLE', max(args.warmup, 20)))     # profiling runs shorten it
   for _ in range(settle):
     one_step()
   barrier()

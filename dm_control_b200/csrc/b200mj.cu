@@ -2290,13 +2290,16 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   }
 }
 
-extern "C" __global__ void __launch_bounds__(256)
+// (160, 2): at most five phase-aligned warps per CTA and a 204-register budget, so that two CTAs share an SM (shared memory
+// allows no more); the
+// rarely taken convex narrow phase (cvx_mpr) would otherwise set the kernel's register count to 255 and halve occupancy
+extern "C" __global__ void __launch_bounds__(160, 2)
 b200mj_pos_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                   const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
                   int extra_disable, int flags, int dump, int env0) {
   pos_kernel_body<false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0);
 }
-extern "C" __global__ void __launch_bounds__(256)
+extern "C" __global__ void __launch_bounds__(160, 2)
 b200mj_posfinal_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                        const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
                        int extra_disable, int flags, int dump, int env0) {
@@ -2538,7 +2541,7 @@ static void build_layout(b200mj_model* M) {
     // several small CTAs per SM: no phase barriers in the split kernels
     // position kernels: CTAs of up to 5 phase-aligned warps, two CTAs per SM when they fit
     M->epb_pos = pick(M->smem_pos) > 5 ? 5 : pick(M->smem_pos);
-    if (const char* ev = getenv("B200MJ_EPB_POS")) { int v = atoi(ev); if (v >= 1 && v <= pick(M->smem_pos)) M->epb_pos = v; }
+    if (const char* ev = getenv("B200MJ_EPB_POS")) { int v = atoi(ev); if (v >= 1 && v <= pick(M->smem_pos) && v <= 5) M->epb_pos = v; }   // __launch_bounds__(160, ..)
     M->epb_acc = pick(M->smem_accs_b[M->nbucket - 1]) >= 1 ? 1 : 0;   // one warp per CTA: out-of-bucket environments exit at once
   }
 }
