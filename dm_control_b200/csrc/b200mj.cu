@@ -50,7 +50,7 @@ struct DevModel {
   // per-environment geoms (b200mj_model_set_variable_geoms): geom_varid[g] = slot k of io.var_geom_pos / var_geom_size, or -1
   const int* geom_varid; int nvargeom;
   int ldv;          // padded row length of nv-wide matrices (odd => conflict-free column walks)
-  int integrator, iterations, ls_iterations, disableflags;
+  int integrator, iterations, ls_iterations, disableflags, solver;
   int any_damping, acc_sensors;
   double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
 };
@@ -69,6 +69,7 @@ struct Lay {
   int sens;                              // sensordata staging
   int vold;                              // last-step acceleration kernel: qvel before integration (for rne_post_constraint)
   int colbuf;                            // compile-time-size algebra: column broadcast buffer (TN_COLBUF_DOUBLES)
+  int pgsA, pgsX, pgsB;                  // PGS solver (fused kernel only): A = J M^-1 J' + R [nj x nj], M^-1 J' [nj x ld], b [nj]
   int total;
 };
 
@@ -1762,6 +1763,74 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   return iter;
 }
 
+// --- dual solver: projected Gauss-Seidel (mj_solPGS; oracle/mjoracle.cpp solve_pgs has the statement of the method) ----
+// Runs in the fused kernel only (b200mj_step falls back to it for PGS models): the dense nefc x nefc matrix lives in
+// the workspace. Rows are swept in order, one at a time, by the whole warp (lanes = columns of the row).
+__device__ __forceinline__ int solve_pgs(const Ctx& c, int nefc) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  if (nefc == 0) {
+    FOR_LANES(i, nv) { W(qacc)[i] = W(qaccs)[i]; W(qcon)[i] = 0; }
+    __syncwarp();
+    return 0;
+  }
+  double* A = W(pgsA); double* X = W(pgsX); double* B = W(pgsB); double* f = W(force);
+  const int* eqf = reinterpret_cast<const int*>(W(eqflag));
+  // X_r = M^-1 J_r'  (W(H), W(dinv) hold the factor of M from fwd_acceleration)
+  _Pragma("unroll 1") for (int r = 0; r < nefc; r++) {
+    chol_forward(W(H), W(dinv), W(J) + r * ld, X + r * ld, nv, lane);
+    chol_back(W(H), W(dinv), X + r * ld, X + r * ld, nv, lane);
+  }
+  _Pragma("unroll 1") for (int i = 0; i < nefc; i++) {
+    FOR_LANES(j, nefc) A[i * nefc + j] = dot_rows(W(J) + i * ld, X + j * ld, nv) + (i == j ? 1.0 / W(efcD)[i] : 0.0);
+  }
+  FOR_LANES(r, nefc) B[r] = dot_rows(W(J) + r * ld, W(qaccs), nv) - W(aref)[r];
+  __syncwarp();
+  // warm start: forces implied by qacc_warmstart, kept only if their dual cost is negative
+  if (!(c.disableflags & BMJ_DSBL_WARMSTART)) {
+    FOR_LANES(r, nefc) {
+      const double jar = dot_rows(W(J) + r * ld, W(qaccws), nv) - W(aref)[r];
+      f[r] = (eqf[r] || jar < 0) ? -W(efcD)[r] * jar : 0.0;
+    }
+    __syncwarp();
+    double part = 0;
+    FOR_LANES(i, nefc) part += f[i] * (0.5 * dot_rows(A + i * nefc, f, nefc) + B[i]);
+    const double cost = warp_sum(part);
+    __syncwarp();
+    if (cost > 0) { FOR_LANES(r, nefc) f[r] = 0; }
+  } else { FOR_LANES(r, nefc) f[r] = 0; }
+  __syncwarp();
+  const double scale = 1 / (m.meaninertia * max(1, nv));
+  int iter = 0;
+  _Pragma("unroll 1") while (iter < m.iterations) {
+    double improvement = 0;
+    _Pragma("unroll 1") for (int i = 0; i < nefc; i++) {
+      double part = 0;
+      FOR_LANES(j, nefc) part += A[i * nefc + j] * f[j];
+      const double res = B[i] + warp_sum(part);
+      const double Aii = A[i * nefc + i], old = f[i];
+      double fi = old - res / Aii;
+      if (!eqf[i] && fi < 0) fi = 0;
+      const double delta = fi - old;
+      improvement -= 0.5 * delta * delta * Aii + delta * res;
+      __syncwarp();
+      if (lane == 0) f[i] = fi;
+      __syncwarp();
+    }
+    iter++;
+    if (improvement * scale < m.tolerance) break;
+  }
+  FOR_LANES(i, nv) {
+    double sum = 0;
+    _Pragma("unroll 1") for (int r = 0; r < nefc; r++) sum += W(J)[r * ld + i] * f[r];
+    W(qcon)[i] = sum;
+    W(tmpv)[i] = W(smooth)[i] + sum;
+  }
+  __syncwarp();
+  chol_forward(W(H), W(dinv), W(tmpv), W(qacc), nv, lane);
+  chol_back(W(H), W(dinv), W(qacc), W(qacc), nv, lane);
+  return iter;
+}
+
 // cacc / cfrc_int with qacc + external contact forces (for accelerometer / force / torque sensors)
 __device__ __forceinline__ void rne_post_constraint(const Ctx& c, const b200mj_io& io, int env, int ncon) {
   const DevModel& m = c.m; int lane = c.lane;
@@ -2142,7 +2211,7 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
       fwd_actuation(c);
       fwd_acceleration<0>(c, io, env);
       PHASE_SYNC(1);
-      niter = solve_newton<0>(c, nefc);
+      niter = m.solver == BMJ_SOL_PGS ? solve_pgs(c, nefc) : solve_newton<0>(c, nefc);
     }
     if (sub == 0) { r_ncon = ncon; r_nefc = nefc; if (!final_pass) r_niter = niter; }
     const bool out_acc = !final_pass && sub == 0 && last;
@@ -2454,6 +2523,8 @@ static void build_layout(b200mj_model* M) {
   L.con = take(m.nconmax * CON_STRIDE);
   L.rk = take(m.integrator == BMJ_INT_RK4 ? (m.nq + 3 * nv + 2 * m.na + 8) : 0);
   L.sens = take(m.nsensordata);
+  const bool pgs = m.solver == BMJ_SOL_PGS;
+  L.pgsA = take(pgs ? nj * nj : 0); L.pgsX = take(pgs ? nj * ld : 0); L.pgsB = take(pgs ? nj : 0);
   L.total = o;
   M->smem_per_env = (size_t)o * sizeof(double);
   // One CTA per SM holding as many environments (= warps) as the 227 KB of shared memory allow, at most 8: the
@@ -2555,7 +2626,7 @@ const char* b200mj_error_string(int code) {
     case 0: return "ok";
     case -1: return "bad argument";
     case -2: return "CUDA allocation / copy failed";
-    case -3: return "model feature outside the supported subset (condim 4/6, frictionloss, nv > 64, non-Newton solver)";
+    case -3: return "model feature outside the supported subset (condim 4/6, frictionloss, nv > 64, CG solver, elliptic cones, mesh / hfield geoms)";
     case -4: return "per-environment workspace exceeds 227 KB of shared memory: lower nconmax / njmax";
     case -5: return "kernel launch failed";
     default: return "unknown error";
@@ -2622,7 +2693,7 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   m.neq = h_sizes[BMJ_NEQ]; m.nsensor = h_sizes[BMJ_NSENSOR]; m.nsensordata = h_sizes[BMJ_NSENSORDATA];
   m.npair = h_sizes[BMJ_NPAIR]; m.nlevel = h_sizes[BMJ_NLEVEL]; m.nconmax = h_sizes[BMJ_NCONMAX]; m.njmax = h_sizes[BMJ_NJMAX];
   m.ldv = m.nv | 1;
-  m.integrator = h_opti[BMJ_OPT_INTEGRATOR]; m.iterations = h_opti[BMJ_OPT_ITERATIONS];
+  m.integrator = h_opti[BMJ_OPT_INTEGRATOR]; m.iterations = h_opti[BMJ_OPT_ITERATIONS]; m.solver = h_opti[BMJ_OPT_SOLVER];
   m.ls_iterations = h_opti[BMJ_OPT_LS_ITERATIONS]; m.disableflags = h_opti[BMJ_OPT_DISABLEFLAGS];
   m.timestep = h_optr[BMJ_OPT_TIMESTEP];
   for (int i = 0; i < 3; i++) m.gravity[i] = h_optr[BMJ_OPT_GRAVITY_X + i];
@@ -2632,7 +2703,7 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   for (int i = 0; i < m.nv; i++) if (h_damp[i] > 0) m.any_damping = 1;
   m.acc_sensors = 0;
   for (int i = 0; i < n_sens; i++) { int t = h_sens_type[i]; if (t == BMJ_SENS_ACCELEROMETER || t == BMJ_SENS_FORCE || t == BMJ_SENS_TORQUE) m.acc_sensors = 1; }
-  bool unsupported = m.nv > 64 || h_opti[BMJ_OPT_SOLVER] != BMJ_SOL_NEWTON || h_opti[BMJ_OPT_CONE] != 0 ||
+  bool unsupported = m.nv > 64 || (h_opti[BMJ_OPT_SOLVER] != BMJ_SOL_NEWTON && h_opti[BMJ_OPT_SOLVER] != BMJ_SOL_PGS) || h_opti[BMJ_OPT_CONE] != 0 ||
                      (m.integrator != BMJ_INT_EULER && m.integrator != BMJ_INT_RK4);
   for (int i = 0; i < n_condim; i++) if (h_condim[i] != 1 && h_condim[i] != 3) unsupported = true;
   {   // geom types without a narrow-phase function here (height fields, meshes) must not slip through as contact-free geoms
@@ -2827,6 +2898,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   // Split path: Euler, legacy ordering, no applied forces routed in, workspaces fit. Everything else (RK4, the
   // non-legacy ordering, qfrc/xfrc_applied) runs through the fused kernel.
   bool can_split = split_enabled() && nstep >= (split_enabled() >= 2 ? 1 : 2) && (flags & B200MJ_STEP_LEGACY) && M->dm.integrator == BMJ_INT_EULER &&
+                   M->dm.solver == BMJ_SOL_NEWTON &&
                    !io->qfrc_applied && !io->xfrc_applied && M->epb_pos >= 1 && M->epb_acc >= 1 && io->qpos && io->qvel &&
                    (M->dm.na == 0 || io->act);
   if (!can_split) return launch(M, io, batch, nstep, flags, MODE_STEP, 0, stream);

@@ -1404,6 +1404,71 @@ static void solve_newton(const OModel* m, OData* d) {
   d->solver_niter = iter;
 }
 
+// --- dual solver: projected Gauss-Seidel (mj_solPGS) ------------------------------------------------
+// min over force of  1/2 f' A f + f' b,  A = J M^-1 J' + diag(R),  b = J qacc_smooth - aref,  with f_i >= 0 for every
+// row that is not an equality (limits, pyramidal contact edges). One sweep updates the rows in order,
+// f_i <- project(f_i - (A_i f + b_i) / A_ii); the sweep's cost decrease, scaled like the Newton solver's, stops the
+// iteration. Warm start: the forces the previous acceleration implies (primal constraint update at qacc_warmstart),
+// kept only if their dual cost is negative (zero forces cost 0). The testing humanoid of the reference asks for this
+// solver (dm_control/mujoco/testing/assets/humanoid.xml:9, solver="PGS" iterations="50").
+static void solve_pgs(const OModel* m, OData* d) {
+  const int nv = m->nv, nefc = d->nefc;
+  static thread_local vec A, B, X, f;
+  A.assign((size_t)nefc * nefc, 0); B.assign(nefc, 0); X.assign((size_t)nefc * nv, 0); f.assign(nefc, 0);
+  for (int r = 0; r < nefc; r++) chol_solve(&X[(size_t)r * nv], d->L.data(), &d->efc_J[(size_t)r * nv], nv);    // M^-1 J_r'
+  for (int i = 0; i < nefc; i++) {
+    for (int j = 0; j < nefc; j++) {
+      real s = 0;
+      for (int k = 0; k < nv; k++) s += d->efc_J[(size_t)i * nv + k] * X[(size_t)j * nv + k];
+      A[(size_t)i * nefc + j] = s;
+    }
+    A[(size_t)i * nefc + i] += d->efc_R[i];
+    real s = 0;
+    for (int k = 0; k < nv; k++) s += d->efc_J[(size_t)i * nv + k] * d->qacc_smooth[k];
+    B[i] = s - d->efc_aref[i];
+  }
+  auto dual_cost = [&]() {
+    real c = 0;
+    for (int i = 0; i < nefc; i++) { real s = 0; for (int j = 0; j < nefc; j++) s += A[(size_t)i * nefc + j] * f[j]; c += f[i] * (0.5 * s + B[i]); }
+    return c;
+  };
+  if (!(m->disableflags & BMJ_DSBL_WARMSTART)) {
+    for (int r = 0; r < nefc; r++) {
+      real s = 0;
+      for (int k = 0; k < nv; k++) s += d->efc_J[(size_t)r * nv + k] * d->qacc_warmstart[k];
+      const real jar = s - d->efc_aref[r];
+      f[r] = row_active(d->efc_type[r], jar) ? -d->efc_D[r] * jar : 0;
+    }
+    if (dual_cost() > 0) f.assign(nefc, 0);
+  }
+  const real scale = 1 / (m->meaninertia * std::max(1, nv));
+  int iter = 0;
+  while (iter < m->iterations) {
+    real improvement = 0;
+    for (int i = 0; i < nefc; i++) {
+      real res = B[i];
+      for (int j = 0; j < nefc; j++) res += A[(size_t)i * nefc + j] * f[j];
+      const real old = f[i];
+      f[i] -= res / A[(size_t)i * nefc + i];
+      if (d->efc_type[i] != BMJ_CNSTR_EQUALITY && f[i] < 0) f[i] = 0;
+      const real delta = f[i] - old;
+      improvement -= 0.5 * delta * delta * A[(size_t)i * nefc + i] + delta * res;
+    }
+    iter++;
+    if (improvement * scale < m->tolerance) break;
+  }
+  for (int r = 0; r < nefc; r++) { d->efc_force[r] = f[r]; d->efc_state[r] = f[r] != 0 || d->efc_type[r] == BMJ_CNSTR_EQUALITY; }
+  for (int i = 0; i < nv; i++) {
+    real s = 0;
+    for (int r = 0; r < nefc; r++) s += d->efc_J[(size_t)r * nv + i] * f[r];
+    d->qfrc_constraint[i] = s;
+  }
+  vec rhs(nv);
+  for (int i = 0; i < nv; i++) rhs[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+  chol_solve(d->qacc.data(), d->L.data(), rhs.data(), nv);
+  d->solver_niter = iter;
+}
+
 static void fwd_constraint(const OModel* m, OData* d) {
   int nv = m->nv;
   if (d->nefc == 0) {
@@ -1412,7 +1477,8 @@ static void fwd_constraint(const OModel* m, OData* d) {
     d->solver_niter = 0;
     return;
   }
-  solve_newton(m, d);
+  if (m->solver == BMJ_SOL_PGS) solve_pgs(m, d);
+  else solve_newton(m, d);
 }
 
 // ------------------------------------------------------------------------------------------------
