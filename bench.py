@@ -313,11 +313,14 @@ def run_gpu(args):
     packed = torch.empty(batch, OBS_DIM + 2, dtype=torch.float64, device=dev)
     gathered = sharding.alloc_gather(packed, gather_world) if gather_world > 1 else None
 
-    def pack(ts):
-      o = ts.observation
+    def pack_block(reward, o, discount):
+      # device-side epilogue of the control step (captured with it): the observation dict as one [B, 69] block
       packed[:, :21] = o['joint_angles']; packed[:, 21] = o['head_height']; packed[:, 22:34] = o['extremities']
       packed[:, 34:37] = o['torso_vertical']; packed[:, 37:40] = o['com_velocity']; packed[:, 40:67] = o['velocity']
-      packed[:, 67] = ts.reward; packed[:, 68] = ts.discount
+      packed[:, 67] = reward; packed[:, 68] = discount
+    env.post_step_hook = pack_block
+
+    def pack(ts):
       if gather_world > 1:
         # NCCL over NVLink: observations/rewards of every rank, in environment order (north_star)
         sharding.gather_packed(packed, gathered)

@@ -60,6 +60,9 @@ class BatchedEnvironment:
     # buffer; returned tensors are static buffers that the next step overwrites.
     self._graph_step = graph_step
     self._step_graphs = {}
+    # Optional device-side epilogue of a control step, `hook(reward, observation, discount)`: runs (and is captured)
+    # with the step — e.g. packing the observation dict into one [B, k] block for a single device->host copy.
+    self.post_step_hook = None
 
   @property
   def physics(self):
@@ -128,6 +131,8 @@ class BatchedEnvironment:
       discount = torch.where(ended & ~last, term, discount)
       last = last | ended
     step_type = torch.where(last, LAST, MID)
+    if self.post_step_hook is not None:
+      self.post_step_hook(reward, obs, discount)
     return reward, obs, discount, last, step_type, term is not None
 
   def _graphed_step(self, action):

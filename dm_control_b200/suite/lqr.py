@@ -1,4 +1,5 @@
-"""Batched LQR domain (reference: dm_control/suite/lqr.py:38-267) and its Riccati solver (suite/lqr_solver.py:27-82).
+"""Batched LQR domain (reference: dm_control/suite/lqr.py:38-267). The Riccati solver the reference pairs with it
+(suite/lqr_solver.py:27-82) is a test pin and lives in tests/lqr_riccati.py.
 
 A chain of `n_bodies` unit spheres on collinear slide joints with random spring stiffness, the first `n_actuators`
 of them driven by motors, constraints disabled: a linear system whose optimal policy and cost-to-go are known in
@@ -110,37 +111,6 @@ class LQRLevel(base.Task):
     """Discount 0 where the state norm fell below 1e-6, NaN (= keep going) elsewhere."""
     norm = physics.state_norm()
     return torch.where(norm < self._TERMINAL_TOL, torch.zeros_like(norm), torch.full_like(norm, float('nan')))
-
-
-def solve(mass, stiffness, damping, dt, n_controls, control_cost_coef):
-  """Optimal cost-to-go Hessian P, gain K (u = K x) and closed-loop decay rate beta of the discrete-time LQR problem
-  the domain poses (reference: lqr_solver.py:27-82, same matrices): x = (q, v), v' = v + dt M^-1(-Kq q - Bv v + u),
-  q' = q + dt v'."""
-  import scipy.linalg
-  n, m = mass.shape[0], n_controls
-  j = np.linalg.solve(-mass, np.hstack((np.diag(stiffness), np.diag(damping))))
-  a = np.eye(2 * n) + dt * np.vstack((dt * j + np.hstack((np.zeros((n, n)), np.eye(n))), j))
-  b = np.vstack((np.eye(m), np.zeros((n - m, m))))
-  bc = np.linalg.solve(mass, b)
-  b = dt * np.vstack((dt * bc, bc))
-  q = np.diag(np.hstack([np.ones(n), np.zeros(n)]))
-  r = control_cost_coef * np.eye(m)
-  p = scipy.linalg.solve_discrete_are(a, b, q, r)
-  k = -np.linalg.solve(b.T.dot(p.dot(b)) + r, b.T.dot(p.dot(a)))
-  beta = np.abs(np.linalg.eigvals(a + b.dot(k))).max()
-  if beta >= 1.0:
-    raise RuntimeError('Controlled system is unstable.')
-  return p, k, beta
-
-
-def solve_env(env):
-  """`lqr_solver.solve(env)` for a batched environment (the model, hence P, K, beta, is shared by the batch)."""
-  phys = env.physics
-  model = phys.model
-  phys.forward()
-  mass = phys.data.qM[0].reshape(model.nv, model.nv).cpu().numpy()
-  return solve(mass, np.asarray(model.jnt_stiffness).ravel(), np.asarray(model.dof_damping).ravel(),
-               float(model.opt.timestep), model.nu, env.task.control_cost_coef)
 
 
 def compile_model(n_bodies, n_actuators, random):

@@ -9,6 +9,10 @@ closed form that needs no MuJoCo binary. As in the reference, the first loop ite
 import math
 
 import numpy as np
+
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import lqr_riccati   # noqa: E402
 import pytest
 
 from dm_control_b200.suite import lqr
@@ -33,7 +37,7 @@ def test_lqr_optimal_policy_oracle(n_bodies, n_actuators):
   m = 1000 * 4 / 3 * math.pi * 0.1 ** 3
   expect = m * (n_bodies - np.maximum.outer(np.arange(n_bodies), np.arange(n_bodies)))
   np.testing.assert_allclose(mass, expect, rtol=1e-12)
-  p, k, beta = lqr.solve(mass, np.asarray(model.jnt_stiffness).ravel(), np.asarray(model.dof_damping).ravel(),
+  p, k, beta = lqr_riccati.riccati(mass, np.asarray(model.jnt_stiffness).ravel(), np.asarray(model.dof_damping).ravel(),
                          float(model.opt.timestep), model.nu, 0.1)
   rs = np.random.RandomState(3)
   unit = rs.randn(n_bodies)
@@ -71,7 +75,7 @@ def test_lqr_optimal_policy_gpu(level):
   from dm_control_b200 import control, suite
   B = 32
   env = suite.load('lqr', level, batch=B, seed=0)
-  p, k, beta = lqr.solve_env(env)
+  p, k, beta = lqr_riccati.riccati_for_env(env)
   K = torch.as_tensor(k, device=env.physics.device)
   ts = env.reset()
   x0 = torch.cat([ts.observation['position'], ts.observation['velocity']], dim=1)
