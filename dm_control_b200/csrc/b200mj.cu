@@ -32,6 +32,7 @@
 #include "../../include/b200mj_convex.h"
 
 #define FULL 0xffffffffu
+#define B200MJ_INTERNAL_ACC_SYNC (1 << 16)     // host -> acceleration kernels only (not part of the ABI flags)
 #define FOR_LANES(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
 
 // ------------------------------------------------------------------------------------------------
@@ -79,6 +80,11 @@ struct Hand { int M, J, efcD, aref, eqflag, bias, passive, tenlen, tenJ, counts,
 // second row, written only in the last physics step: what the acceleration-stage sensors need from the position stage
 struct Hand2 { int xpos, xquat, xmat, xipos, scom, cinert, cdof, cdofdot, cvel, con, total; };
 
+// Row-bucket compaction (split path): the position kernel appends every environment to the list of its row-count
+// bucket (count[b] = entries so far, list[b * cap ..]); the acceleration launch of a bucket then runs dense CTAs of
+// several warps over that list instead of one single-warp CTA per environment of which most exit at once.
+struct Compact { int* count; int* list; int cap; int nbucket; int rows_cap[4]; };
+
 struct b200mj_model {
   DevModel dm;
   Lay lay;
@@ -91,6 +97,7 @@ struct b200mj_model {
   // environment groups x row buckets run on their own streams (independent work: hides each launch's tail)
   cudaStream_t gmain[3], gaux[3][4]; cudaEvent_t ev_fork, ev_join[3], ev_pos[3], ev_acc[3][4]; int streams_ok;
   double* d_hand; int hand_batch;
+  int* d_bcount; int* d_blist;     // compaction: counters [3 groups][BCOUNT_SLOTS][4], lists [3 groups][4 buckets][hand_batch]
   // the trailing mj_step1 of the last split-path step left a complete handover for this (io, batch): see B200MJ_STEP_REUSE_POS
   const double* reuse_qpos; int reuse_batch; int reuse_flags; int reuse_ok;
   int epb_pos, epb_acc;
@@ -2283,7 +2290,8 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
 // otherwise the position/velocity half of a physics step, optionally dumping what the acceleration-stage sensors need.
 template <bool FINAL>
 __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L, const Hand& H, const Hand2& H2, const b200mj_io& io,
-                                                double* hand, double* hand2, int batch, int extra_disable, int flags, int dump, int env0) {
+                                                double* hand, double* hand2, int batch, int extra_disable, int flags, int dump, int env0,
+                                                const Compact& cp) {
   extern __shared__ double smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env = env0 + blockIdx.x * (blockDim.x >> 5) + warp;      // this launch covers environments [env0, batch)
@@ -2350,6 +2358,22 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
     }
   }
   FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];      // quaternions were normalised in place
+  if (cp.count != nullptr && (!FINAL || with_constraints)) {
+    // bucket lists for the acceleration launches: one shared-memory ticket per environment, one global atomic per CTA
+    // and bucket (every warp of the CTA gets here: the shadows of environments past the batch end take no ticket)
+    int* cta = reinterpret_cast<int*>(smem + (size_t)(blockDim.x >> 5) * L.total);      // 8 ints behind the workspaces
+    if (threadIdx.x < 8) cta[threadIdx.x] = 0;
+    __syncthreads();
+    int b = 0, my = 0;
+    if (live && lane == 0) {
+      while (b + 1 < cp.nbucket && nefc > cp.rows_cap[b]) b++;
+      my = atomicAdd(&cta[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < cp.nbucket) cta[4 + threadIdx.x] = cta[threadIdx.x] ? atomicAdd(&cp.count[threadIdx.x], cta[threadIdx.x]) : 0;
+    __syncthreads();
+    if (live && lane == 0) cp.list[(size_t)b * cp.cap + cta[4 + b] + my] = env;
+  }
   if (live && io.warning && lane == 0) {
     int* w = io.warning + e * BMJ_NWARNING;
     if (wfull) w[BMJ_WARN_CONTACTFULL] += 1;
@@ -2365,33 +2389,50 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
 extern "C" __global__ void __launch_bounds__(160, 2)
 b200mj_pos_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                   const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
-                  int extra_disable, int flags, int dump, int env0) {
-  pos_kernel_body<false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0);
+                  int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
+  pos_kernel_body<false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
 }
 extern "C" __global__ void __launch_bounds__(160, 2)
 b200mj_posfinal_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                        const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
-                       int extra_disable, int flags, int dump, int env0) {
-  pos_kernel_body<true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0);
+                       int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
+  pos_kernel_body<true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
 }
 
 // LAST = last physics step of a fused step(): acceleration-stage sensors and outputs are produced here
 template <bool LAST, int NVT>
 __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L, const Hand& H, const Hand2& H2, const b200mj_io& io,
                                                 const double* hand, const double* hand2, int batch, int extra_disable, int first_pass,
-                                                int rows_gt, int rows_le, int flags, int env0) {
+                                                int rows_gt, int rows_le, int flags, int env0, const int* bucket_count, const int* bucket_list) {
   extern __shared__ double smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int env = env0 + blockIdx.x * (blockDim.x >> 5) + warp;
-  if (env >= batch) return;
+  int env;
+  bool live = true;
+  // B200MJ_ACC_SYNC: the warps of a compacted CTA are phase-aligned by barriers (load -> M^-1 -> every Newton trip ->
+  // Euler), so that instruction lines are fetched once per CTA: the unrolled algebra executes 83 KB of SASS against a
+  // 32 KB L1.5 I-cache. Warps past the end of the list then shadow its last entry (same control flow, no stores).
+  const bool sync = (flags & B200MJ_INTERNAL_ACC_SYNC) != 0 && bucket_list != nullptr && blockDim.x > 32;
+  if (bucket_list != nullptr) {
+    // compacted launch: warp k of the grid takes entry k of this bucket's list (written by the position kernel)
+    int k = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int n = *bucket_count;
+    if (k >= n) {
+      if (!sync || blockIdx.x * (blockDim.x >> 5) >= n) return;
+      live = false; k = n - 1;
+    }
+    env = bucket_list[k];
+  } else {
+    env = env0 + blockIdx.x * (blockDim.x >> 5) + warp;
+    if (env >= batch) return;
+  }
   size_t e = (size_t)env;
   const double* hrow = hand + e * H.total;
   const int* cnt = reinterpret_cast<const int*>(hrow + H.counts);
   const int ncon = cnt[0], nefc = cnt[1];
   // row-count bucket: this launch's workspace holds up to rows_le constraint rows; environments with more (or
   // fewer than rows_gt+1) rows are served by the launch with the matching workspace and leave at once here
-  if (nefc <= rows_gt || nefc > rows_le) return;
-  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, 0);
+  if (!sync && (nefc <= rows_gt || nefc > rows_le)) return;
+  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, sync ? 3 : 0);
   c.set_env(env, io);
   const int nv = NVT > 0 ? NVT : m.nv, ld = NVT > 0 ? (NVT | 1) : m.ldv;
   // ---- load state + handover ----
@@ -2413,12 +2454,16 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   if (check_bad(c, W(ctrl), m.nu)) { w_badctrl = first_pass; FOR_LANES(i, m.nu) W(ctrl)[i] = 0; __syncwarp(); }
   fwd_actuation(c);
   b200mj_io io_noforce = io; io_noforce.qfrc_applied = nullptr; io_noforce.xfrc_applied = nullptr;
+  if (sync) __syncthreads();
   fwd_acceleration<NVT>(c, io_noforce, env);
+  if (sync) __syncthreads();
   int niter = solve_newton<NVT>(c, nefc);
-  if (LAST) write_outputs(c, io, env, ncon, nefc, niter, false, true, false);
+  if (LAST && live) write_outputs(c, io, env, ncon, nefc, niter, false, true, false);
   if (want_sens) FOR_LANES(i, nv) W(vold)[i] = W(qvel)[i];
+  if (sync) __syncthreads();
   if (check_bad(c, W(qacc), nv)) { w_badqacc = 1; reset_state(c, &time); }
   else euler_step<NVT>(c, &time);
+  if (!live) return;      // shadows: no stores (the sensor epilogue below has no barriers)
   // ---- store state ----
   FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];
   FOR_LANES(i, nv) { io.qvel[e * nv + i] = W(qvel)[i]; if (io.qacc_warmstart) io.qacc_warmstart[e * nv + i] = W(qaccws)[i]; }
@@ -2452,14 +2497,16 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
 extern "C" __global__ void __launch_bounds__(256)
 b200mj_acc_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                   const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
-                  int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0) {
-  acc_kernel_body<false, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
+                  int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0, const int* bucket_count,
+                  const int* bucket_list) {
+  acc_kernel_body<false, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list);
 }
 extern "C" __global__ void __launch_bounds__(256)
 b200mj_acclast_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                       const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
-                      int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0) {
-  acc_kernel_body<true, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
+                  int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0, const int* bucket_count,
+                  const int* bucket_list) {
+  acc_kernel_body<true, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list);
 }
 
 // Acceleration kernels with nv fixed at compile time (register-resident algebra, tn_* above). One instantiation per
@@ -2469,11 +2516,12 @@ b200mj_acclast_kernel(const __grid_constant__ DevModel m, const __grid_constant_
 #define B200MJ_NV_LIST(X) X(6) X(9) X(12) X(18) X(22) X(27)
 #endif
 template <bool LAST, int NVT>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(128, 4)
 b200mj_acc_tn_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                      const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
-                     int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0) {
-  acc_kernel_body<LAST, NVT>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0);
+                     int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0, const int* bucket_count,
+                     const int* bucket_list) {
+  acc_kernel_body<LAST, NVT>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2482,7 +2530,8 @@ b200mj_acc_tn_kernel(const __grid_constant__ DevModel m, const __grid_constant__
 static int64_t g_launches = 0;
 
 typedef void (*acc_kernel_fn)(const DevModel, const Lay, const Hand, const Hand2, const b200mj_io, const double*, const double*,
-                              int, int, int, int, int, int, int);
+                              int, int, int, int, int, int, int, const int*, const int*);
+#define BCOUNT_SLOTS 64
 // the compile-time-size acceleration kernel for nv dofs, or nullptr (B200MJ_TN=0 disables them: A/B runs)
 static acc_kernel_fn tn_kernel(int nv, bool last) {
   static int on = -1;
@@ -2609,7 +2658,7 @@ static void build_layout(b200mj_model* M) {
     H2.cinert = take(10 * nb); H2.cdof = take(6 * nv); H2.cdofdot = take(6 * nv); H2.cvel = take(6 * nb);
     H2.con = take(m.nconmax * CON_STRIDE);
     H2.total = o;
-    auto pick = [](size_t per_env) { int e = (int)((227 * 1024) / (per_env ? per_env : 1)); return e > 8 ? 8 : e; };
+    auto pick = [](size_t per_env) { int e = (int)((227 * 1024 - 64) / (per_env ? per_env : 1)); return e > 8 ? 8 : e; };   // 64: CTA scratch of the bucket compaction
     // several small CTAs per SM: no phase barriers in the split kernels
     // position kernels: CTAs of up to 5 phase-aligned warps, two CTAs per SM when they fit
     M->epb_pos = pick(M->smem_pos) > 5 ? 5 : pick(M->smem_pos);
@@ -2795,6 +2844,8 @@ void b200mj_model_destroy(b200mj_model* M) {
   if (M->d_varid) cudaFree(M->d_varid);
   if (M->d_hand) cudaFree(M->d_hand);
   if (M->d_hand2) cudaFree(M->d_hand2);
+  if (M->d_bcount) cudaFree(M->d_bcount);
+  if (M->d_blist) cudaFree(M->d_blist);
   if (M->streams_ok) {
     for (int g = 0; g < 3; g++) {
       cudaStreamDestroy(M->gmain[g]); cudaEventDestroy(M->ev_join[g]); cudaEventDestroy(M->ev_pos[g]);
@@ -2909,6 +2960,12 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0; M->reuse_ok = 0;
     if (cudaMalloc(&M->d_hand, (size_t)batch * M->hand.total * sizeof(double)) != cudaSuccess) return -2;
     if (cudaMalloc(&M->d_hand2, (size_t)batch * M->hand2.total * sizeof(double)) != cudaSuccess) return -2;
+    if (M->d_bcount) cudaFree(M->d_bcount);
+    if (M->d_blist) cudaFree(M->d_blist);
+    M->d_bcount = M->d_blist = nullptr;
+    if (cudaMalloc(&M->d_bcount, (size_t)3 * BCOUNT_SLOTS * 4 * sizeof(int)) != cudaSuccess) return -2;
+    if (cudaMalloc(&M->d_blist, (size_t)3 * 4 * batch * sizeof(int)) != cudaSuccess) return -2;
+    cudaMemset(M->d_bcount, 0, (size_t)3 * BCOUNT_SLOTS * 4 * sizeof(int));
     M->hand_batch = batch;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -2931,17 +2988,40 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   int ngroups = (all_split && batch >= 2048) ? ngroups_env : 1;
   static int acc_pad = -1;    // occupancy experiments only: extra dynamic shared memory per acceleration CTA
   if (acc_pad < 0) { const char* e = getenv("B200MJ_ACC_PAD"); acc_pad = e ? atoi(e) : 0; }
+  // Row-bucket compaction (B200MJ_COMPACT, default on): acceleration CTAs of B200MJ_ACC_WARPS warps over dense per-bucket
+  // environment lists. Slot k of a group's counters belongs to physics step k of a call; the trailing mj_step1 writes
+  // slot 0 for the next call (B200MJ_STEP_REUSE_POS). The slot sequence is the same in every call, so a captured
+  // CUDA graph of this function stays valid.
+  static int compact_on = -1, acc_warps = 4, acc_sync = 0;
+  if (compact_on < 0) {
+    const char* e = getenv("B200MJ_COMPACT"); compact_on = e ? atoi(e) : 1;
+    if (const char* a = getenv("B200MJ_ACC_SYNC")) acc_sync = atoi(a);
+    if (const char* w = getenv("B200MJ_ACC_WARPS")) { int v = atoi(w); if (v >= 1 && v <= 8) acc_warps = v; }
+  }
+  const bool compact = compact_on && all_split && nstep + 1 <= BCOUNT_SLOTS && M->d_bcount && M->d_blist;
   if (ngroups > 1) cudaEventRecord(M->ev_fork, st);
   for (int g = 0; g < ngroups; g++) {
     const int e0 = (int)((long long)batch * g / ngroups), e1 = (int)((long long)batch * (g + 1) / ngroups), cnt = e1 - e0;
     cudaStream_t sm = (g == 0) ? st : M->gmain[g];
     if (g > 0) cudaStreamWaitEvent(sm, M->ev_fork, 0);
     const int gp = (cnt + M->epb_pos - 1) / M->epb_pos;
+    int* gcount = M->d_bcount ? M->d_bcount + (size_t)g * BCOUNT_SLOTS * 4 : nullptr;
+    int* glist = M->d_blist ? M->d_blist + (size_t)g * 4 * M->hand_batch : nullptr;
+    auto compact_for = [&](int slot) {
+      Compact cp; memset(&cp, 0, sizeof(cp));
+      if (compact) {
+        cp.count = gcount + slot * 4; cp.list = glist; cp.cap = M->hand_batch; cp.nbucket = M->nbucket;
+        for (int b = 0; b < M->nbucket; b++) cp.rows_cap[b] = M->rows_cap[b];
+        cudaMemsetAsync(cp.count, 0, 4 * sizeof(int), sm);
+      }
+      return cp;
+    };
     for (int s = 0; s < nsplit; s++) {
       const bool last = all_split && s == nstep - 1;
       if (!(reuse && s == 0)) {
-        B200MJ_LAUNCH(b200mj_pos_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                                 e1, 0, flags, last && want_sens, e0);
+        const Compact cp = compact_for(s);
+        B200MJ_LAUNCH(b200mj_pos_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                                                                                 e1, 0, flags, last && want_sens, e0, cp);
         g_launches++;
       }
       if (M->nbucket > 1) cudaEventRecord(M->ev_pos[g], sm);
@@ -2954,23 +3034,32 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         int gt = b == 0 ? -1 : M->rows_cap[b - 1], le = M->rows_cap[b];
         cudaStream_t sb = b == 0 ? sm : M->gaux[g][b];     // buckets are independent: let them share the SMs
         if (b > 0) cudaStreamWaitEvent(sb, M->ev_pos[g], 0);
+        const size_t ws = (last ? M->smem_accs_b[b] : M->smem_acc_b[b]);
+        // warps per CTA of a compacted launch: as many as fit 227 KB, at most acc_warps
+        int wpc = 1;
+        if (compact) { wpc = (int)((227 * 1024) / ws); if (wpc > acc_warps) wpc = acc_warps; if (wpc < 1) wpc = 1; }
+        const int grid = compact ? (cnt + wpc - 1) / wpc : cnt;
+        const int* bc = compact ? gcount + s * 4 + b : nullptr;
+        const int* bl = compact ? glist + (size_t)b * M->hand_batch : nullptr;
+        const Lay& la = last ? M->lay_accs_b[b] : M->lay_acc_b[b];
+        const int aflags = flags | ((compact && acc_sync && wpc > 1) ? B200MJ_INTERNAL_ACC_SYNC : 0);
         if (M->tn_nv) {
           acc_kernel_fn fn = tn_kernel(M->tn_nv, last);
-          const Lay& la = last ? M->lay_accs_b[b] : M->lay_acc_b[b];
-          B200MJ_LAUNCH(fn, cnt, 32, (last ? M->smem_accs_b[b] : M->smem_acc_b[b]) + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                        e1, 0, s == 0, gt, le, flags, e0);
-        } else if (last) B200MJ_LAUNCH(b200mj_acclast_kernel, cnt, 32, M->smem_accs_b[b] + acc_pad, sb, M->dm, M->lay_accs_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                            e1, 0, s == 0, gt, le, flags, e0);
-        else B200MJ_LAUNCH(b200mj_acc_kernel, cnt, 32, M->smem_acc_b[b] + acc_pad, sb, M->dm, M->lay_acc_b[b], M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                  e1, 0, s == 0, gt, le, flags, e0);
+          B200MJ_LAUNCH(fn, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                        e1, 0, s == 0, gt, le, aflags, e0, bc, bl);
+        } else if (last) B200MJ_LAUNCH(b200mj_acclast_kernel, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                                                                            e1, 0, s == 0, gt, le, aflags, e0, bc, bl);
+        else B200MJ_LAUNCH(b200mj_acc_kernel, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                                                                  e1, 0, s == 0, gt, le, aflags, e0, bc, bl);
         if (b > 0) cudaEventRecord(M->ev_acc[g][b], sb);
         g_launches++;
       }
       for (int b = 1; b < M->nbucket; b++) cudaStreamWaitEvent(sm, M->ev_acc[g][b], 0);   // join after the main-stream bucket is queued
     }
     if (all_split) {
-      B200MJ_LAUNCH(b200mj_posfinal_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                                    e1, 0, flags, want_sens, e0);
+      const Compact cp = compact_for(0);      // the next call's first acceleration launches read slot 0
+      B200MJ_LAUNCH(b200mj_posfinal_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+                                                                                    e1, 0, flags, want_sens, e0, cp);
       g_launches++;
     }
     if (g > 0) { cudaEventRecord(M->ev_join[g], sm); cudaStreamWaitEvent(st, M->ev_join[g], 0); }
