@@ -239,6 +239,17 @@ class BatchedPhysics:
                                        self._stream()))
     self._pos_current = bool(self.legacy_step and self._full_final and nstep >= 1)
 
+  def bind(self, kind, names):
+    """Batched counterpart of `mjcf.Physics.bind` (dm_control/mjcf/physics.py:516-652): attribute access to the model
+    and data rows of the named elements, prefix-free; state writes mark the physics dirty and the next derived read
+    runs `forward()` lazily. See dm_control_b200/binding.py."""
+    from . import binding
+    return binding.Binding(self, kind, names)
+
+  @property
+  def is_dirty(self):
+    return bool(getattr(self, '_bind_dirty', False))
+
   def mark_as_dirty(self):
     """The state tensors were written directly: the next step() recomputes the position stage first."""
     self._pos_current = False
@@ -246,6 +257,7 @@ class BatchedPhysics:
   def forward(self, extra_disableflags=0):
     """mj_forward on every environment (reference: engine.py:335-343)."""
     self._pos_current = False
+    self._bind_dirty = False
     self._sync_model()
     with self.check_invalid_state():
       with torch.cuda.device(self.device):

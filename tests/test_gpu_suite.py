@@ -115,3 +115,37 @@ def test_whole_step_graph_equals_eager(domain, task, nu):
     if graphed:
       assert any(isinstance(v, tuple) for v in env._step_graphs.values())      # a graph was really captured and replayed
   assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_bind_prefix_free_access_and_lazy_forward():
+  """`physics.bind(kind, names)` (mjcf/physics.py:516-652): prefix-free model/data access per element, ragged joint /
+  sensor fields, and the dirty contract — a qpos write through a binding makes the next derived read run forward()."""
+  from dm_control_b200 import testing_models as tm
+  from dm_control_b200.physics import BatchedPhysics
+  phys = BatchedPhysics(tm.load('humanoid'), batch=3)
+  m = phys.model
+  head, hands = phys.bind('body', 'head'), phys.bind('body', ['left_hand', 'right_hand'])
+  assert head.element_id == m.name2id('head', 'body') and tuple(hands.xpos.shape) == (3, 2, 3) and tuple(head.xpos.shape) == (3, 3)
+  assert torch.equal(head.xpos, phys.named.data.xpos['head'])
+  assert abs(float(head.mass) - float(np.asarray(m.body_mass)[head.element_id])) == 0.0
+  knee = phys.bind('joint', 'right_knee')
+  assert tuple(knee.range.shape) == (2,) and tuple(knee.qpos.shape) == (3, 1)
+  root = phys.bind('joint', 'root')
+  assert tuple(root.qpos.shape) == (3, 7) and tuple(root.qvel.shape) == (3, 6)
+  z0 = head.xpos[:, 2].clone()
+  assert not phys.is_dirty
+  q = root.qpos.clone(); q[:, 2] += 0.25
+  root.qpos = q                                   # state write through the binding -> dirty
+  assert phys.is_dirty
+  z1 = head.xpos[:, 2]                            # derived read -> forward() runs lazily, once
+  assert not phys.is_dirty and float((z1 - z0 - 0.25).abs().max()) < 1e-12
+  sens = phys.bind('sensor', 'torso_subtreelinvel')
+  assert tuple(sens.sensordata.shape) == (3, 3)
+  act = phys.bind('actuator', ['abdomen_y', 'abdomen_z'])
+  act.ctrl = torch.tensor([0.5, -0.5], dtype=torch.float64)
+  assert phys.data.ctrl[:, m.name2id('abdomen_y', 'actuator')].tolist() == [0.5] * 3 and not phys.is_dirty
+  floor = phys.bind('geom', 'floor')
+  v = m._version
+  floor.friction = [0.9, 0.005, 0.0001]           # model write: tracked (re-uploaded before the next call)
+  assert m._version == v + 1 and float(np.asarray(m.geom_friction).reshape(-1, 3)[floor.element_id, 0]) == 0.9
+  phys.step()
