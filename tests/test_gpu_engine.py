@@ -314,3 +314,22 @@ def test_per_environment_geoms(oracle_mod):
       o.control_step(1)
     assert abs(z[e] - o.qpos[2]) < 1e-9, (e, z[e], o.qpos[2])
   assert z[1] - z[0] > 0.29 and z[0] - z[2] > 0.09          # resting on platforms of different heights
+
+
+@pytest.mark.parametrize('feature,xml', [
+    ('condim 4 (torsional friction)', '<mujoco><worldbody><geom type="plane" size="1 1 .1"/><body pos="0 0 .2"><freejoint/><geom size=".1" condim="4"/></body></worldbody></mujoco>'),
+    ('condim 6 (rolling friction)', '<mujoco><worldbody><geom type="plane" size="1 1 .1"/><body pos="0 0 .2"><freejoint/><geom size=".1" condim="6"/></body></worldbody></mujoco>'),
+    ('CG solver', '<mujoco><option solver="CG"/><worldbody><geom type="plane" size="1 1 .1"/><body pos="0 0 .2"><freejoint/><geom size=".1"/></body></worldbody></mujoco>'),
+    ('elliptic cones', '<mujoco><option cone="elliptic"/><worldbody><geom type="plane" size="1 1 .1"/><body pos="0 0 .2"><freejoint/><geom size=".1"/></body></worldbody></mujoco>'),
+])
+def test_unsupported_features_are_refused_not_approximated(feature, xml):
+  """wrapper/core_test.py:426-462 pins contact torques for condim 4 / 6: this engine has condim 1 / 3 only, and a model
+  that asks for more must be refused at model creation (error -3), never run with silently different physics."""
+  from dm_control_b200 import lib, mjcf_compile
+  from dm_control_b200.physics import BatchedPhysics
+  try:
+    model = mjcf_compile.compile_xml(xml)
+  except (NotImplementedError, ValueError):
+    return                                  # refused by the compiler already
+  with pytest.raises(lib.EngineError, match='-3'):
+    BatchedPhysics(model, batch=2)
