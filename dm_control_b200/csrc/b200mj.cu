@@ -2992,7 +2992,10 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   // environment lists. Slot k of a group's counters belongs to physics step k of a call; the trailing mj_step1 writes
   // slot 0 for the next call (B200MJ_STEP_REUSE_POS). The slot sequence is the same in every call, so a captured
   // CUDA graph of this function stays valid.
-  static int compact_on = -1, acc_warps = 4, acc_sync = 0;
+  // Measured on the humanoid workload, kernel group per control step (profiles/r2_ab_compact*.txt): one-warp CTAs
+  // 5.56 ms; compacted 2 / 3 / 4 / 8 warps per CTA 5.34 / 5.27 / 5.12 / 5.35 ms; 4 warps phase-aligned 4.79 ms
+  // (8 aligned: 5.26). The compile-time-size kernels are built for at most 4 warps per CTA (__launch_bounds__(128, 4)).
+  static int compact_on = -1, acc_warps = 4, acc_sync = 1;
   if (compact_on < 0) {
     const char* e = getenv("B200MJ_COMPACT"); compact_on = e ? atoi(e) : 1;
     if (const char* a = getenv("B200MJ_ACC_SYNC")) acc_sync = atoi(a);
@@ -3037,7 +3040,12 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         const size_t ws = (last ? M->smem_accs_b[b] : M->smem_acc_b[b]);
         // warps per CTA of a compacted launch: as many as fit 227 KB, at most acc_warps
         int wpc = 1;
-        if (compact) { wpc = (int)((227 * 1024) / ws); if (wpc > acc_warps) wpc = acc_warps; if (wpc < 1) wpc = 1; }
+        if (compact) {
+          static int per_bucket[4] = {0, 0, 0, 0}, parsed = 0;     // B200MJ_ACC_WARPS_B="4,3,2,2": warps per CTA by bucket (experiments)
+          if (!parsed) { parsed = 1; if (const char* e = getenv("B200MJ_ACC_WARPS_B")) sscanf(e, "%d,%d,%d,%d", &per_bucket[0], &per_bucket[1], &per_bucket[2], &per_bucket[3]); }
+          const int want = per_bucket[b] > 0 ? per_bucket[b] : acc_warps;
+          wpc = (int)((227 * 1024) / ws); if (wpc > want) wpc = want; if (M->tn_nv && wpc > 4) wpc = 4; if (wpc < 1) wpc = 1;
+        }
         const int grid = compact ? (cnt + wpc - 1) / wpc : cnt;
         const int* bc = compact ? gcount + s * 4 + b : nullptr;
         const int* bl = compact ? glist + (size_t)b * M->hand_batch : nullptr;
