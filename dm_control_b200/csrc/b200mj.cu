@@ -99,7 +99,7 @@ struct b200mj_model {
   double* d_hand; int hand_batch;
   int* d_bcount; int* d_blist;     // compaction: counters [3 groups][BCOUNT_SLOTS][4], lists [3 groups][4 buckets][hand_batch]
   // the trailing mj_step1 of the last split-path step left a complete handover for this (io, batch): see B200MJ_STEP_REUSE_POS
-  const double* reuse_qpos; int reuse_batch; int reuse_flags; int reuse_ok;
+  const double* reuse_qpos; int reuse_batch; int reuse_flags; int reuse_ok; int reuse_has_dump;
   int epb_pos, epb_acc;
   size_t smem_pos, smem_acc;
   int* d_idata;
@@ -2976,8 +2976,11 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   const bool all_split = split_enabled() >= 2;
   const int nsplit = all_split ? nstep : nstep - 1;
   // B200MJ_STEP_REUSE_POS: the previous call's trailing mj_step1 wrote this state's handover rows already
+  // (the trailing mj_step1 dumps what the acceleration-stage sensors need only when the call had one physics step: a
+  // call whose first step is also its last must then find that dump, or recompute the position stage)
   const bool reuse = (flags & B200MJ_STEP_REUSE_POS) && all_split && nstep >= 1 && M->reuse_ok && M->reuse_qpos == io->qpos &&
-                     M->reuse_batch == batch && M->reuse_flags == (flags & ~B200MJ_STEP_REUSE_POS);
+                     M->reuse_batch == batch && M->reuse_flags == (flags & ~B200MJ_STEP_REUSE_POS) &&
+                     (nstep > 1 || !want_sens || M->reuse_has_dump);
   M->reuse_ok = 0;
   // Environment groups (B200MJ_GROUPS, default 2 for batches >= 2048): the launch sequence of each group is
   // independent of the others, so groups run on their own streams and one group's position kernel fills the tail of
@@ -3067,14 +3070,14 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     if (all_split) {
       const Compact cp = compact_for(0);      // the next call's first acceleration launches read slot 0
       B200MJ_LAUNCH(b200mj_posfinal_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                                    e1, 0, flags, want_sens, e0, cp);
+                                                                                    e1, 0, flags, want_sens && nstep == 1, e0, cp);
       g_launches++;
     }
     if (g > 0) { cudaEventRecord(M->ev_join[g], sm); cudaStreamWaitEvent(st, M->ev_join[g], 0); }
   }
   if (cudaGetLastError() != cudaSuccess) return -5;
   if (all_split) {
-    if (flags & B200MJ_STEP_FULL_FINAL) { M->reuse_ok = 1; M->reuse_qpos = io->qpos; M->reuse_batch = batch; M->reuse_flags = flags & ~B200MJ_STEP_REUSE_POS; }
+    if (flags & B200MJ_STEP_FULL_FINAL) { M->reuse_ok = 1; M->reuse_qpos = io->qpos; M->reuse_batch = batch; M->reuse_flags = flags & ~B200MJ_STEP_REUSE_POS; M->reuse_has_dump = want_sens && nstep == 1; }
     return 0;
   }
   return launch(M, io, batch, 1, flags, MODE_STEP, 0, stream);

@@ -479,4 +479,8 @@ def test_reuse_of_trailing_position_stage_is_bit_identical(name, B, ncalls):
     for u, v in zip(x, y):
       np.testing.assert_array_equal(u, v)
   groups = 2 if B >= 2048 else 1
-  assert (n1 - n0) - (n2 - n1) == (ncalls - 1) * groups        # one position launch saved per call and group after the first
+  # one position launch saved per call and group after the first — except for a one-step call that follows a longer one:
+  # the trailing mj_step1 dumps what the acceleration-stage sensors need only after one-step calls, so that call
+  # recomputes its position stage
+  saved = sum(1 for t in range(1, ncalls) if not (ns[t] == 1 and ns[t - 1] > 1 and model.nsensordata > 0))
+  assert (n1 - n0) - (n2 - n1) == saved * groups

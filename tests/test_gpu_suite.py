@@ -122,7 +122,7 @@ def test_bind_prefix_free_access_and_lazy_forward():
   sensor fields, and the dirty contract — a qpos write through a binding makes the next derived read run forward()."""
   from dm_control_b200 import testing_models as tm
   from dm_control_b200.physics import BatchedPhysics
-  phys = BatchedPhysics(tm.load('humanoid'), batch=3)
+  phys = BatchedPhysics(tm.load('humanoid').copy(), batch=3)      # a private copy: the test edits the model
   m = phys.model
   head, hands = phys.bind('body', 'head'), phys.bind('body', ['left_hand', 'right_hand'])
   assert head.element_id == m.name2id('head', 'body') and tuple(hands.xpos.shape) == (3, 2, 3) and tuple(head.xpos.shape) == (3, 3)
