@@ -3045,7 +3045,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         int wpc = 1;
         if (compact) {
           static int per_bucket[4] = {0, 0, 0, 0}, parsed = 0;     // B200MJ_ACC_WARPS_B="4,3,2,2": warps per CTA by bucket (experiments)
-          if (!parsed) { parsed = 1; if (const char* e = getenv("B200MJ_ACC_WARPS_B")) sscanf(e, "%d,%d,%d,%d", &per_bucket[0], &per_bucket[1], &per_bucket[2], &per_bucket[3]); }
+          if (!parsed) { parsed = 1; if (const char* e = getenv("B200MJ_ACC_WARPS_B")) sscanf(e, "%d%*c%d%*c%d%*c%d", &per_bucket[0], &per_bucket[1], &per_bucket[2], &per_bucket[3]); }
           const int want = per_bucket[b] > 0 ? per_bucket[b] : acc_warps;
           wpc = (int)((227 * 1024) / ws); if (wpc > want) wpc = want; if (M->tn_nv && wpc > 4) wpc = 4; if (wpc < 1) wpc = 1;
         }
