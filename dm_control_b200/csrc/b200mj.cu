@@ -33,6 +33,7 @@
 
 #define FULL 0xffffffffu
 #define B200MJ_INTERNAL_ACC_SYNC (1 << 16)     // host -> acceleration kernels only (not part of the ABI flags)
+#define B200MJ_INTERNAL_ACC_SYNC_COARSE (1 << 17)   // barriers at the stage boundaries only, Newton trips run free
 #define FOR_LANES(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
 
 // ------------------------------------------------------------------------------------------------
@@ -2432,7 +2433,7 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   // row-count bucket: this launch's workspace holds up to rows_le constraint rows; environments with more (or
   // fewer than rows_gt+1) rows are served by the launch with the matching workspace and leave at once here
   if (!sync && (nefc <= rows_gt || nefc > rows_le)) return;
-  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, sync ? 3 : 0);
+  Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, sync ? ((flags & B200MJ_INTERNAL_ACC_SYNC_COARSE) ? 1 : 3) : 0);
   c.set_env(env, io);
   const int nv = NVT > 0 ? NVT : m.nv, ld = NVT > 0 ? (NVT | 1) : m.ldv;
   // ---- load state + handover ----
@@ -2998,7 +2999,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   // Measured on the humanoid workload, kernel group per control step (profiles/r2_ab_compact*.txt): one-warp CTAs
   // 5.56 ms; compacted 2 / 3 / 4 / 8 warps per CTA 5.34 / 5.27 / 5.12 / 5.35 ms; 4 warps phase-aligned 4.79 ms
   // (8 aligned: 5.26). The compile-time-size kernels are built for at most 4 warps per CTA (__launch_bounds__(128, 4)).
-  static int compact_on = -1, acc_warps = 4, acc_sync = 1;
+  static int compact_on = -1, acc_warps = 4, acc_sync = 2;      // B200MJ_ACC_SYNC: 0 off, 1 stage boundaries only, 2 + every Newton trip
   if (compact_on < 0) {
     const char* e = getenv("B200MJ_COMPACT"); compact_on = e ? atoi(e) : 1;
     if (const char* a = getenv("B200MJ_ACC_SYNC")) acc_sync = atoi(a);
@@ -3053,7 +3054,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         const int* bc = compact ? gcount + s * 4 + b : nullptr;
         const int* bl = compact ? glist + (size_t)b * M->hand_batch : nullptr;
         const Lay& la = last ? M->lay_accs_b[b] : M->lay_acc_b[b];
-        const int aflags = flags | ((compact && acc_sync && wpc > 1) ? B200MJ_INTERNAL_ACC_SYNC : 0);
+        const int aflags = flags | ((compact && acc_sync && wpc > 1) ? (B200MJ_INTERNAL_ACC_SYNC | (acc_sync == 1 ? B200MJ_INTERNAL_ACC_SYNC_COARSE : 0)) : 0);
         if (M->tn_nv) {
           acc_kernel_fn fn = tn_kernel(M->tn_nv, last);
           B200MJ_LAUNCH(fn, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
