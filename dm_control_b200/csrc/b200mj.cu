@@ -84,7 +84,10 @@ struct Hand2 { int xpos, xquat, xmat, xipos, scom, cinert, cdof, cdofdot, cvel, 
 // Row-bucket compaction (split path): the position kernel appends every environment to the list of its row-count
 // bucket (count[b] = entries so far, list[b * cap ..]); the acceleration launch of a bucket then runs dense CTAs of
 // several warps over that list instead of one single-warp CTA per environment of which most exit at once.
-struct Compact { int* count; int* list; int cap; int nbucket; int rows_cap[4]; };
+// Two classes per bucket by the Newton iteration count of the environment's previous physics step (a CTA lives as long
+// as its slowest warp: like with like): class 0 fills a bucket's list from the front (count[b]), class 1 from the back
+// (count[4 + b]).
+struct Compact { int* count; int* list; int cap; int nbucket; int rows_cap[4]; const int* prev_niter; int niter_split; };
 
 struct b200mj_model {
   DevModel dm;
@@ -98,7 +101,8 @@ struct b200mj_model {
   // environment groups x row buckets run on their own streams (independent work: hides each launch's tail)
   cudaStream_t gmain[3], gaux[3][4]; cudaEvent_t ev_fork, ev_join[3], ev_pos[3], ev_acc[3][4]; int streams_ok;
   double* d_hand; int hand_batch;
-  int* d_bcount; int* d_blist;     // compaction: counters [3 groups][BCOUNT_SLOTS][4], lists [3 groups][4 buckets][hand_batch]
+  int* d_bcount; int* d_blist;     // compaction: counters [3 groups][BCOUNT_SLOTS][8], lists [3 groups][4 buckets][hand_batch]
+  int* d_niter;                    // Newton iterations of every environment's previous physics step [hand_batch]
   // the trailing mj_step1 of the last split-path step left a complete handover for this (io, batch): see B200MJ_STEP_REUSE_POS
   const double* reuse_qpos; int reuse_batch; int reuse_flags; int reuse_ok; int reuse_has_dump;
   int epb_pos, epb_acc;
@@ -2362,18 +2366,22 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   if (cp.count != nullptr && (!FINAL || with_constraints)) {
     // bucket lists for the acceleration launches: one shared-memory ticket per environment, one global atomic per CTA
     // and bucket (every warp of the CTA gets here: the shadows of environments past the batch end take no ticket)
-    int* cta = reinterpret_cast<int*>(smem + (size_t)(blockDim.x >> 5) * L.total);      // 8 ints behind the workspaces
-    if (threadIdx.x < 8) cta[threadIdx.x] = 0;
+    int* cta = reinterpret_cast<int*>(smem + (size_t)(blockDim.x >> 5) * L.total);      // 16 ints behind the workspaces
+    if (threadIdx.x < 16) cta[threadIdx.x] = 0;
     __syncthreads();
     int b = 0, my = 0;
     if (live && lane == 0) {
       while (b + 1 < cp.nbucket && nefc > cp.rows_cap[b]) b++;
+      if (cp.prev_niter && cp.prev_niter[env] > cp.niter_split) b += 4;      // slow class: from the back of the list
       my = atomicAdd(&cta[b], 1);
     }
     __syncthreads();
-    if (threadIdx.x < cp.nbucket) cta[4 + threadIdx.x] = cta[threadIdx.x] ? atomicAdd(&cp.count[threadIdx.x], cta[threadIdx.x]) : 0;
+    if (threadIdx.x < 8) cta[8 + threadIdx.x] = cta[threadIdx.x] ? atomicAdd(&cp.count[threadIdx.x], cta[threadIdx.x]) : 0;
     __syncthreads();
-    if (live && lane == 0) cp.list[(size_t)b * cp.cap + cta[4 + b] + my] = env;
+    if (live && lane == 0) {
+      const int at = cta[8 + b] + my;
+      cp.list[(size_t)(b & 3) * cp.cap + (b < 4 ? at : cp.cap - 1 - at)] = env;
+    }
   }
   if (live && io.warning && lane == 0) {
     int* w = io.warning + e * BMJ_NWARNING;
@@ -2404,7 +2412,8 @@ b200mj_posfinal_kernel(const __grid_constant__ DevModel m, const __grid_constant
 template <bool LAST, int NVT>
 __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L, const Hand& H, const Hand2& H2, const b200mj_io& io,
                                                 const double* hand, const double* hand2, int batch, int extra_disable, int first_pass,
-                                                int rows_gt, int rows_le, int flags, int env0, const int* bucket_count, const int* bucket_list) {
+                                                int rows_gt, int rows_le, int flags, int env0, const int* bucket_count, const int* bucket_list,
+                                                int list_cap, int* niter_out) {
   extern __shared__ double smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env;
@@ -2414,14 +2423,19 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   // 32 KB L1.5 I-cache. Warps past the end of the list then shadow its last entry (same control flow, no stores).
   const bool sync = (flags & B200MJ_INTERNAL_ACC_SYNC) != 0 && bucket_list != nullptr && blockDim.x > 32;
   if (bucket_list != nullptr) {
-    // compacted launch: warp k of the grid takes entry k of this bucket's list (written by the position kernel)
-    int k = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int n = *bucket_count;
+    // compacted launch: the first CTAs walk the bucket's fast class from the front of its list, the following ones the
+    // slow class from the back (bucket_count[0], bucket_count[4]: entries of either class; list_cap = list length)
+    const int W = blockDim.x >> 5;
+    const int n0 = bucket_count[0], n1 = bucket_count[4], c0 = (n0 + W - 1) / W;
+    int cta_id = blockIdx.x, n = n0;
+    const bool slow = cta_id >= c0;
+    if (slow) { cta_id -= c0; n = n1; }
+    int k = cta_id * W + warp;
     if (k >= n) {
-      if (!sync || blockIdx.x * (blockDim.x >> 5) >= n) return;
+      if (!sync || cta_id * W >= n) return;
       live = false; k = n - 1;
     }
-    env = bucket_list[k];
+    env = bucket_list[slow ? list_cap - 1 - k : k];
   } else {
     env = env0 + blockIdx.x * (blockDim.x >> 5) + warp;
     if (env >= batch) return;
@@ -2465,6 +2479,7 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   if (check_bad(c, W(qacc), nv)) { w_badqacc = 1; reset_state(c, &time); }
   else euler_step<NVT>(c, &time);
   if (!live) return;      // shadows: no stores (the sensor epilogue below has no barriers)
+  if (niter_out && lane == 0) niter_out[env] = niter;      // the next physics step's CTA class
   // ---- store state ----
   FOR_LANES(i, m.nq) io.qpos[e * m.nq + i] = W(qpos)[i];
   FOR_LANES(i, nv) { io.qvel[e * nv + i] = W(qvel)[i]; if (io.qacc_warmstart) io.qacc_warmstart[e * nv + i] = W(qaccws)[i]; }
@@ -2499,15 +2514,15 @@ extern "C" __global__ void __launch_bounds__(256)
 b200mj_acc_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                   const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
                   int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0, const int* bucket_count,
-                  const int* bucket_list) {
-  acc_kernel_body<false, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list);
+                  const int* bucket_list, int list_cap, int* niter_out) {
+  acc_kernel_body<false, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list, list_cap, niter_out);
 }
 extern "C" __global__ void __launch_bounds__(256)
 b200mj_acclast_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                       const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
                   int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0, const int* bucket_count,
-                  const int* bucket_list) {
-  acc_kernel_body<true, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list);
+                  const int* bucket_list, int list_cap, int* niter_out) {
+  acc_kernel_body<true, 0>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list, list_cap, niter_out);
 }
 
 // Acceleration kernels with nv fixed at compile time (register-resident algebra, tn_* above). One instantiation per
@@ -2521,8 +2536,8 @@ __global__ void __launch_bounds__(128, 4)
 b200mj_acc_tn_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                      const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, const double* hand, const double* hand2,
                      int batch, int extra_disable, int first_pass, int rows_gt, int rows_le, int flags, int env0, const int* bucket_count,
-                     const int* bucket_list) {
-  acc_kernel_body<LAST, NVT>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list);
+                     const int* bucket_list, int list_cap, int* niter_out) {
+  acc_kernel_body<LAST, NVT>(m, L, H, H2, io, hand, hand2, batch, extra_disable, first_pass, rows_gt, rows_le, flags, env0, bucket_count, bucket_list, list_cap, niter_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2531,7 +2546,7 @@ b200mj_acc_tn_kernel(const __grid_constant__ DevModel m, const __grid_constant__
 static int64_t g_launches = 0;
 
 typedef void (*acc_kernel_fn)(const DevModel, const Lay, const Hand, const Hand2, const b200mj_io, const double*, const double*,
-                              int, int, int, int, int, int, int, const int*, const int*);
+                              int, int, int, int, int, int, int, const int*, const int*, int, int*);
 #define BCOUNT_SLOTS 64
 // the compile-time-size acceleration kernel for nv dofs, or nullptr (B200MJ_TN=0 disables them: A/B runs)
 static acc_kernel_fn tn_kernel(int nv, bool last) {
@@ -2847,6 +2862,7 @@ void b200mj_model_destroy(b200mj_model* M) {
   if (M->d_hand2) cudaFree(M->d_hand2);
   if (M->d_bcount) cudaFree(M->d_bcount);
   if (M->d_blist) cudaFree(M->d_blist);
+  if (M->d_niter) cudaFree(M->d_niter);
   if (M->streams_ok) {
     for (int g = 0; g < 3; g++) {
       cudaStreamDestroy(M->gmain[g]); cudaEventDestroy(M->ev_join[g]); cudaEventDestroy(M->ev_pos[g]);
@@ -2964,9 +2980,13 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     if (M->d_bcount) cudaFree(M->d_bcount);
     if (M->d_blist) cudaFree(M->d_blist);
     M->d_bcount = M->d_blist = nullptr;
-    if (cudaMalloc(&M->d_bcount, (size_t)3 * BCOUNT_SLOTS * 4 * sizeof(int)) != cudaSuccess) return -2;
+    if (M->d_niter) cudaFree(M->d_niter);
+    M->d_niter = nullptr;
+    if (cudaMalloc(&M->d_bcount, (size_t)3 * BCOUNT_SLOTS * 8 * sizeof(int)) != cudaSuccess) return -2;
     if (cudaMalloc(&M->d_blist, (size_t)3 * 4 * batch * sizeof(int)) != cudaSuccess) return -2;
-    cudaMemset(M->d_bcount, 0, (size_t)3 * BCOUNT_SLOTS * 4 * sizeof(int));
+    if (cudaMalloc(&M->d_niter, (size_t)batch * sizeof(int)) != cudaSuccess) return -2;
+    cudaMemset(M->d_bcount, 0, (size_t)3 * BCOUNT_SLOTS * 8 * sizeof(int));
+    cudaMemset(M->d_niter, 0, (size_t)batch * sizeof(int));
     M->hand_batch = batch;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -2999,10 +3019,12 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
   // Measured on the humanoid workload, kernel group per control step (profiles/r2_ab_compact*.txt): one-warp CTAs
   // 5.56 ms; compacted 2 / 3 / 4 / 8 warps per CTA 5.34 / 5.27 / 5.12 / 5.35 ms; 4 warps phase-aligned 4.79 ms
   // (8 aligned: 5.26). The compile-time-size kernels are built for at most 4 warps per CTA (__launch_bounds__(128, 4)).
+  static int niter_split = 0;      // B200MJ_NITER_SPLIT: iteration count above which an environment joins its bucket's slow class (0: one class)
   static int compact_on = -1, acc_warps = 4, acc_sync = 2;      // B200MJ_ACC_SYNC: 0 off, 1 stage boundaries only, 2 + every Newton trip
   if (compact_on < 0) {
     const char* e = getenv("B200MJ_COMPACT"); compact_on = e ? atoi(e) : 1;
     if (const char* a = getenv("B200MJ_ACC_SYNC")) acc_sync = atoi(a);
+    if (const char* n = getenv("B200MJ_NITER_SPLIT")) niter_split = atoi(n);
     if (const char* w = getenv("B200MJ_ACC_WARPS")) { int v = atoi(w); if (v >= 1 && v <= 8) acc_warps = v; }
   }
   const bool compact = compact_on && all_split && nstep + 1 <= BCOUNT_SLOTS && M->d_bcount && M->d_blist;
@@ -3012,14 +3034,15 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     cudaStream_t sm = (g == 0) ? st : M->gmain[g];
     if (g > 0) cudaStreamWaitEvent(sm, M->ev_fork, 0);
     const int gp = (cnt + M->epb_pos - 1) / M->epb_pos;
-    int* gcount = M->d_bcount ? M->d_bcount + (size_t)g * BCOUNT_SLOTS * 4 : nullptr;
+    int* gcount = M->d_bcount ? M->d_bcount + (size_t)g * BCOUNT_SLOTS * 8 : nullptr;
     int* glist = M->d_blist ? M->d_blist + (size_t)g * 4 * M->hand_batch : nullptr;
     auto compact_for = [&](int slot) {
       Compact cp; memset(&cp, 0, sizeof(cp));
       if (compact) {
-        cp.count = gcount + slot * 4; cp.list = glist; cp.cap = M->hand_batch; cp.nbucket = M->nbucket;
+        cp.count = gcount + slot * 8; cp.list = glist; cp.cap = M->hand_batch; cp.nbucket = M->nbucket;
         for (int b = 0; b < M->nbucket; b++) cp.rows_cap[b] = M->rows_cap[b];
-        cudaMemsetAsync(cp.count, 0, 4 * sizeof(int), sm);
+        cp.prev_niter = niter_split > 0 ? M->d_niter : nullptr; cp.niter_split = niter_split;
+        cudaMemsetAsync(cp.count, 0, 8 * sizeof(int), sm);
       }
       return cp;
     };
@@ -3050,19 +3073,19 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
           const int want = per_bucket[b] > 0 ? per_bucket[b] : acc_warps;
           wpc = (int)((227 * 1024) / ws); if (wpc > want) wpc = want; if (M->tn_nv && wpc > 4) wpc = 4; if (wpc < 1) wpc = 1;
         }
-        const int grid = compact ? (cnt + wpc - 1) / wpc : cnt;
-        const int* bc = compact ? gcount + s * 4 + b : nullptr;
+        const int grid = compact ? (cnt + wpc - 1) / wpc + (niter_split > 0 ? 1 : 0) : cnt;      // two classes: one more partial CTA
+        const int* bc = compact ? gcount + s * 8 + b : nullptr;
         const int* bl = compact ? glist + (size_t)b * M->hand_batch : nullptr;
         const Lay& la = last ? M->lay_accs_b[b] : M->lay_acc_b[b];
         const int aflags = flags | ((compact && acc_sync && wpc > 1) ? (B200MJ_INTERNAL_ACC_SYNC | (acc_sync == 1 ? B200MJ_INTERNAL_ACC_SYNC_COARSE : 0)) : 0);
         if (M->tn_nv) {
           acc_kernel_fn fn = tn_kernel(M->tn_nv, last);
           B200MJ_LAUNCH(fn, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                        e1, 0, s == 0, gt, le, aflags, e0, bc, bl);
+                        e1, 0, s == 0, gt, le, aflags, e0, bc, bl, M->hand_batch, (compact && niter_split > 0) ? M->d_niter : nullptr);
         } else if (last) B200MJ_LAUNCH(b200mj_acclast_kernel, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                            e1, 0, s == 0, gt, le, aflags, e0, bc, bl);
+                                                                            e1, 0, s == 0, gt, le, aflags, e0, bc, bl, M->hand_batch, (compact && niter_split > 0) ? M->d_niter : nullptr);
         else B200MJ_LAUNCH(b200mj_acc_kernel, grid, 32 * wpc, ws * wpc + acc_pad, sb, M->dm, la, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
-                                                                  e1, 0, s == 0, gt, le, aflags, e0, bc, bl);
+                                                                  e1, 0, s == 0, gt, le, aflags, e0, bc, bl, M->hand_batch, (compact && niter_split > 0) ? M->d_niter : nullptr);
         if (b > 0) cudaEventRecord(M->ev_acc[g][b], sb);
         g_launches++;
       }

@@ -52,6 +52,8 @@ class _Opt:
     object.__setattr__(self, '_m', model)
 
   def __getattr__(self, name):
+    if name.startswith('_'):
+      raise AttributeError(name)      # (unpickling probes dunder names before `_m` exists)
     m = self._m
     if name == 'gravity':
       return m.fields['opt_real'][OPTR['GRAVITY_X']:OPTR['GRAVITY_X'] + 3]

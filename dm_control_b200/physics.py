@@ -204,6 +204,30 @@ class BatchedPhysics:
       f |= _lib.STEP_REUSE_POS
     return f
 
+  # ---- pickling (reference: engine.py:287-304 copy / 370-378 __getstate__: model + data travel, the handle is rebuilt) ----
+  def __getstate__(self):
+    state = {n: getattr(self.data, n).cpu() for n in ('qpos', 'qvel', 'act', 'qacc_warmstart', 'time', 'ctrl')}
+    if self._applied_on:
+      state['qfrc_applied'] = self.data.qfrc_applied.cpu(); state['xfrc_applied'] = self.data.xfrc_applied.cpu()
+    var = getattr(self, '_var_geom_ids', None)
+    if var is not None:
+      state['var_geom_pos'] = self.data.var_geom_pos.cpu(); state['var_geom_size'] = self.data.var_geom_size.cpu()
+    return dict(model=self.model, batch=self.batch, device=str(self.device), sensors=self._sensors, full_final=self._full_final,
+                legacy_step=self.legacy_step, check_errors=self.check_errors, applied=self._applied_on, var_geom_ids=var, state=state,
+                outputs=[n for n, _ in list(self._FIELDS) + list(self._INT_FIELDS) if hasattr(self.data, n)])
+
+  def __setstate__(self, st):
+    self.__init__(st['model'], batch=st['batch'], device=st['device'], outputs=st['outputs'], sensors=st['sensors'],
+                  full_final=st['full_final'])
+    self.legacy_step, self.check_errors = st['legacy_step'], st['check_errors']
+    if st['applied']:
+      self.enable_applied_forces(True)
+    if st['var_geom_ids'] is not None:
+      self.set_variable_geoms(st['var_geom_ids'])
+    for n, t in st['state'].items():
+      getattr(self.data, n).copy_(t.to(self.device))
+    self.forward()
+
   def _sync_model(self):
     if self.model._version != self._model_version:
       self._upload_model()

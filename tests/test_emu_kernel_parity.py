@@ -197,6 +197,10 @@ def test_launch_knobs_do_not_change_results():
   # the default path: acceleration kernels with nv fixed at compile time (register-resident algebra)
   ref = digest()
   for knobs in (dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_BUCKETS='6,12,24'), dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'),
+                # acceleration launches: one-warp CTAs, compacted lists with 2 / 4 warps, with / without phase barriers, two
+                # iteration-count classes per bucket: scheduling only
+                dict(B200MJ_COMPACT='0'), dict(B200MJ_ACC_WARPS='2'), dict(B200MJ_ACC_SYNC='0'), dict(B200MJ_ACC_SYNC='1'),
+                dict(B200MJ_NITER_SPLIT='3'), dict(B200MJ_NITER_SPLIT='2', B200MJ_ACC_WARPS='3'),
                 # the emulator running the lanes of every block in descending instead of ascending order: a cross-lane
                 # dependency through shared memory that no collective or barrier separates would change the result
                 dict(B200MJ_EMU_ORDER='reverse')):

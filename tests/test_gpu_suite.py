@@ -149,3 +149,20 @@ def test_bind_prefix_free_access_and_lazy_forward():
   floor.friction = [0.9, 0.005, 0.0001]           # model write: tracked (re-uploaded before the next call)
   assert m._version == v + 1 and float(np.asarray(m.geom_friction).reshape(-1, 3)[floor.element_id, 0]) == 0.9
   phys.step()
+
+
+def test_physics_pickles_with_model_and_state():
+  """engine_test.py:574-589 (`pickle.loads(pickle.dumps(physics))`): model and state travel, the copy steps in lock-step."""
+  import pickle
+  from dm_control_b200 import testing_models as tm
+  from dm_control_b200.physics import BatchedPhysics
+  a = BatchedPhysics(tm.load('cheetah'), batch=5, outputs=('sensordata', 'xpos'))
+  q0, v0 = tm.initial_states(a.model, 'cheetah', 5, 4)
+  a.data.qpos.copy_(torch.as_tensor(q0)); a.data.qvel.copy_(torch.as_tensor(v0)); a.forward()
+  a.set_control(torch.full((6,), 0.3, dtype=torch.float64)); a.step(7)
+  b = pickle.loads(pickle.dumps(a))
+  assert b.batch == 5 and torch.equal(a.get_state(), b.get_state()) and torch.equal(a.data.qacc_warmstart, b.data.qacc_warmstart)
+  assert torch.equal(a.data.xpos, b.data.xpos) and not hasattr(b.data, 'xmat')
+  for p in (a, b):
+    p.step(5)
+  assert torch.equal(a.get_state(), b.get_state()) and torch.equal(a.data.sensordata, b.data.sensordata)
