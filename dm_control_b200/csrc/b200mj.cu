@@ -17,8 +17,10 @@
 // THIS source for logic errors without a GPU. Test infrastructure only: the product library is built by nvcc without
 // this macro, and nothing in dm_control_b200/ ever loads the emulation build.
 #include "cuda_emu.h"
+#define B200MJ_DYN_SMEM        // cuda_emu.h defines `smem` at namespace scope (a block-scope extern of a thread_local trips g++ in templates)
 #else
 #include <cuda_runtime.h>
+#define B200MJ_DYN_SMEM extern __shared__ double smem[];
 #define B200MJ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 #include <math.h>
@@ -87,7 +89,8 @@ struct Hand2 { int xpos, xquat, xmat, xipos, scom, cinert, cdof, cdofdot, cvel, 
 // Two classes per bucket by the Newton iteration count of the environment's previous physics step (a CTA lives as long
 // as its slowest warp: like with like): class 0 fills a bucket's list from the front (count[b]), class 1 from the back
 // (count[4 + b]).
-struct Compact { int* count; int* list; int cap; int nbucket; int rows_cap[4]; const int* prev_niter; int niter_split; };
+struct Compact { int* count; int* list; int cap; int nbucket; int rows_cap[4]; const int* prev_niter; int niter_split; int shadow_row; };
+#define SHADOW_ROWS 24   // private handover rows for the shadow warps of a launch's last CTA: [3 groups][8 warps]
 
 struct b200mj_model {
   DevModel dm;
@@ -101,6 +104,7 @@ struct b200mj_model {
   // environment groups x row buckets run on their own streams (independent work: hides each launch's tail)
   cudaStream_t gmain[3], gaux[3][4]; cudaEvent_t ev_fork, ev_join[3], ev_pos[3], ev_acc[3][4]; int streams_ok;
   double* d_hand; int hand_batch;
+  int convex_pairs;                // some candidate pair needs cvx_capsule_box / cvx_pair (else: primitive-only position kernels)
   int* d_bcount; int* d_blist;     // compaction: counters [3 groups][BCOUNT_SLOTS][8], lists [3 groups][4 buckets][hand_batch]
   int* d_niter;                    // Newton iterations of every environment's previous physics step [hand_batch]
   // the trailing mj_step1 of the last split-path step left a complete handover for this (io, batch): see B200MJ_STEP_REUSE_POS
@@ -915,6 +919,9 @@ __device__ __forceinline__ void raw_sphere_sphere(double* stg, int& n, double ma
 }
 
 // returns the number of raw contacts staged for this lane's pair (normal points from geom1 to geom2)
+// CVX = false: the model's candidate pairs are all analytic primitive pairs (decided at model_create), so the convex routines
+// (cvx_capsule_box / cvx_pair: ~50 registers and 0.8 KB of stack in the position kernels) are compiled out.
+template <bool CVX>
 __device__ __noinline__ int narrowphase(double* stg, int t1, int t2, double margin, const double* p1, const double* m1, const double* s1,
                                         const double* p2, const double* m2, const double* s2) {
   int n = 0;
@@ -1034,21 +1041,23 @@ __device__ __noinline__ int narrowphase(double* stg, int t1, int t2, double marg
       return n;
     }
   }
-  if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_BOX) {
-    double out[14];
-    const int nc = cvx_capsule_box(p1, m1, s1, p2, m2, s2, margin, out);
-    if (nc > 0) stage_contact(stg, n, out[0], out + 1, out + 4);
-    if (nc > 1) stage_contact(stg, n, out[7], out + 8, out + 11);
-    return n;
-  }
-  if (!(t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE)) {
-    // every remaining pair of convex primitives (an ellipsoid, a cylinder or two boxes involved): MPR, one contact
-    if (t1 >= BMJ_GEOM_SPHERE && t2 <= BMJ_GEOM_BOX) {
-      double dist, pos[3], nrm[3];
-      if (cvx_pair(t1, p1, m1, s1, t2, p2, m2, s2, margin, &dist, pos, nrm)) stage_contact(stg, n, dist, pos, nrm);
+  if constexpr (CVX) {
+    if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_BOX) {
+      double out[14];
+      const int nc = cvx_capsule_box(p1, m1, s1, p2, m2, s2, margin, out);
+      if (nc > 0) stage_contact(stg, n, out[0], out + 1, out + 4);
+      if (nc > 1) stage_contact(stg, n, out[7], out + 8, out + 11);
+      return n;
     }
-    return n;
-  }
+    if (!(t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE)) {
+      // every remaining pair of convex primitives (an ellipsoid, a cylinder or two boxes involved): MPR, one contact
+      if (t1 >= BMJ_GEOM_SPHERE && t2 <= BMJ_GEOM_BOX) {
+        double dist, pos[3], nrm[3];
+        if (cvx_pair(t1, p1, m1, s1, t2, p2, m2, s2, margin, &dist, pos, nrm)) stage_contact(stg, n, dist, pos, nrm);
+      }
+      return n;
+    }
+  } else if (!(t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE)) return 0;   // unreachable: see pair_needs_convex()
   if (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE) {
     double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
     double dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
@@ -1116,6 +1125,7 @@ __device__ __forceinline__ void make_frame(double* frame, const double* normal, 
 #define CON_STRIDE 16
 __device__ __forceinline__ int* con_ints(double* rec) { return reinterpret_cast<int*>(rec + 14); }
 
+template <bool CVX>
 __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
   const DevModel& m = c.m; int lane = c.lane;
   int ncon = 0;
@@ -1141,7 +1151,7 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
         double bound = rb1 + rb2 + margin;
         keep = dot3(dif, dif) <= bound * bound;
       }
-      if (keep) n = narrowphase(stg, t1, t2, margin, p1, m1, s1, p2, m2, s2);
+      if (keep) n = narrowphase<CVX>(stg, t1, t2, margin, p1, m1, s1, p2, m2, s2);
     }
     int total;
     int off = warp_excl_scan(n, lane, &total);
@@ -2158,10 +2168,11 @@ enum { MODE_STEP = 0, MODE_FORWARD = 1 };
 // once into the single pass loop below (model / layout operands then come straight from the constant bank).
 //   pass kinds: [posvel + acc + integrate] x nstep  (RK4: 4 passes per step), then for the reference's legacy
 //   ordering one trailing [posvel] pass (= mj_step1 on the new state); MODE_FORWARD = one [posvel + acc] pass.
-extern "C" __global__ void __launch_bounds__(256)
-b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ b200mj_io io,
+// CVX: as for the position kernels (the primitive-only build shares narrowphase<false> with them, so the two paths stay bit-identical).
+template <bool CVX>
+__device__ __forceinline__ void step_kernel_body(const DevModel& m, const Lay& L, const b200mj_io& io,
                    int batch, int nstep, int flags, int mode, int extra_disable, int sync_level, const uint8_t* env_mask) {
-  extern __shared__ double smem[];
+  B200MJ_DYN_SMEM
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env = blockIdx.x * (blockDim.x >> 5) + warp;
   // warps past the end of the batch shadow the last environment (same control flow => same barrier count)
@@ -2208,7 +2219,7 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
     if (!final_pass || full_final) {
       int wfull = 0, cfull = 0;
       PHASE_SYNC(2);
-      ncon = collision(c, &wfull);
+      ncon = collision<CVX>(c, &wfull);
       PHASE_SYNC(2);
       nefc = make_constraint(c, ncon, &cfull);
       w_contactfull += wfull; w_cnstrfull += cfull;
@@ -2283,6 +2294,16 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
     if (w_badctrl) w[BMJ_WARN_BADCTRL] += w_badctrl;
   }
 }
+extern "C" __global__ void __launch_bounds__(256)
+b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ b200mj_io io,
+                   int batch, int nstep, int flags, int mode, int extra_disable, int sync_level, const uint8_t* env_mask) {
+  step_kernel_body<true>(m, L, io, batch, nstep, flags, mode, extra_disable, sync_level, env_mask);
+}
+extern "C" __global__ void __launch_bounds__(256)
+b200mj_step_prim_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ b200mj_io io,
+                        int batch, int nstep, int flags, int mode, int extra_disable, int sync_level, const uint8_t* env_mask) {
+  step_kernel_body<false>(m, L, io, batch, nstep, flags, mode, extra_disable, sync_level, env_mask);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Split path: the same stage functions in two smaller kernels. A pass is  [b200mj_pos_kernel -> b200mj_acc_kernel];
@@ -2293,11 +2314,11 @@ b200mj_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ L
 // ------------------------------------------------------------------------------------------------
 // FINAL = the trailing mj_step1 of the legacy ordering (subtree velocities, position/velocity sensors, outputs);
 // otherwise the position/velocity half of a physics step, optionally dumping what the acceleration-stage sensors need.
-template <bool FINAL>
+template <bool FINAL, bool CVX>
 __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L, const Hand& H, const Hand2& H2, const b200mj_io& io,
                                                 double* hand, double* hand2, int batch, int extra_disable, int flags, int dump, int env0,
                                                 const Compact& cp) {
-  extern __shared__ double smem[];
+  B200MJ_DYN_SMEM
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env = env0 + blockIdx.x * (blockDim.x >> 5) + warp;      // this launch covers environments [env0, batch)
   // The warps of a CTA are phase-aligned by barriers between the stages (the kernel executes ~84 KB of SASS per
@@ -2309,14 +2330,16 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   Ctx c(m, L, smem + (size_t)warp * L.total, lane, m.disableflags | extra_disable, blockDim.x > 32 ? 1 : 0);
   c.set_env(env, io);
   size_t e = (size_t)env;
-  double* hrow = hand + e * H.total;
+  // A shadow warp gets a handover row of its own: the stages read back what they wrote there (raw-contact staging, Jacobian rows), so
+  // sharing the live environment's row would race; the io arrays are only ever overwritten with identical values.
+  const size_t hr = live ? e : (size_t)(cp.shadow_row + warp);
+  double* hrow = hand + hr * H.total;
   c.pM = hrow + H.M; c.pJ = hrow + H.J; c.pD = hrow + H.efcD; c.pAref = hrow + H.aref; c.pBias = hrow + H.bias;
   c.pPassive = hrow + H.passive; c.pEq = reinterpret_cast<int*>(hrow + H.eqflag);
-  c.stage = c.ws + L.scom;      // the dynamics block [scom .. cfrc] is not written before collision has run
+  c.stage = hrow + H.J;         // raw-contact staging: the row's Jacobian block (L2), written only later by make_constraint
   FOR_LANES(i, m.nq) W(qpos)[i] = io.qpos[e * m.nq + i];
   FOR_LANES(i, m.nv) W(qvel)[i] = io.qvel[e * m.nv + i];
   const bool want_sens = FINAL && (flags & B200MJ_STEP_SENSORS) != 0;
-  if (FINAL && io.sensordata) FOR_LANES(i, m.nsensordata) W(sens)[i] = io.sensordata[e * m.nsensordata + i];
   __syncwarp();
   int w_badqpos = 0, w_badqvel = 0, did_reset = 0;
   if (check_bad(c, W(qpos), m.nq)) { w_badqpos++; did_reset = 1; }
@@ -2333,7 +2356,7 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   int wfull = 0, cfull = 0, ncon = 0, nefc = 0;
   const bool with_constraints = !FINAL || (flags & B200MJ_STEP_FULL_FINAL) != 0;
   PHASE_SYNC(1);
-  if (with_constraints) ncon = collision(c, &wfull);   // before com_pos: staging lives in the block com_pos starts to fill
+  if (with_constraints) ncon = collision<CVX>(c, &wfull);   // before com_pos: staging lives in the block com_pos starts to fill
   PHASE_SYNC(1);
   com_pos(c);
   crb_and_factor(c);
@@ -2343,6 +2366,8 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
   fwd_velocity(c);
   PHASE_SYNC(1);
   if (FINAL) {
+    // (the sensor block shares storage with cacc / cfrc, which fwd_velocity has finished with; the acceleration-stage values of the last physics step are kept)
+    if (io.sensordata) FOR_LANES(i, m.nsensordata) W(sens)[i] = io.sensordata[e * m.nsensordata + i];
     subtree_vel(c);
     if (want_sens) sensors(c, 3, ncon);
     write_outputs(c, io, env, ncon, nefc, 0, true, false, want_sens);
@@ -2354,7 +2379,7 @@ __device__ __forceinline__ void pos_kernel_body(const DevModel& m, const Lay& L,
     copy_row(hrow + H.tenJ, W(tenJ), m.ntendon * m.ldv, lane);
     if (lane == 0) { int* cnt = reinterpret_cast<int*>(hrow + H.counts); cnt[0] = ncon; cnt[1] = nefc; }
     if (dump) {
-      double* d2 = hand2 + e * H2.total;
+      double* d2 = hand2 + hr * H2.total;
 #define DUMP(dst, src, n) copy_row(d2 + H2.dst, W(src), (n), lane);
       DUMP(xpos, xpos, 3 * m.nbody) DUMP(xquat, xquat, 4 * m.nbody) DUMP(xmat, xmat, 9 * m.nbody) DUMP(xipos, xipos, 3 * m.nbody)
       DUMP(scom, scom, 3 * m.nbody) DUMP(cinert, cinert, 10 * m.nbody) DUMP(cdof, cdof, 6 * m.nv) DUMP(cdofdot, cdofdot, 6 * m.nv)
@@ -2399,13 +2424,27 @@ extern "C" __global__ void __launch_bounds__(160, 2)
 b200mj_pos_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                   const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
                   int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
-  pos_kernel_body<false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
+  pos_kernel_body<false, true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
 }
 extern "C" __global__ void __launch_bounds__(160, 2)
 b200mj_posfinal_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
                        const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
                        int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
-  pos_kernel_body<true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
+  pos_kernel_body<true, true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
+}
+
+// the same for models whose candidate pairs are all analytic primitive pairs (121 registers, no stack spills): three CTAs per SM
+extern "C" __global__ void __launch_bounds__(160, 3)
+b200mj_pos_prim_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
+                  const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
+                  int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
+  pos_kernel_body<false, false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
+}
+extern "C" __global__ void __launch_bounds__(160, 3)
+b200mj_posfinal_prim_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
+                       const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
+                       int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
+  pos_kernel_body<true, false>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
 }
 
 // LAST = last physics step of a fused step(): acceleration-stage sensors and outputs are produced here
@@ -2414,7 +2453,7 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
                                                 const double* hand, const double* hand2, int batch, int extra_disable, int first_pass,
                                                 int rows_gt, int rows_le, int flags, int env0, const int* bucket_count, const int* bucket_list,
                                                 int list_cap, int* niter_out) {
-  extern __shared__ double smem[];
+  B200MJ_DYN_SMEM
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env;
   bool live = true;
@@ -2603,16 +2642,36 @@ static void build_layout(b200mj_model* M) {
   {
     Lay& P = M->lay_pos; memset(&P, 0, sizeof(P));
     o = 0;
+    // Lifetimes (pos_kernel_body): kinematics -> collision -> com_pos -> crb_and_factor -> make_constraint -> fwd_velocity [-> subtree_vel,
+    // sensors]. Storage shared along that line, so that three 5-warp CTAs fit one SM (humanoid: 14.3 KB per environment, was 19.2):
+    //   [gxpos gxmat]      dead after collision  ==  crb (crb_and_factor), then cacc, cfrc (fwd_velocity), then slinvel, sens (trailing step1)
+    //   [xanchor xaxis]    dead after com_pos    ==  cdofdot (fwd_velocity)
+    // The narrow phase stages its raw contacts in the (not yet written) Jacobian block of the environment's handover row in L2.
     P.qpos = take(m.nq); P.qvel = take(nv);
     P.xpos = take(3 * nb); P.xquat = take(4 * nb); P.xmat = take(9 * nb); P.xipos = take(3 * nb);
-    P.gxpos = take(3 * m.ngeom); P.gxmat = take(9 * m.ngeom); P.xanchor = take(3 * m.njnt); P.xaxis = take(3 * m.njnt);
-    int blk = o;    // dynamics block: doubles as the narrow-phase staging area before com_pos runs
-    P.scom = take(3 * nb); P.slinvel = take(3 * nb); P.cinert = take(10 * nb); P.cdof = take(6 * nv); P.cdofdot = take(6 * nv);
-    P.cvel = take(6 * nb); P.crb = take(10 * nb); P.cacc = take(6 * nb); P.cfrc = take(6 * nb);
-    if (m.npair > 0 && o - blk < STAGE_DOUBLES) take(STAGE_DOUBLES - (o - blk));
+    P.scom = take(3 * nb); P.cinert = take(10 * nb); P.cdof = take(6 * nv); P.cvel = take(6 * nb);
+    {
+      const int a0 = o;
+      P.xanchor = take(3 * m.njnt); P.xaxis = take(3 * m.njnt);
+      const int a1 = o;
+      o = a0; P.cdofdot = take(6 * nv);
+      if (o < a1) o = a1;
+    }
+    {
+      const int b0 = o;
+      P.gxpos = take(3 * m.ngeom); P.gxmat = take(9 * m.ngeom);
+      const int b1 = o;
+      o = b0; P.crb = take(10 * nb);
+      const int b2 = o;
+      o = b0; P.cacc = take(6 * nb); P.cfrc = take(6 * nb);
+      const int b3 = o;
+      o = b0; P.slinvel = take(3 * nb); P.sens = take(m.nsensordata);
+      if (o < b1) o = b1;
+      if (o < b2) o = b2;
+      if (o < b3) o = b3;
+    }
     P.tenlen = take(m.ntendon); P.tenJ = take(m.ntendon * ld);
     P.con = take(m.nconmax * CON_STRIDE);
-    P.sens = take(m.nsensordata);
     P.total = o;
     M->smem_pos = (size_t)o * sizeof(double);
     auto acc_layout = [&](Lay& A, int rows, bool with_sens) {
@@ -2665,7 +2724,7 @@ static void build_layout(b200mj_model* M) {
     }
     Hand& Hd = M->hand;
     o = 0;
-    Hd.M = take(ntri); Hd.J = take(nj * ld); Hd.efcD = take(nj); Hd.aref = take(nj); Hd.eqflag = take((nj + 1) / 2);
+    Hd.M = take(ntri); Hd.J = take((m.npair > 0 && nj * ld < STAGE_DOUBLES) ? STAGE_DOUBLES : nj * ld); Hd.efcD = take(nj); Hd.aref = take(nj); Hd.eqflag = take((nj + 1) / 2);
     Hd.bias = take(nv); Hd.passive = take(nv); Hd.tenlen = take(m.ntendon); Hd.tenJ = take(m.ntendon * ld); Hd.counts = take(2);
     Hd.total = o;
     Hand2& H2 = M->hand2;
@@ -2797,6 +2856,15 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
     B200MJ_MODEL_FIELDS(HS_I, HS_R)
 #undef HS_I
 #undef HS_R
+    // does any candidate pair reach the convex routines (see narrowphase<CVX>)? If not the position kernels are the primitive-only builds.
+    M->convex_pairs = 0;
+    for (int p = 0; p < m.npair; p++) {
+      const int t1 = hf.geom_type[hf.pair_geom1[p]], t2 = hf.geom_type[hf.pair_geom2[p]];
+      const bool analytic = t1 == BMJ_GEOM_PLANE || (t1 == BMJ_GEOM_SPHERE && (t2 == BMJ_GEOM_SPHERE || t2 == BMJ_GEOM_CAPSULE || t2 == BMJ_GEOM_BOX)) ||
+                            (t1 == BMJ_GEOM_CAPSULE && t2 == BMJ_GEOM_CAPSULE);
+      if (!analytic) M->convex_pairs = 1;
+    }
+    if (const char* ev = getenv("B200MJ_POS_CVX")) if (atoi(ev) == 1) M->convex_pairs = 1;   // A/B: force the general build
     const int nv = m.nv, nu = m.nu;
     int* adr = new int[nv + 1];
     int* ids = new int[(size_t)nv * (nu > 0 ? nu : 1)];
@@ -2840,10 +2908,13 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming);
   M->streams_ok = 1;
   cudaFuncSetAttribute(b200mj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(b200mj_step_prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_acclast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_posfinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(b200mj_pos_prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(b200mj_posfinal_prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (M->tn_nv) {
     cudaFuncSetAttribute(tn_kernel(M->tn_nv, false), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tn_kernel(M->tn_nv, true), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -2950,7 +3021,7 @@ static int launch(const b200mj_model* M, const b200mj_io* io, int batch, int nst
   if (const char* pad = getenv("B200MJ_EXTRA_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
   static int sync_level = -1;
   if (sync_level < 0) { const char* sl = getenv("B200MJ_SYNC_LEVEL"); sync_level = sl ? atoi(sl) : 1; }
-  B200MJ_LAUNCH(b200mj_step_kernel, grid, 32 * epb, smem, (cudaStream_t)stream, M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level, env_mask);
+  B200MJ_LAUNCH((M->convex_pairs ? b200mj_step_kernel : b200mj_step_prim_kernel), grid, 32 * epb, smem, (cudaStream_t)stream, M->dm, M->lay, *io, batch, nstep, flags, mode, extra, sync_level, env_mask);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
@@ -2975,8 +3046,8 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     if (M->d_hand) cudaFree(M->d_hand);
     if (M->d_hand2) cudaFree(M->d_hand2);
     M->d_hand = M->d_hand2 = nullptr; M->hand_batch = 0; M->reuse_ok = 0;
-    if (cudaMalloc(&M->d_hand, (size_t)batch * M->hand.total * sizeof(double)) != cudaSuccess) return -2;
-    if (cudaMalloc(&M->d_hand2, (size_t)batch * M->hand2.total * sizeof(double)) != cudaSuccess) return -2;
+    if (cudaMalloc(&M->d_hand, (size_t)(batch + SHADOW_ROWS) * M->hand.total * sizeof(double)) != cudaSuccess) return -2;
+    if (cudaMalloc(&M->d_hand2, (size_t)(batch + SHADOW_ROWS) * M->hand2.total * sizeof(double)) != cudaSuccess) return -2;
     if (M->d_bcount) cudaFree(M->d_bcount);
     if (M->d_blist) cudaFree(M->d_blist);
     M->d_bcount = M->d_blist = nullptr;
@@ -3038,6 +3109,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     int* glist = M->d_blist ? M->d_blist + (size_t)g * 4 * M->hand_batch : nullptr;
     auto compact_for = [&](int slot) {
       Compact cp; memset(&cp, 0, sizeof(cp));
+      cp.shadow_row = M->hand_batch + g * 8;
       if (compact) {
         cp.count = gcount + slot * 8; cp.list = glist; cp.cap = M->hand_batch; cp.nbucket = M->nbucket;
         for (int b = 0; b < M->nbucket; b++) cp.rows_cap[b] = M->rows_cap[b];
@@ -3050,7 +3122,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
       const bool last = all_split && s == nstep - 1;
       if (!(reuse && s == 0)) {
         const Compact cp = compact_for(s);
-        B200MJ_LAUNCH(b200mj_pos_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        B200MJ_LAUNCH((M->convex_pairs ? b200mj_pos_kernel : b200mj_pos_prim_kernel), gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                                  e1, 0, flags, last && want_sens, e0, cp);
         g_launches++;
       }
@@ -3093,7 +3165,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     }
     if (all_split) {
       const Compact cp = compact_for(0);      // the next call's first acceleration launches read slot 0
-      B200MJ_LAUNCH(b200mj_posfinal_kernel, gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+      B200MJ_LAUNCH((M->convex_pairs ? b200mj_posfinal_kernel : b200mj_posfinal_prim_kernel), gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                                     e1, 0, flags, want_sens && nstep == 1, e0, cp);
       g_launches++;
     }
