@@ -74,6 +74,10 @@ struct Lay {
   int vold;                              // last-step acceleration kernel: qvel before integration (for rne_post_constraint)
   int colbuf;                            // compile-time-size algebra: column broadcast buffer (TN_COLBUF_DOUBLES)
   int pgsA, pgsX, pgsB;                  // PGS solver (fused kernel only): A = J M^-1 J' + R [nj x nj], M^-1 J' [nj x ld], b [nj]
+  // dual form of the Newton direction (runtime-size acceleration kernels, nv >= 32, row buckets of at most 32 rows):
+  // dV = rows of M^-1 J' [rows x ld]; dS = scratch [rows^2 + tri(rows) + 3 rows] for A = J M^-1 J', the factor of the
+  // active block R + A_aa and its right-hand side (aliases H, which is free between chol(M) and the Euler step)
+  int dual, dV, dS, drows;
   int total;
 };
 
@@ -437,6 +441,73 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
     tj += j + 1;
   }
   if (b) chol_forward(Lm, dinv, b, y, n, lane);
+}
+
+// M X = B for K right-hand sides at once (M = L L^T, L packed, n <= 64; B, X: K rows of stride ld, may alias).
+// The K substitutions share every load of L and run as independent dependency chains, eight at a time: one pass of
+// 2 n steps serves eight right-hand sides (a single substitution is latency-bound: one shuffle + one DFMA per step).
+// Lanes own rows `lane` and `lane + 32` of the unknowns. Serves the dual form of the Newton direction (rows of M^-1 J').
+__device__ __noinline__ void chol_solve_multi(const double* Lm, const double* dinv, int n, const double* Bm, double* Xm, int ld, int K, int lane) {
+  const int i0 = lane, i1 = lane + 32;
+  const bool in0 = i0 < n, in1 = i1 < n;
+  const double* L0 = Lm + tri(i0); const double* L1 = Lm + tri(i1);
+  _Pragma("unroll 1") for (int r0 = 0; r0 < K; r0 += 8) {
+    double a0[8], a1[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int r = r0 + q;
+      a0[q] = (r < K && in0) ? Bm[r * ld + i0] : 0.0;
+      a1[q] = (r < K && in1) ? Bm[r * ld + i1] : 0.0;
+    }
+    // forward: L y = b
+    _Pragma("unroll 1") for (int j = 0; j < n; j++) {
+      const double dj = dinv[j];
+      const double l0 = (in0 && i0 > j) ? L0[j] : 0.0, l1 = (in1 && i1 > j) ? L1[j] : 0.0;
+      if (j < 32) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const double v = __shfl_sync(FULL, a0[q], j) * dj;
+          a0[q] = (lane == j) ? v : a0[q] - l0 * v;
+          a1[q] -= l1 * v;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const double v = __shfl_sync(FULL, a1[q], j - 32) * dj;
+          a1[q] = (i1 == j) ? v : a1[q] - l1 * v;
+        }
+      }
+    }
+    // backward: L^T x = y
+    int tj = tri(n - 1);
+    _Pragma("unroll 1") for (int j = n - 1; j >= 0; j--) {
+      const double dj = dinv[j];
+      const double l0 = (i0 < j) ? Lm[tj + i0] : 0.0, l1 = (i1 < j) ? Lm[tj + i1] : 0.0;     // i0 < j <= n - 1
+      if (j >= 32) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const double v = __shfl_sync(FULL, a1[q], j - 32) * dj;
+          a1[q] = (i1 == j) ? v : a1[q] - l1 * v;
+          a0[q] -= l0 * v;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const double v = __shfl_sync(FULL, a0[q], j) * dj;
+          a0[q] = (lane == j) ? v : a0[q] - l0 * v;
+        }
+      }
+      tj -= j;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int r = r0 + q;
+      if (r < K && in0) Xm[r * ld + i0] = a0[q];
+      if (r < K && in1) Xm[r * ld + i1] = a1[q];
+    }
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1607,11 +1678,70 @@ __device__ __forceinline__ Primal constraint_update(const Ctx& c, int nefc) {
   return p;
 }
 
+// --- dual form of the Newton direction (c.L.dual) --------------------------------------------------------------------
+// The Hessian of the primal problem is H = M + J_a' D_a J_a over the active rows a. With few rows and many dofs the
+// Woodbury identity gives the same direction from an nact x nact system instead of an nv x nv factorisation:
+//   H^-1 g = u - V_a' (R_a + A_aa)^-1 J_a u,   u = M^-1 g = qacc - qacc_smooth - V' force,
+//   V = J M^-1 (rows, computed once per physics step from chol(M)),  A = J M^-1 J',  R = 1 / D.
+// The CMU humanoid (nv = 62) has ~10 rows in a typical step and the Newton solver refactors on almost every iteration:
+// ~3.5 factorisations of 62 x 62 per physics step become one eight-at-a-time substitution pass and 3.5 factorisations
+// of ~5 x 5. Same iterates as the primal form up to rounding (tests/test_gpu_parity.py, tests/test_emu_kernel_parity.py).
+__device__ __forceinline__ void dual_prepare(const Ctx& c, int nefc) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  chol_solve_multi(W(H), W(dinv), nv, W(J), W(dV), ld, nefc, lane);      // H holds chol(M) (fwd_acceleration)
+  double* A = W(dS);                                                    // may alias H: chol(M) is dead from here on
+  _Pragma("unroll 1") for (int r = 0; r < nefc; r++) {
+    if (lane <= r) { const double a = dot_rows(W(J) + r * ld, W(dV) + lane * ld, nv); A[r * nefc + lane] = a; A[lane * nefc + r] = a; }
+  }
+  __syncwarp();
+}
+
+// grad, |grad|; search = -H^-1 grad through the dual form. Returns |grad|.
+__device__ __forceinline__ double newton_direction_dual(const Ctx& c, int nefc, int nact, bool refactor) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  const int* alist = reinterpret_cast<const int*>(W(actlist));
+  double* A = W(dS); double* S = A + nefc * nefc; double* sdinv = S + tri(c.L.drows); double* t = sdinv + c.L.drows; double* y = t + c.L.drows;
+  double gpart = 0;
+  FOR_LANES(i, nv) {
+    const double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; gpart += g * g;
+    double u0 = W(qacc)[i] - W(qaccs)[i], u1 = 0;
+    int a = 0;
+    _Pragma("unroll 1") for (; a + 2 <= nact; a += 2) { const int r0 = alist[a], r1 = alist[a + 1]; u0 -= W(dV)[r0 * ld + i] * W(force)[r0]; u1 -= W(dV)[r1 * ld + i] * W(force)[r1]; }
+    if (a < nact) { const int r0 = alist[a]; u0 -= W(dV)[r0 * ld + i] * W(force)[r0]; }
+    W(tmpv)[i] = u0 + u1;
+  }
+  const double gnorm = sqrt(warp_sum(gpart));
+  __syncwarp();
+  if (nact > 0) {
+    FOR_LANES(a, nact) t[a] = dot_rows(W(J) + alist[a] * ld, W(tmpv), nv);
+    if (refactor) {
+      FOR_LANES(a, nact) {
+        const int ra = alist[a]; const double* Ar = A + ra * nefc; double* Sa = S + tri(a);
+        _Pragma("unroll 1") for (int b = 0; b < a; b++) Sa[b] = Ar[alist[b]];
+        Sa[a] = Ar[ra] + 1.0 / W(efcD)[ra];
+      }
+      __syncwarp();
+      chol_factor(S, S, sdinv, nact, lane, t, y);
+    } else { __syncwarp(); chol_forward(S, sdinv, t, y, nact, lane); }
+    chol_back(S, sdinv, y, y, nact, lane);
+  }
+  FOR_LANES(i, nv) {
+    double s0 = W(tmpv)[i], s1 = 0;
+    int a = 0;
+    _Pragma("unroll 1") for (; a + 2 <= nact; a += 2) { s0 -= W(dV)[alist[a] * ld + i] * y[a]; s1 -= W(dV)[alist[a + 1] * ld + i] * y[a + 1]; }
+    if (a < nact) s0 -= W(dV)[alist[a] * ld + i] * y[a];
+    W(search)[i] = -(s0 + s1);
+  }
+  __syncwarp();
+  return gnorm;
+}
+
 // grad; (re)assemble H = M + J^T diag(SD) J and factor it only when the active set changed; search = -H^-1 grad.
 // Returns |grad|.
 template <int NVT>
 __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int nact, bool refactor) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  if constexpr (NVT == 0) { if (c.L.dual) return newton_direction_dual(c, nefc, nact, refactor); }
   double gpart = 0;
   FOR_LANES(i, nv) { double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; W(grad)[i] = g; gpart += g * g; }
   double gnorm = sqrt(warp_sum(gpart));
@@ -1721,6 +1851,7 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
   Primal pr; pr.cost = 0; pr.gauss = 0; pr.nact = 0; pr.changed = 1;
   const bool active = nefc > 0;
+  if constexpr (NVT == 0) { if (active && c.L.dual) dual_prepare(c, nefc); }
   if (active) {
     // start point: the warm start if it has lower cost than the unconstrained acceleration (MuJoCo's rule).
     // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart restored (only when it won)
@@ -2674,6 +2805,11 @@ static void build_layout(b200mj_model* M) {
     P.con = take(m.nconmax * CON_STRIDE);
     P.total = o;
     M->smem_pos = (size_t)o * sizeof(double);
+    // dual form of the Newton direction in the runtime-size kernels (B200MJ_DUAL_MIN_NV, default 32: the two-rows-per-lane
+    // factorisation; 0 disables)
+    int dual_min_nv = 32;
+    if (const char* ev = getenv("B200MJ_DUAL_MIN_NV")) dual_min_nv = atoi(ev);
+    auto tri_host = [](int i) { return (i * (i + 1)) / 2; };
     auto acc_layout = [&](Lay& A, int rows, bool with_sens) {
       memset(&A, 0, sizeof(A));
       o = 0;
@@ -2688,6 +2824,11 @@ static void build_layout(b200mj_model* M) {
       A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
       A.bias = take(nv); A.passive = take(nv); A.qfact = take(nv); A.smooth = take(nv); A.qaccs = take(nv);
       A.qcon = take(nv); A.Ma = take(nv); A.grad = take(nv); A.search = take(nv); A.Mv = take(nv); A.tmpv = take(nv);
+      if (dual_min_nv > 0 && !M->tn_nv && nv >= dual_min_nv && rows <= 32 && m.solver == BMJ_SOL_NEWTON) {
+        A.dual = 1; A.drows = rows; A.dV = take(rows * ld);
+        const int need = rows * rows + tri_host(rows) + 3 * rows + 2;
+        A.dS = need <= ntri ? A.H : take(need);
+      }
       if (with_sens) {
         const int acc_end = o;
         o = u0;
