@@ -69,6 +69,7 @@ struct Lay {
   int J, efcD, efcSD, aref, jar, jv, force, eqflag, actlist;
   int bias, passive, qfact, smooth, qaccs, qacc, qcon, Ma, grad, search, Mv, tmpv;
   int con;                               // contact records, 16 doubles each
+  int cq;                                // collision: queue of candidate pairs that passed the bounding tests (64 ints)
   int rk;                                // RK4 scratch: X0q, X0v, X0a, accv, acca, accd
   int sens;                              // sensordata staging
   int vold;                              // last-step acceleration kernel: qvel before integration (for rne_post_constraint)
@@ -423,22 +424,93 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
     }
     return;
   }
-  // n >= 32: two rows per lane, one column at a time; the right-hand side takes a separate pass
+  // n >= 32: two rows per lane (lane, lane + 32), left-looking by blocks of four columns like the path above: the part
+  // of the eight dot products left of the block shares its loads (2 own-row + 4 pivot-row loads per 8 multiply-adds; one
+  // column at a time with a dot product per row took 4 loads per 2), the eight accumulators are independent chains,
+  // and inside the block pivots and cross terms travel by shuffle. Rows 0..31 are finished once the block start passes
+  // 32: from there on only the second row of every lane is updated. The right-hand side takes a separate pass.
   const int i0 = lane, i1 = lane + 32, ti0 = tri(i0), ti1 = tri(i1);
-  int tj = 0;
-  _Pragma("unroll 1") for (int j = 0; j < n; j++) {
-    double t0 = 0, t1 = 0;
-    const double* Lj = Lm + tj;
-    if (i0 >= j && i0 < n) t0 = A[ti0 + j] - dot_rows(Lm + ti0, Lj, j);
-    if (i1 >= j && i1 < n) t1 = A[ti1 + j] - dot_rows(Lm + ti1, Lj, j);
-    double piv = __shfl_sync(FULL, j < 32 ? t0 : t1, j & 31);
-    if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
-    double inv = rsqrt(piv);
-    if (i0 == j || i1 == j) { Lm[tj + j] = piv * inv; dinv[j] = inv; }
-    if (i0 > j && i0 < n) Lm[ti0 + j] = t0 * inv;
-    if (i1 > j && i1 < n) Lm[ti1 + j] = t1 * inv;
+  const bool in1 = i1 < n;
+  const double* A0 = A + ti0; const double* A1 = in1 ? A + ti1 : A;
+  double* L0 = Lm + ti0; double* L1 = in1 ? Lm + ti1 : Lm;      // idle second rows read row 0, never write
+  int tj0 = 0;
+  _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += 4) {
+    const int j1 = min(j0 + 1, n - 1), j2 = min(j0 + 2, n - 1), j3 = min(j0 + 3, n - 1);
+    const double* r0 = Lm + tj0; const double* r1 = Lm + tri(j1); const double* r2 = Lm + tri(j2); const double* r3 = Lm + tri(j3);
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;      // s: row i0, u: row i1
+    const bool low = j0 < 32;                                                   // warp-uniform
+    if (low) {
+      _Pragma("unroll 1") for (int k = 0; k < j0; k += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double b0 = r0[k + q], b1 = r1[k + q], b2 = r2[k + q], b3 = r3[k + q];
+          const double a0 = L0[k + q], a1 = L1[k + q];      // rows above the block read finished entries: their sums are discarded below
+          s0 += a0 * b0; s1 += a0 * b1; s2 += a0 * b2; s3 += a0 * b3;
+          u0 += a1 * b0; u1 += a1 * b1; u2 += a1 * b2; u3 += a1 * b3;
+        }
+      }
+    } else {
+      _Pragma("unroll 1") for (int k = 0; k < j0; k += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double a1 = L1[k + q];
+          u0 += a1 * r0[k + q]; u1 += a1 * r1[k + q]; u2 += a1 * r2[k + q]; u3 += a1 * r3[k + q];
+        }
+      }
+    }
+    // (row, column) pairs of this block that exist: row >= column, column < n
+    const bool c1 = j0 + 1 < n, c2 = j0 + 2 < n, c3 = j0 + 3 < n;
+    const bool p00 = low && i0 >= j0, p01 = low && c1 && i0 >= j0 + 1, p02 = low && c2 && i0 >= j0 + 2, p03 = low && c3 && i0 >= j0 + 3;
+    const bool p10 = in1 && i1 >= j0, p11 = in1 && c1 && i1 >= j0 + 1, p12 = in1 && c2 && i1 >= j0 + 2, p13 = in1 && c3 && i1 >= j0 + 3;
+    s0 = p00 ? A0[j0] - s0 : 0.0; s1 = p01 ? A0[j0 + 1] - s1 : 0.0; s2 = p02 ? A0[j0 + 2] - s2 : 0.0; s3 = p03 ? A0[j0 + 3] - s3 : 0.0;
+    u0 = p10 ? A1[j0] - u0 : 0.0; u1 = p11 ? A1[j0 + 1] - u1 : 0.0; u2 = p12 ? A1[j0 + 2] - u2 : 0.0; u3 = p13 ? A1[j0 + 3] - u3 : 0.0;
+    // value of row j of this block (rows j0..j0+3 live in the first rows of lanes j when j < 32, else in the second rows of lanes j - 32)
+#define ROWVAL(sv, uv, j) __shfl_sync(FULL, low ? (sv) : (uv), (j) & 31)
+    double m0, m1 = 0, m2 = 0, n0, n1 = 0, n2 = 0;      // scaled columns: m = first row, n = second row
+    {
+      double piv = ROWVAL(s0, u0, j0);
+      if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+      const double inv = rsqrt(piv);
+      m0 = s0 * inv; n0 = u0 * inv;
+      if (p00) L0[j0] = (i0 == j0) ? piv * inv : m0;
+      if (p10) L1[j0] = (i1 == j0) ? piv * inv : n0;
+      if (lane == (j0 & 31)) dinv[j0] = inv;
+    }
+    if (c1) {
+      const double x = ROWVAL(m0, n0, j0 + 1);
+      s1 -= m0 * x; u1 -= n0 * x;
+      double piv = ROWVAL(s1, u1, j0 + 1);
+      if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+      const double inv = rsqrt(piv);
+      m1 = s1 * inv; n1 = u1 * inv;
+      if (p01) L0[j0 + 1] = (i0 == j0 + 1) ? piv * inv : m1;
+      if (p11) L1[j0 + 1] = (i1 == j0 + 1) ? piv * inv : n1;
+      if (lane == ((j0 + 1) & 31)) dinv[j0 + 1] = inv;
+    }
+    if (c2) {
+      const double x0 = ROWVAL(m0, n0, j0 + 2), x1 = ROWVAL(m1, n1, j0 + 2);
+      s2 -= m0 * x0; u2 -= n0 * x0; s2 -= m1 * x1; u2 -= n1 * x1;
+      double piv = ROWVAL(s2, u2, j0 + 2);
+      if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+      const double inv = rsqrt(piv);
+      m2 = s2 * inv; n2 = u2 * inv;
+      if (p02) L0[j0 + 2] = (i0 == j0 + 2) ? piv * inv : m2;
+      if (p12) L1[j0 + 2] = (i1 == j0 + 2) ? piv * inv : n2;
+      if (lane == ((j0 + 2) & 31)) dinv[j0 + 2] = inv;
+    }
+    if (c3) {
+      const double x0 = ROWVAL(m0, n0, j0 + 3), x1 = ROWVAL(m1, n1, j0 + 3), x2 = ROWVAL(m2, n2, j0 + 3);
+      s3 -= m0 * x0; u3 -= n0 * x0; s3 -= m1 * x1; u3 -= n1 * x1; s3 -= m2 * x2; u3 -= n2 * x2;
+      double piv = ROWVAL(s3, u3, j0 + 3);
+      if (piv < BMJ_MINVAL) piv = BMJ_MINVAL;
+      const double inv = rsqrt(piv);
+      if (p03) L0[j0 + 3] = (i0 == j0 + 3) ? piv * inv : s3 * inv;
+      if (p13) L1[j0 + 3] = (i1 == j0 + 3) ? piv * inv : u3 * inv;
+      if (lane == ((j0 + 3) & 31)) dinv[j0 + 3] = inv;
+    }
+#undef ROWVAL
     __syncwarp();
-    tj += j + 1;
+    tj0 += 4 * j0 + 10;
   }
   if (b) chol_forward(Lm, dinv, b, y, n, lane);
 }
@@ -1202,28 +1274,68 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
   int ncon = 0;
   if (c.disableflags & (BMJ_DSBL_CONTACT | BMJ_DSBL_CONSTRAINT)) return 0;
   double* stg = c.stage + lane;   // staging: the Jacobian buffer (fused kernel) / the not-yet-written dynamics block (split)
-  _Pragma("unroll 1") for (int base = 0; base < m.npair; base += 32) {
-    int p = base + lane;
-    int n = 0, g1 = 0, g2 = 0;
-    if (p < m.npair) {
-      g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
-      int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-      double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
-      const double* p1 = W(gxpos) + 3 * g1; const double* p2 = W(gxpos) + 3 * g2;
-      const double* m1 = W(gxmat) + 9 * g1; const double* m2 = W(gxmat) + 9 * g2;
-      bool keep;
-      double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-      double s1[3], s2[3];
-      const double rb1 = geom_size_of(c, g1, s1), rb2 = geom_size_of(c, g2, s2);
-      if (t1 == BMJ_GEOM_PLANE) {
-        double nr[3] = {m1[2], m1[5], m1[8]};
-        keep = dot3(dif, nr) <= rb2 + margin;
-      } else {
-        double bound = rb1 + rb2 + margin;
-        keep = dot3(dif, dif) <= bound * bound;
+  // Two phases, interleaved: the bounding tests of 32 candidate pairs at a time append the survivors to a queue (in pair
+  // order), and the narrow phase runs over 32 queued pairs at a time. Few of a model's candidate pairs pass the bounds
+  // in any one step (CMU corridor: 2 113 candidates, a few dozen survivors), and the narrow phase is divergent code: run
+  // per 32 candidates, every chunk with one survivor paid for a whole pass. Contacts come out in pair order as before.
+  int* queue = reinterpret_cast<int*>(W(cq));
+  int qn = 0, base = 0;
+  _Pragma("unroll 1") while (base < m.npair || qn > 0) {
+    _Pragma("unroll 1") while (qn < 32 && base < m.npair) {
+      const int p = base + lane;
+      bool keep = false;
+      if (p < m.npair) {
+        const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
+        const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+        const double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
+        const double* p1 = W(gxpos) + 3 * g1; const double* p2 = W(gxpos) + 3 * g2;
+        const double* m1 = W(gxmat) + 9 * g1; const double* m2 = W(gxmat) + 9 * g2;
+        double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+        double s1[3], s2[3];
+        const double rb1 = geom_size_of(c, g1, s1), rb2 = geom_size_of(c, g2, s2);
+        if (t1 == BMJ_GEOM_PLANE) {
+          double nr[3] = {m1[2], m1[5], m1[8]};
+          keep = dot3(dif, nr) <= rb2 + margin;
+        } else {
+          double bound = rb1 + rb2 + margin;
+          keep = dot3(dif, dif) <= bound * bound;
+          // boxes (corridor walls: long, thin, with a bounding sphere that reaches most of the walker): the other geom's
+          // bounding sphere against the box's slabs, in the box frame — conservative, so the contact set is unchanged
+          if (keep && t2 == BMJ_GEOM_BOX) {
+            double loc[3]; matT_vec(loc, m2, dif);
+            const double r = rb1 + margin;
+            keep = fabs(loc[0]) <= s2[0] + r && fabs(loc[1]) <= s2[1] + r && fabs(loc[2]) <= s2[2] + r;
+          }
+          if (keep && t1 == BMJ_GEOM_BOX) {
+            double loc[3]; matT_vec(loc, m1, dif);
+            const double r = rb2 + margin;
+            keep = fabs(loc[0]) <= s1[0] + r && fabs(loc[1]) <= s1[1] + r && fabs(loc[2]) <= s1[2] + r;
+          }
+        }
       }
-      if (keep) n = narrowphase<CVX>(stg, t1, t2, margin, p1, m1, s1, p2, m2, s2);
+      const unsigned bal = __ballot_sync(FULL, keep);
+      if (keep) queue[qn + __popc(bal & ((1u << lane) - 1))] = p;
+      qn += __popc(bal);
+      base += 32;
     }
+    __syncwarp();
+    const int take = qn < 32 ? qn : 32;
+    int n = 0, g1 = 0, g2 = 0;
+    if (lane < take) {
+      const int p = queue[lane];
+      g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
+      const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+      const double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
+      double s1[3], s2[3];
+      geom_size_of(c, g1, s1); geom_size_of(c, g2, s2);
+      n = narrowphase<CVX>(stg, t1, t2, margin, W(gxpos) + 3 * g1, W(gxmat) + 9 * g1, s1, W(gxpos) + 3 * g2, W(gxmat) + 9 * g2, s2);
+    }
+    // the queue's remainder moves to the front
+    const int rest = qn - take;
+    const int moved = lane < rest ? queue[take + lane] : 0;
+    __syncwarp();
+    if (lane < rest) queue[lane] = moved;
+    qn = rest;
     int total;
     int off = warp_excl_scan(n, lane, &total);
     if (total == 0) continue;
@@ -2755,7 +2867,7 @@ static void build_layout(b200mj_model* M) {
   L.force = take(nj); L.eqflag = take((nj + 1) / 2); L.actlist = take((nj + 1) / 2);
   L.bias = take(nv); L.passive = take(nv); L.qfact = take(nv); L.smooth = take(nv); L.qaccs = take(nv); L.qacc = take(nv);
   L.qcon = take(nv); L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv); L.tmpv = take(nv);
-  L.con = take(m.nconmax * CON_STRIDE);
+  L.con = take(m.nconmax * CON_STRIDE); L.cq = take(m.npair > 0 ? 32 : 0);
   L.rk = take(m.integrator == BMJ_INT_RK4 ? (m.nq + 3 * nv + 2 * m.na + 8) : 0);
   L.sens = take(m.nsensordata);
   const bool pgs = m.solver == BMJ_SOL_PGS;
@@ -2802,7 +2914,7 @@ static void build_layout(b200mj_model* M) {
       if (o < b3) o = b3;
     }
     P.tenlen = take(m.ntendon); P.tenJ = take(m.ntendon * ld);
-    P.con = take(m.nconmax * CON_STRIDE);
+    P.con = take(m.nconmax * CON_STRIDE); P.cq = take(m.npair > 0 ? 32 : 0);
     P.total = o;
     M->smem_pos = (size_t)o * sizeof(double);
     // dual form of the Newton direction in the runtime-size kernels (B200MJ_DUAL_MIN_NV, default 32: the two-rows-per-lane
