@@ -79,6 +79,7 @@ struct Lay {
   // dV = rows of M^-1 J' [rows x ld]; dS = scratch [rows^2 + tri(rows) + 3 rows] for A = J M^-1 J', the factor of the
   // active block R + A_aa and its right-hand side (aliases H, which is free between chol(M) and the Euler step)
   int dual, dV, dS, drows;
+  int mglobal;                           // runtime-size acceleration kernels, nv >= 32: M stays in the handover row (no workspace copy)
   int total;
 };
 
@@ -114,7 +115,7 @@ struct b200mj_model {
   int* d_niter;                    // Newton iterations of every environment's previous physics step [hand_batch]
   // the trailing mj_step1 of the last split-path step left a complete handover for this (io, batch): see B200MJ_STEP_REUSE_POS
   const double* reuse_qpos; int reuse_batch; int reuse_flags; int reuse_ok; int reuse_has_dump;
-  int epb_pos, epb_acc;
+  int epb_pos, epb_acc, pos_big;
   size_t smem_pos, smem_acc;
   int* d_idata;
   double* d_rdata;
@@ -235,11 +236,12 @@ struct Ctx {
   // where the position/velocity stage deposits what the acceleration stage consumes: the workspace itself in the
   // fused kernel, this environment's row of the L2-resident handover buffer in the split position kernel
   double *pM, *pJ, *pD, *pAref, *pBias, *pPassive; int* pEq; double* stage;
+  const double* Mc;     // acceleration stage: the joint-space inertia, read-only — the workspace copy, or (L.mglobal) the handover row in L2
   int env; const double* var_pos; const double* var_size;      // per-environment geoms (set_env)
   __device__ void set_env(int e, const b200mj_io& io) { env = e; var_pos = io.var_geom_pos; var_size = io.var_geom_size; }
   __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df, int sl) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df), sync_level(sl), env(0), var_pos(nullptr), var_size(nullptr) {
     pM = ws_ + L_.M; pJ = ws_ + L_.J; pD = ws_ + L_.efcD; pAref = ws_ + L_.aref; pBias = ws_ + L_.bias; pPassive = ws_ + L_.passive;
-    pEq = reinterpret_cast<int*>(ws_ + L_.eqflag); stage = ws_ + L_.J;
+    pEq = reinterpret_cast<int*>(ws_ + L_.eqflag); stage = ws_ + L_.J; Mc = pM;
   }
 };
 #define W(name) (c.ws + c.L.name)
@@ -1730,7 +1732,7 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
     tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(smooth), W(qaccs), W(J), W(efcSD), reinterpret_cast<const int*>(W(actlist)), opaque_zero(), W(colbuf));
     tn_back<NVT>(W(H), W(dinv), W(qaccs), W(qaccs), lane, 0);
   } else {
-    chol_factor(W(M), W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
+    chol_factor(c.Mc, W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
     chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
   }
 }
@@ -1746,7 +1748,7 @@ __device__ __forceinline__ void compute_Ma_jar(const Ctx& c, int nefc) {
     if (lane < NVT) W(Ma)[lane] = tn_symv_row<NVT>(W(M), W(qacc), lane);
     FOR_LANES(r, nefc) W(jar)[r] = tn_dot_row<NVT>(W(J) + r * ld, W(qacc)) - W(aref)[r];
   } else {
-    FOR_LANES(i, nv) W(Ma)[i] = symv_row(W(M), W(qacc), nv, i);
+    FOR_LANES(i, nv) W(Ma)[i] = symv_row(c.Mc, W(qacc), nv, i);
     FOR_LANES(r, nefc) W(jar)[r] = dot_rows(W(J) + r * ld, W(qacc), nv) - W(aref)[r];
   }
   __syncwarp();
@@ -1815,7 +1817,7 @@ __device__ __forceinline__ double newton_direction_dual(const Ctx& c, int nefc, 
   double* A = W(dS); double* S = A + nefc * nefc; double* sdinv = S + tri(c.L.drows); double* t = sdinv + c.L.drows; double* y = t + c.L.drows;
   double gpart = 0;
   FOR_LANES(i, nv) {
-    const double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; gpart += g * g;
+    const double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; gpart += g * g; W(grad)[i] = g;
     double u0 = W(qacc)[i] - W(qaccs)[i], u1 = 0;
     int a = 0;
     _Pragma("unroll 1") for (; a + 2 <= nact; a += 2) { const int r0 = alist[a], r1 = alist[a + 1]; u0 -= W(dV)[r0 * ld + i] * W(force)[r0]; u1 -= W(dV)[r1 * ld + i] * W(force)[r1]; }
@@ -1837,12 +1839,17 @@ __device__ __forceinline__ double newton_direction_dual(const Ctx& c, int nefc, 
     } else { __syncwarp(); chol_forward(S, sdinv, t, y, nact, lane); }
     chol_back(S, sdinv, y, y, nact, lane);
   }
+  // search = -(u - V_a' y), and M search = -(M u - J_a' y) = -(grad - J_a' y) for free: the line search needs no product with M
   FOR_LANES(i, nv) {
-    double s0 = W(tmpv)[i], s1 = 0;
+    double s0 = W(tmpv)[i], s1 = 0, m0 = W(grad)[i], m1 = 0;
     int a = 0;
-    _Pragma("unroll 1") for (; a + 2 <= nact; a += 2) { s0 -= W(dV)[alist[a] * ld + i] * y[a]; s1 -= W(dV)[alist[a + 1] * ld + i] * y[a + 1]; }
-    if (a < nact) s0 -= W(dV)[alist[a] * ld + i] * y[a];
-    W(search)[i] = -(s0 + s1);
+    _Pragma("unroll 1") for (; a + 2 <= nact; a += 2) {
+      const int r0 = alist[a], r1 = alist[a + 1];
+      s0 -= W(dV)[r0 * ld + i] * y[a]; s1 -= W(dV)[r1 * ld + i] * y[a + 1];
+      m0 -= W(J)[r0 * ld + i] * y[a]; m1 -= W(J)[r1 * ld + i] * y[a + 1];
+    }
+    if (a < nact) { const int r0 = alist[a]; s0 -= W(dV)[r0 * ld + i] * y[a]; m0 -= W(J)[r0 * ld + i] * y[a]; }
+    W(search)[i] = -(s0 + s1); W(Mv)[i] = -(m0 + m1);
   }
   __syncwarp();
   return gnorm;
@@ -1872,7 +1879,7 @@ __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int n
         double acc[8];
         const int t0 = tri(i0) + j;      // packed (i0 + q, j) sits at t0 + q * i0 + q (q + 1) / 2; rows above the diagonal are skipped
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = (i0 + q < nv && i0 + q >= j) ? W(M)[t0 + q * i0 + ((q * (q + 1)) >> 1)] : 0.0;
+        for (int q = 0; q < 8; q++) acc[q] = (i0 + q < nv && i0 + q >= j) ? c.Mc[t0 + q * i0 + ((q * (q + 1)) >> 1)] : 0.0;
         _Pragma("unroll 1") for (int a = 0; a < nact; a++) {
           int r = alist[a];
           const double* Jr = W(J) + r * ld;
@@ -1924,8 +1931,9 @@ __device__ __forceinline__ double line_search(const Ctx& c, int nefc, const Prim
     }
     FOR_LANES(r, nefc) W(jv)[r] = tn_dot_row<NVT>(W(J) + r * ld, W(search));
   } else {
+    const bool have_mv = c.L.dual != 0;      // the dual form of the direction delivers M search as well (newton_direction_dual)
     FOR_LANES(i, nv) {
-      double s = symv_row(W(M), W(search), nv, i);
+      double s = have_mv ? W(Mv)[i] : symv_row(c.Mc, W(search), nv, i);
       W(Mv)[i] = s;
       g1 += W(search)[i] * (W(Ma)[i] - W(smooth)[i]); g2 += 0.5 * W(search)[i] * s;
     }
@@ -2343,7 +2351,7 @@ __device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
       FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
     }
   } else if (m.any_damping && !(c.disableflags & BMJ_DSBL_EULERDAMP)) {
-    _Pragma("unroll 1") for (int i = lane; i < tri(nv); i += 32) W(H)[i] = W(M)[i];
+    copy_row(W(H), c.Mc, tri(nv), lane);
     FOR_LANES(i, nv) W(tmpv)[i] = W(smooth)[i] + W(qcon)[i];
     __syncwarp();
     FOR_LANES(i, nv) W(H)[tri(i) + i] += h * m.dof_damping[i];
@@ -2676,6 +2684,21 @@ b200mj_posfinal_kernel(const __grid_constant__ DevModel m, const __grid_constant
   pos_kernel_body<true, true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
 }
 
+// large models (CMU corridor: 30 KB of position workspace per environment, one CTA per SM either way): up to seven
+// phase-aligned warps in that one CTA and the full register budget
+extern "C" __global__ void __launch_bounds__(224, 1)
+b200mj_pos_big_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
+                      const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
+                      int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
+  pos_kernel_body<false, true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
+}
+extern "C" __global__ void __launch_bounds__(224, 1)
+b200mj_posfinal_big_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
+                           const __grid_constant__ Hand2 H2, const __grid_constant__ b200mj_io io, double* hand, double* hand2, int batch,
+                           int extra_disable, int flags, int dump, int env0, const __grid_constant__ Compact cp) {
+  pos_kernel_body<true, true>(m, L, H, H2, io, hand, hand2, batch, extra_disable, flags, dump, env0, cp);
+}
+
 // the same for models whose candidate pairs are all analytic primitive pairs (121 registers, no stack spills): three CTAs per SM
 extern "C" __global__ void __launch_bounds__(160, 3)
 b200mj_pos_prim_kernel(const __grid_constant__ DevModel m, const __grid_constant__ Lay L, const __grid_constant__ Hand H,
@@ -2738,7 +2761,8 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
                      W(bias)[i] = hrow[H.bias + i]; W(passive)[i] = hrow[H.passive + i]; }
   FOR_LANES(i, m.na) W(act)[i] = io.act[e * m.na + i];
   FOR_LANES(i, m.nu) W(ctrl)[i] = io.ctrl ? io.ctrl[e * m.nu + i] : 0.0;
-  copy_row(W(M), hrow + H.M, tri(nv), lane);
+  if (L.mglobal) c.Mc = hrow + H.M;      // read where the position kernel left it (L2): one factorisation, one product and the Euler copy
+  else copy_row(W(M), hrow + H.M, tri(nv), lane);
   copy_row(W(J), hrow + H.J, nefc * ld, lane);
   FOR_LANES(r, nefc) { W(efcD)[r] = hrow[H.efcD + r]; W(aref)[r] = hrow[H.aref + r];
                        reinterpret_cast<int*>(W(eqflag))[r] = reinterpret_cast<const int*>(hrow + H.eqflag)[r]; W(efcSD)[r] = 0; }
@@ -2922,6 +2946,8 @@ static void build_layout(b200mj_model* M) {
     int dual_min_nv = 32;
     if (const char* ev = getenv("B200MJ_DUAL_MIN_NV")) dual_min_nv = atoi(ev);
     auto tri_host = [](int i) { return (i * (i + 1)) / 2; };
+    int mglobal_on = 1;
+    if (const char* ev = getenv("B200MJ_M_GLOBAL")) mglobal_on = atoi(ev);
     auto acc_layout = [&](Lay& A, int rows, bool with_sens) {
       memset(&A, 0, sizeof(A));
       o = 0;
@@ -2931,7 +2957,8 @@ static void build_layout(b200mj_model* M) {
       // Everything below is dead once the state has been integrated; the sensor-carrying variant then re-uses the
       // storage for the position-stage dump that rne_post_constraint and the acceleration-stage sensors read.
       const int u0 = o;
-      A.M = take(ntri); A.H = take(ntri); A.dinv = take(nv);
+      A.mglobal = (mglobal_on && !M->tn_nv && nv >= 32) ? 1 : 0;
+      A.M = take(A.mglobal ? 0 : ntri); A.H = take(ntri); A.dinv = take(nv);
       A.J = take(rows * ld); A.efcD = take(rows); A.efcSD = take(rows); A.aref = take(rows); A.jar = take(rows); A.jv = take(rows);
       A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
       A.bias = take(nv); A.passive = take(nv); A.qfact = take(nv); A.smooth = take(nv); A.qaccs = take(nv);
@@ -2990,7 +3017,10 @@ static void build_layout(b200mj_model* M) {
     // several small CTAs per SM: no phase barriers in the split kernels
     // position kernels: CTAs of up to 5 phase-aligned warps, two CTAs per SM when they fit
     M->epb_pos = pick(M->smem_pos) > 5 ? 5 : pick(M->smem_pos);
-    if (const char* ev = getenv("B200MJ_EPB_POS")) { int v = atoi(ev); if (v >= 1 && v <= pick(M->smem_pos) && v <= 5) M->epb_pos = v; }   // __launch_bounds__(160, ..)
+    // one 5-warp CTA per SM and room for more warps: the `big` kernels (up to 7 warps, __launch_bounds__(224, 1))
+    M->pos_big = 0;
+    if (2 * 5 * M->smem_pos + 2 * 64 > 227 * 1024 && pick(M->smem_pos) > 5) { M->pos_big = 1; M->epb_pos = pick(M->smem_pos) > 7 ? 7 : pick(M->smem_pos); }
+    if (const char* ev = getenv("B200MJ_EPB_POS")) { int v = atoi(ev); if (v >= 1 && v <= pick(M->smem_pos) && v <= (M->pos_big ? 7 : 5)) M->epb_pos = v; }   // __launch_bounds__(160, ..)
     M->epb_acc = pick(M->smem_accs_b[M->nbucket - 1]) >= 1 ? 1 : 0;   // one warp per CTA: out-of-bucket environments exit at once
   }
 }
@@ -3168,6 +3198,8 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
   cudaFuncSetAttribute(b200mj_posfinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_pos_prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(b200mj_posfinal_prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(b200mj_pos_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(b200mj_posfinal_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (M->tn_nv) {
     cudaFuncSetAttribute(tn_kernel(M->tn_nv, false), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tn_kernel(M->tn_nv, true), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -3375,7 +3407,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
       const bool last = all_split && s == nstep - 1;
       if (!(reuse && s == 0)) {
         const Compact cp = compact_for(s);
-        B200MJ_LAUNCH((M->convex_pairs ? b200mj_pos_kernel : b200mj_pos_prim_kernel), gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+        B200MJ_LAUNCH((M->pos_big ? b200mj_pos_big_kernel : M->convex_pairs ? b200mj_pos_kernel : b200mj_pos_prim_kernel), gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                                  e1, 0, flags, last && want_sens, e0, cp);
         g_launches++;
       }
@@ -3396,7 +3428,10 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
           static int per_bucket[4] = {0, 0, 0, 0}, parsed = 0;     // B200MJ_ACC_WARPS_B="4,3,2,2": warps per CTA by bucket (experiments)
           if (!parsed) { parsed = 1; if (const char* e = getenv("B200MJ_ACC_WARPS_B")) sscanf(e, "%d%*c%d%*c%d%*c%d", &per_bucket[0], &per_bucket[1], &per_bucket[2], &per_bucket[3]); }
           const int want = per_bucket[b] > 0 ? per_bucket[b] : acc_warps;
-          wpc = (int)((227 * 1024) / ws); if (wpc > want) wpc = want; if (M->tn_nv && wpc > 4) wpc = 4; if (wpc < 1) wpc = 1;
+          int cap = (int)((227 * 1024) / ws); if (cap > want) cap = want; if (M->tn_nv && cap > 4) cap = 4; if (cap < 1) cap = 1;
+          // as many resident warps per SM as 227 KB allow (CMU corridor, 37 KB per warp: two CTAs of 3 instead of one of 4); ties: the larger CTA
+          int best = 0;
+          for (int w = cap; w >= 1; w--) { const int res = (int)((227 * 1024) / ((w * ws) + 1024)) * w; if (res > best) { best = res; wpc = w; } }
         }
         const int grid = compact ? (cnt + wpc - 1) / wpc + (niter_split > 0 ? 1 : 0) : cnt;      // two classes: one more partial CTA
         const int* bc = compact ? gcount + s * 8 + b : nullptr;
@@ -3418,7 +3453,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
     }
     if (all_split) {
       const Compact cp = compact_for(0);      // the next call's first acceleration launches read slot 0
-      B200MJ_LAUNCH((M->convex_pairs ? b200mj_posfinal_kernel : b200mj_posfinal_prim_kernel), gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
+      B200MJ_LAUNCH((M->pos_big ? b200mj_posfinal_big_kernel : M->convex_pairs ? b200mj_posfinal_kernel : b200mj_posfinal_prim_kernel), gp, 32 * M->epb_pos, M->smem_pos * M->epb_pos + 64, sm, M->dm, M->lay_pos, M->hand, M->hand2, *io, M->d_hand, M->d_hand2,
                                                                                     e1, 0, flags, want_sens && nstep == 1, e0, cp);
       g_launches++;
     }
