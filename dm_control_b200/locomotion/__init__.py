@@ -3,8 +3,8 @@
 Reference pieces (all under dm_control/): `locomotion/examples/basic_cmu_2019.py:34-63` (the environment),
 `composer/environment.py:412-465` (step / substep / hook order), `locomotion/tasks/corridors.py:33-158` (task),
 `locomotion/arenas/corridors.py:94-175,330-440` (arena + per-episode walls), `locomotion/walkers/cmu_humanoid.py`,
-`legacy_base.py`, `base.py` (walker, observables). The egocentric camera observable needs a renderer and is not part of
-the batched task (out of scope).
+`legacy_base.py`, `base.py` (walker, observables). `egocentric_camera=True` adds the walker's 64 x 64 head-camera
+observable, ray-cast on the device by the rendering hand-off (dm_control_b200/render.py; not MuJoCo's OpenGL pixels).
 """
 from __future__ import annotations
 

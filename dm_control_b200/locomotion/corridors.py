@@ -70,8 +70,14 @@ class RunThroughCorridor(composer.Task):
   """Reward for running down the corridor at 3 m/s; ends when a non-foot geom touches the ground or an end effector
   drops below -0.5 m (tasks/corridors.py:33-158)."""
 
-  def __init__(self, physics, seed=0, contact_termination=True):
+  def __init__(self, physics, seed=0, contact_termination=True, egocentric_camera=False):
     self._walker = CMUWalker(physics.model, physics.device)
+    # walker.observables.egocentric_camera (legacy_base.py:276-279: the head camera, 64 x 64): ray-cast by the rendering
+    # hand-off (dm_control_b200/render.py), every environment seeing its own walls
+    self._camera = None
+    if egocentric_camera:
+      from .. import render
+      self._camera = render.Camera(physics, height=64, width=64, camera_id='egocentric', sites=False)
     self._contact_termination = contact_termination
     self._gen = torch.Generator(device=physics.device).manual_seed(seed)
     m = physics.model
@@ -150,12 +156,14 @@ class RunThroughCorridor(composer.Task):
     obs['walker/sensors_velocimeter'] = d.sensordata.index_select(1, w.s_veloc)
     obs['walker/sensors_torque'] = torch.tanh(2 * d.sensordata.index_select(1, w.s_torque) / _TORQUE_THRESHOLD)
     obs['walker/sensors_touch'] = (d.sensordata.index_select(1, w.s_touch) > _TOUCH_THRESHOLD).to(torch.float64)
+    if self._camera is not None:
+      obs['walker/egocentric_camera'] = self._camera.render()
     return obs
 
 
-def cmu_humanoid_run_walls(batch=1, seed=0, time_limit=_TIME_LIMIT, **physics_kw):
-  physics_kw.setdefault('outputs', OUTPUTS)
+def cmu_humanoid_run_walls(batch=1, seed=0, time_limit=_TIME_LIMIT, egocentric_camera=False, **physics_kw):
+  physics_kw.setdefault('outputs', OUTPUTS + (('geom_xpos', 'geom_xmat') if egocentric_camera else ()))
   physics = BatchedPhysics(testing_models.load('cmu_corridor_walls'), batch=batch, **physics_kw)
-  task = RunThroughCorridor(physics, seed=seed)
+  task = RunThroughCorridor(physics, seed=seed, egocentric_camera=egocentric_camera)
   return composer.BatchedComposerEnvironment(physics, task, time_limit=time_limit, physics_timestep=_PHYSICS_TIMESTEP,
                                              control_timestep=_CONTROL_TIMESTEP)

@@ -286,8 +286,17 @@ class _Compiler:
     self.joints = []
     self.geoms = []
     self.sites = []
+    self.cameras = []
     self.names = {k: {} for k in ('body', 'joint', 'geom', 'site', 'actuator', 'tendon', 'sensor', 'equality',
-                                  'key')}
+                                  'key', 'camera')}
+    # visual-only tables (rendering hand-off, dm_control_b200/render.py): material colours; they never reach the physics blob
+    self.material_rgba = {}
+    for asset in root.findall('asset'):
+      for mat in asset.findall('material'):
+        a = self.defaults.get('material', mat.attrib.get('class'))
+        a.update(mat.attrib)
+        if 'name' in a:
+          self.material_rgba[a['name']] = _floats(a.get('rgba', '1 1 1 1'), 4)
 
   # ---- attribute helpers -------------------------------------------------------------------
   def _merged(self, tag, elem, childclass):
@@ -343,6 +352,8 @@ class _Compiler:
         self._add_joint(child, bid, childclass)
       elif child.tag == 'site':
         self._add_site(child, bid, childclass)
+      elif child.tag == 'camera':
+        self._add_camera(child, bid, childclass)
       elif child.tag == 'inertial':
         a = child.attrib
         inert = dict(pos=_floats(a['pos'], 3), quat=self._frame_quat(a), mass=float(a['mass']))
@@ -437,7 +448,8 @@ class _Compiler:
              friction=_pad(_floats(a.get('friction', '1 0.005 0.0001')), [1, 0.005, 0.0001]),
              solmix=float(a.get('solmix', 1)), solref=_floats(a.get('solref', '0.02 1'), 2),
              solimp=_solimp(a.get('solimp')), margin=float(a.get('margin', 0)), gap=float(a.get('gap', 0)),
-             density=float(a.get('density', 1000)), mass=(float(a['mass']) if 'mass' in a else None))
+             density=float(a.get('density', 1000)), mass=(float(a['mass']) if 'mass' in a else None),
+             rgba=self._rgba(a), group=int(a.get('group', 0)))
     self.names['geom'][name] = len(self.geoms)
     self.geoms.append(g)
 
@@ -461,7 +473,25 @@ class _Compiler:
         size[2] = 0.5 * np.linalg.norm(vec)
     name = a.get('name', f'_site{len(self.sites)}')
     self.names['site'][name] = len(self.sites)
-    self.sites.append(dict(name=name, body=bid, type=stype, size=size, pos=pos, quat=quat))
+    self.sites.append(dict(name=name, body=bid, type=stype, size=size, pos=pos, quat=quat, rgba=self._rgba(a),
+                           group=int(a.get('group', 0))))
+
+  def _rgba(self, a):
+    # explicit rgba wins; else the material's colour; else MuJoCo's default grey
+    if 'rgba' in a:
+      return _floats(a['rgba'], 4)
+    if a.get('material') in self.material_rgba:
+      return self.material_rgba[a['material']].copy()
+    return np.array([0.5, 0.5, 0.5, 1.0])
+
+  def _add_camera(self, elem, bid, childclass):
+    """<camera>: pose in the body frame, vertical field of view, tracking mode (MuJoCo XML reference, body/camera)."""
+    a = self._merged('camera', elem, childclass)
+    name = a.get('name', f'_camera{len(self.cameras)}')
+    mode = {'fixed': 0, 'track': 1, 'trackcom': 2, 'targetbody': 3, 'targetbodycom': 4}[a.get('mode', 'fixed')]
+    self.names['camera'][name] = len(self.cameras)
+    self.cameras.append(dict(name=name, body=bid, pos=_floats(a.get('pos', '0 0 0'), 3), quat=self._frame_quat(a), mode=mode,
+                             fovy=(float(a['fovy']) if 'fovy' in a else None), target=a.get('target')))
 
 
 def _pad(v, default):
@@ -976,8 +1006,69 @@ def _finish(c, root, nconmax, njmax):
   names = {k: dict(v) for k, v in c.names.items()}
   ordered = dict(body=[b['name'] for b in c.bodies], joint=[j['name'] for j in J], geom=[g['name'] for g in G],
                  site=[s['name'] for s in S], actuator=[a['name'] for a in acts],
-                 tendon=[t['name'] for t in tendons], sensor=[s['name'] for s in sens])
-  return _model.Model(F, names, ordered)
+                 tendon=[t['name'] for t in tendons], sensor=[s['name'] for s in sens],
+                 camera=[cam['name'] for cam in c.cameras])
+  return _model.Model(F, names, ordered, vis=_visual_tables(c, root, F, G, S))
+
+
+def _visual_tables(c, root, F, G, S):
+  """What a renderer needs and the physics does not: colours, visibility groups, cameras, the model's extent.
+
+  Stands where mjModel's geom_rgba / geom_group / site_* / cam_* / vis.global / stat.{center,extent} stand in the
+  reference (read by engine.py:642-946 through MuJoCo's mjv_updateScene); consumed by dm_control_b200/render.py."""
+  glob = {}
+  for v in root.findall('visual'):
+    for g in v.findall('global'):
+      glob.update(g.attrib)
+  fovy0 = float(glob.get('fovy', 45))
+  ncam = len(c.cameras)
+  xpos0, xquat0, _, _ = _kin0(F, F['qpos0'])
+  cam_pos0, cam_mat0 = np.zeros((ncam, 3)), np.zeros((ncam, 9))
+  cam_poscom0 = np.zeros((ncam, 3))
+  # subtree centres of mass at qpos0 (trackcom cameras keep their world offset from it)
+  nbody = len(c.bodies)
+  ipos0 = np.stack([xpos0[b] + rot_vec(xquat0[b], F['body_ipos'][b]) for b in range(nbody)]) if nbody else np.zeros((0, 3))
+  msum = np.asarray(F['body_mass'], dtype=np.float64).copy()
+  mpos = ipos0 * msum[:, None]
+  for b in range(nbody - 1, 0, -1):
+    p = F['body_parentid'][b]
+    msum[p] += msum[b]; mpos[p] += mpos[b]
+  scom0 = np.where(msum[:, None] > 0, mpos / np.maximum(msum[:, None], 1e-300), xpos0)
+  for k, cam in enumerate(c.cameras):
+    b = cam['body']
+    cam_pos0[k] = xpos0[b] + rot_vec(xquat0[b], cam['pos'])
+    cam_mat0[k] = quat_to_mat(quat_mul(xquat0[b], cam['quat'])).reshape(-1)
+    cam_poscom0[k] = cam_pos0[k] - scom0[b]
+  # extent / centre from the geoms' bounding spheres at qpos0 (MuJoCo: mj_setConst -> stat.center, stat.extent)
+  if G:
+    gp = np.stack([xpos0[g['body']] + rot_vec(xquat0[g['body']], g['pos']) for g in G])
+    rb = np.array([0.0 if g['type'] == 0 else _geom_rbound(g['type'], g['size']) for g in G])
+    lo, hi = (gp - rb[:, None]).min(0), (gp + rb[:, None]).max(0)
+    center = 0.5 * (lo + hi)
+    extent = float(max(0.5 * np.linalg.norm(hi - lo), 1e-5))
+  else:
+    center, extent = np.zeros(3), 1.0
+  stat = {}
+  for st in root.findall('statistic'):
+    stat.update(st.attrib)
+  if 'extent' in stat:
+    extent = float(stat['extent'])
+  if 'center' in stat:
+    center = _floats(stat['center'], 3)
+  return dict(
+      geom_rgba=np.array([g['rgba'] for g in G], dtype=np.float32).reshape(-1, 4),
+      geom_group=np.array([g['group'] for g in G], dtype=np.int32),
+      site_rgba=np.array([s_['rgba'] for s_ in S], dtype=np.float32).reshape(-1, 4),
+      site_group=np.array([s_['group'] for s_ in S], dtype=np.int32),
+      cam_bodyid=np.array([cam['body'] for cam in c.cameras], dtype=np.int32),
+      cam_mode=np.array([cam['mode'] for cam in c.cameras], dtype=np.int32),
+      cam_targetbodyid=np.array([c.names['body'].get(cam['target'], -1) if cam['target'] else -1 for cam in c.cameras], dtype=np.int32),
+      cam_pos=np.array([cam['pos'] for cam in c.cameras], dtype=np.float64).reshape(-1, 3),
+      cam_quat=np.array([cam['quat'] for cam in c.cameras], dtype=np.float64).reshape(-1, 4),
+      cam_fovy=np.array([cam['fovy'] if cam['fovy'] is not None else fovy0 for cam in c.cameras], dtype=np.float64),
+      cam_pos0=cam_pos0 - (xpos0[[cam['body'] for cam in c.cameras]] if ncam else np.zeros((0, 3))),
+      cam_poscom0=cam_poscom0, cam_mat0=cam_mat0,
+      global_fovy=np.array([fovy0]), stat_center=np.asarray(center, dtype=np.float64), stat_extent=np.array([extent]))
 
 
 def _arr(rows, width):

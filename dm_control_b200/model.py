@@ -42,7 +42,7 @@ NOPTI = len(_OPTI) - 1
 
 # MuJoCo mjtObj names accepted by name2id/id2name (reference: wrapper/core.py:334-387)
 _OBJ_ALIASES = dict(body='body', xbody='body', joint='joint', geom='geom', site='site', actuator='actuator',
-                    tendon='tendon', sensor='sensor', equality='equality', key='key')
+                    tendon='tendon', sensor='sensor', equality='equality', key='key', camera='camera')
 
 
 class _Opt:
@@ -84,7 +84,9 @@ class _Opt:
 class Model:
   """Compiled model: numpy tables keyed by MuJoCo field names."""
 
-  def __init__(self, fields, names, ordered_names):
+  def __init__(self, fields, names, ordered_names, vis=None):
+    # visual-only tables (colours, groups, cameras, extent): rendering hand-off, never part of the physics blob
+    self.vis = {k: np.asarray(v) for k, v in (vis or {}).items()}
     self.fields = {}
     for name, kind in FIELDS:
       arr = np.ascontiguousarray(fields[name], dtype=np.int32 if kind == 'i' else np.float64)
@@ -198,13 +200,15 @@ class Model:
     return np.ascontiguousarray(idata), np.ascontiguousarray(rdata)
 
   def copy(self):
-    return Model({k: v.copy() for k, v in self.fields.items()}, self.names, self.ordered_names)
+    return Model({k: v.copy() for k, v in self.fields.items()}, self.names, self.ordered_names,
+                 vis={k: v.copy() for k, v in self.vis.items()})
 
   # --- binary model I/O (stands where MJB save/load stands: wrapper/core.py:208-234,323-332) ---
   def save(self, path):
     import json
     meta = json.dumps(dict(names=self.names, ordered_names=self.ordered_names, layout=[f for f, _ in FIELDS]))
-    np.savez_compressed(path, __meta__=np.frombuffer(meta.encode(), dtype=np.uint8), **self.fields)
+    np.savez_compressed(path, __meta__=np.frombuffer(meta.encode(), dtype=np.uint8), **self.fields,
+                        **{'vis__' + k: v for k, v in self.vis.items()})
 
   @classmethod
   def load(cls, path):
@@ -212,7 +216,8 @@ class Model:
     with np.load(path) as z:
       meta = json.loads(bytes(z['__meta__']).decode())
       fields = {name: z[name] for name, _ in FIELDS if name in z}
+      vis = {k[len('vis__'):]: z[k] for k in z.files if k.startswith('vis__')}
     missing = [name for name, _ in FIELDS if name not in fields]
     if missing:
       raise ValueError(f'{path}: model file predates the current blob layout (missing {missing}); regenerate it')
-    return cls(fields, meta['names'], meta['ordered_names'])
+    return cls(fields, meta['names'], meta['ordered_names'], vis=vis)

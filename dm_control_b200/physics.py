@@ -270,6 +270,16 @@ class BatchedPhysics:
     from . import binding
     return binding.Binding(self, kind, names)
 
+  def render(self, height=240, width=320, camera_id=-1, depth=False, segmentation=False, **unsupported):
+    """`Physics.render` (engine.py:178-233), batched: [B,H,W,3] uint8 rgb, [B,H,W] float32 depth or [B,H,W,2] int32
+    segmentation of every environment, on the device (dm_control_b200/render.py; a ray caster, not MuJoCo's GL renderer:
+    overlays, scene options / callbacks and render flags are refused)."""
+    from . import render as _render
+    bad = [k for k, v in unsupported.items() if v]
+    if bad:
+      raise NotImplementedError(f'{bad} need MuJoCo\'s OpenGL renderer and are outside the rendering hand-off')
+    return _render.Camera(self, height=height, width=width, camera_id=camera_id).render(depth=depth, segmentation=segmentation)
+
   @property
   def is_dirty(self):
     return bool(getattr(self, '_bind_dirty', False))

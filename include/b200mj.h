@@ -15,6 +15,8 @@
  *   b200mj_contact_force  <- mujoco.mj_contactForce                                           mujoco/wrapper/core.py:546-551
  *   b200mj_subtree_vel    <- mujoco.mj_subtreeVel (after a position/velocity stage)           locomotion/walkers/legacy_base.py:179-186
  *   b200mj_model_set_variable_geoms <- the per-episode recompile of the composer arenas       composer/environment.py:378-383
+ *   b200mj_render         <- Physics.render / Camera.render (rgb, depth, segmentation)         mujoco/engine.py:178-233,840-946
+ *                            (a ray caster over the model's primitives: hand-off images, not MuJoCo's OpenGL pixels)
  *   b200mj_workspace_bytes / b200mj_envs_per_block / b200mj_describe / b200mj_launch_count : instrumentation
  *
  * Threading: a b200mj_model handle owns streams, events and the handover buffers of its last call — like a reference
@@ -116,6 +118,28 @@ int b200mj_step(const b200mj_model* m, const b200mj_io* io, int batch, int nstep
  * (the reference's reset()/after_reset() pass mjDSBL_ACTUATION, engine.py:325-333). */
 int b200mj_forward(const b200mj_model* m, const b200mj_io* io, int batch, int extra_disableflags, int flags,
                    void* stream);
+
+/* Rendering hand-off (dm_control_b200/render.py). One camera per environment looks at that environment's geoms and
+ * sites, whose world frames are outputs of b200mj_step / b200mj_forward (geom_xpos, geom_xmat, site_xpos, site_xmat).
+ * Objects are `nobj` primitives per environment (geoms first, then sites): type (mjtGeom), kind (mjtObj: 5 geom, 6 site),
+ * id within its kind, rgba (float), size (3 doubles; size_stride = doubles between environments, 0 when shared),
+ * pos [batch, nobj, 3], mat [batch, nobj, 9]; objects with visible[i] == 0 are skipped. Camera: cam_xpos [batch, 3],
+ * cam_xmat [batch, 9] (columns: right, up, backward — the camera looks along -z), vertical field of view `fovy` in
+ * degrees; the pixel <-> ray map is the inverse of the reference's camera matrix (engine.py:759-810). Any of the three
+ * outputs may be NULL: rgb uint8 [batch, H, W, 3] (headlight-shaded rgba, black background), depth float32
+ * [batch, H, W] (distance along the optical axis, `zfar` where nothing is hit; hits nearer than `znear` are clipped),
+ * seg int32 [batch, H, W, 2] = (object id, object kind), (-1, -1) for the background. */
+typedef struct b200mj_render_scene {
+  int nobj;
+  const int32_t* obj_type; const int32_t* obj_kind; const int32_t* obj_id; const uint8_t* visible;
+  const float* rgba;
+  const double* size; long long size_stride;
+  const double* pos; const double* mat;
+  const double* cam_xpos; const double* cam_xmat;
+  double fovy, znear, zfar;
+} b200mj_render_scene;
+int b200mj_render(const b200mj_render_scene* scene, int batch, int height, int width, uint8_t* rgb, float* depth, int32_t* seg,
+                  void* stream);
 
 /* End-to-end form with HOST buffers: copies ctrl_host [batch,nu] to the device, runs b200mj_step on the
  * device-resident io, copies `nobs` packed doubles per env (obs_dev -> obs_host) back, synchronises. */

@@ -1,0 +1,293 @@
+"""Rendering hand-off: the ray-cast `Physics.render` / `Camera` against the reference's own known-answers.
+
+CPU tier: the numpy oracle (oracle/render_oracle.py) and the compiler's camera tables are held to
+  * engine_test.py:64-80   testDepthRender        — nearest pixel 2.8 m, furthest 3.0 m (orthographic depth),
+  * engine_test.py:82-131  testSegmentationRender — geom / site ids and mjtObj types in the four corners, -1 at the centre,
+  * engine_test.py:228-275 testCameraMatrix       — a geom's centre, projected with `camera.matrix`, lands on a pixel that
+                                                     the segmentation image labels with that geom (two model cameras and
+                                                     the free camera, three image sizes),
+  * engine_test.py:304-331 — the exceptions.
+GPU tier (`-m gpu`): the CUDA kernel (b200mj_render through `BatchedPhysics.render`) reproduces the same pins and agrees
+with the oracle pixel by pixel on the humanoid (trackcom camera) and on the CMU corridor's egocentric camera with
+per-environment walls.
+
+The scenes are the reference's XML strings; the engine needs at least one degree of freedom, so the GPU twins add an
+invisible free body far away from the scene.
+"""
+import numpy as np
+import pytest
+
+from dm_control_b200 import mjcf_compile as mc
+from oracle import render_oracle as ro
+
+PLANE_AND_BOX = """
+<mujoco>
+  <worldbody>
+    <geom type="plane" pos="0 0 0" size="2 2 .1"/>
+    <geom type="box" size=".1 .1 .1" pos="0 0 .1"/>
+    <camera name="top" pos="0 0 3"/>
+    %s
+  </worldbody>
+</mujoco>
+"""
+BOX_FOUR_CORNERS = """
+<mujoco>
+  <visual>
+    <scale framelength="2"/>
+  </visual>
+  <worldbody>
+    <geom name="box0" type="box" size=".2 .2 .2" pos="-1 1 .1"/>
+    <geom name="box1" type="box" size=".2 .2 .2" pos="1 1 .1"/>
+    <site name="box2" type="box" size=".2 .2 .2" pos="1 -1 .1"/>
+    <site name="box3" type="box" size=".2 .2 .2" pos="-1 -1 .1"/>
+    <camera name="top" pos="0 0 3"/>
+    %s
+  </worldbody>
+</mujoco>
+"""
+TWO_GEOMS_TWO_CAMERAS = """
+<mujoco>
+  <visual>
+    <global fovy="55"/>
+  </visual>
+  <worldbody>
+    <light name="top" pos="0 0 1"/>
+    <geom name="red" pos=".2 0 0" size=".005" rgba="1 0 0 1"/>
+    <geom name="green" pos=".2 .2 .1" size=".005" rgba="0 1 0 1"/>
+    <camera name="cam0" pos="1 .5 1" zaxis="1 .5 1" fovy="20"/>
+    <camera name="cam1" pos=".1 .1 1" xyaxes="1 1 0 -1 0 0"/>
+    %s
+  </worldbody>
+</mujoco>
+"""
+# The free camera's default pose hangs on mjModel.stat.{center, extent}, which MuJoCo derives at compile time and this
+# compiler only estimates (geom bounding spheres at qpos0); the camera-matrix pin does not depend on the pose, so the
+# free-camera case uses an explicit one that sees both geoms.
+FREE_POSE = (np.array([0.2, 0.1, 0.05]), 0.6, 90.0, -45.0)
+# the engine needs nv > 0: an invisible free body, out of every camera's sight, gravity compensated by nothing (it falls; irrelevant)
+DUMMY = '<body name="dummy" pos="0 0 -50"><freejoint/><geom name="dummy" size=".01" rgba="0 0 0 0" contype="0" conaffinity="0"/></body>'
+
+
+def _static_frames(model):
+  """World frames of geoms / sites attached to the world body (all of the pinned scenes')."""
+  q2m = lambda q: ro.quat_to_mat(q).reshape(-1)
+  gx = np.asarray(model.geom_pos).reshape(-1, 3); gm = np.stack([q2m(q) for q in np.asarray(model.geom_quat).reshape(-1, 4)])
+  if model.nsite:
+    sx = np.asarray(model.site_pos).reshape(-1, 3); sm = np.stack([q2m(q) for q in np.asarray(model.site_quat).reshape(-1, 4)])
+  else:
+    sx, sm = np.zeros((0, 3)), np.zeros((0, 9))
+  return gx, gm, sx, sm
+
+
+def _oracle_images(model, camera_id, height, width, free_pose=None):
+  vis = model.vis
+  gx, gm, sx, sm = _static_frames(model)
+  xpos = np.zeros((model.nbody, 3)); xmat = np.tile(np.eye(3).reshape(-1), (model.nbody, 1))
+  if camera_id == -1:
+    lookat, dist, az, el = free_pose or (vis['stat_center'], 1.5 * vis['stat_extent'][0], 90.0, -45.0)
+    cp, cm = ro.free_camera_pose(lookat, dist, az, el)
+    fovy = float(vis['global_fovy'][0])
+  else:
+    cp, cm = ro.camera_pose(vis, camera_id, xpos, xmat, xpos)
+    fovy = float(vis['cam_fovy'][camera_id])
+  rgb, depth, seg = ro.render(vis, np.asarray(model.geom_type), np.asarray(model.geom_size).reshape(-1, 3), gx, gm,
+                              np.asarray(model.site_type), np.asarray(model.site_size).reshape(-1, 3), sx, sm, cp, cm, fovy, height, width)
+  return rgb, depth, seg, (cp, cm, fovy)
+
+
+# ---- CPU tier: oracle + compiler against the reference's known-answers ------------------------------------------------
+
+def test_oracle_depth_render_pin():
+  model = mc.compile_xml(PLANE_AND_BOX % '')
+  _, depth, _, _ = _oracle_images(model, model.name2id('top', 'camera'), 200, 200)
+  np.testing.assert_approx_equal(depth.min(), 2.8, 3)      # engine_test.py:77-78
+  np.testing.assert_approx_equal(depth.max(), 3.0, 3)      # engine_test.py:79-80 (depth is orthographic)
+
+
+def _check_segmentation_pin(pixels, model):
+  np.testing.assert_equal(pixels[95:105, 95:105, 0], -1)
+  np.testing.assert_equal(pixels[95:105, 95:105, 1], -1)
+  np.testing.assert_equal(pixels[15:25, 0:10, 1], ro.OBJ_GEOM)
+  np.testing.assert_equal(pixels[15:25, 190:200, 1], ro.OBJ_GEOM)
+  np.testing.assert_equal(pixels[190:200, 190:200, 1], ro.OBJ_SITE)
+  np.testing.assert_equal(pixels[190:200, 0:10, 1], ro.OBJ_SITE)
+  np.testing.assert_equal(pixels[15:25, 0:10, 0], model.name2id('box0', 'geom'))
+  np.testing.assert_equal(pixels[15:25, 190:200, 0], model.name2id('box1', 'geom'))
+  np.testing.assert_equal(pixels[190:200, 190:200, 0], model.name2id('box2', 'site'))
+  np.testing.assert_equal(pixels[190:200, 0:10, 0], model.name2id('box3', 'site'))
+
+
+def test_oracle_segmentation_render_pin():
+  model = mc.compile_xml(BOX_FOUR_CORNERS % '')
+  _, _, seg, _ = _oracle_images(model, 0, 200, 200)
+  _check_segmentation_pin(seg, model)                     # engine_test.py:104-126
+
+
+@pytest.mark.parametrize('camera_id,height,width', [('cam0', 200, 300), (1, 300, 200), (-1, 400, 400)])
+def test_oracle_camera_matrix_pin(camera_id, height, width):
+  model = mc.compile_xml(TWO_GEOMS_TWO_CAMERAS % '')
+  cid = model.name2id(camera_id, 'camera') if isinstance(camera_id, str) else camera_id
+  _, _, seg, (cp, cm, fovy) = _oracle_images(model, cid, height, width, free_pose=FREE_POSE)
+  image, focal, rotation, translation = ro.camera_matrix(cp, cm, fovy, height, width)
+  cam = image @ focal @ rotation @ translation
+  gx = np.asarray(model.geom_pos).reshape(-1, 3)
+  for geom_id in (0, 1):
+    xs, ys, s = cam.dot(np.array([*gx[geom_id], 1.0]))      # xyz2pixels, engine_test.py:243-246
+    row, column = int(round(ys / s)), int(round(xs / s))
+    assert tuple(seg[row, column]) == (geom_id, ro.OBJ_GEOM)
+
+
+def test_compiler_camera_tables():
+  model = mc.compile_xml(TWO_GEOMS_TWO_CAMERAS % '')
+  vis = model.vis
+  assert vis['cam_fovy'].tolist() == [20.0, 55.0] and float(vis['global_fovy'][0]) == 55.0
+  z = ro.quat_to_mat(vis['cam_quat'][0])[:, 2]
+  np.testing.assert_allclose(z, np.array([1, .5, 1]) / 1.5, atol=1e-12)          # zaxis="1 .5 1"
+  R = ro.quat_to_mat(vis['cam_quat'][1])
+  np.testing.assert_allclose(R[:, 0], np.array([1, 1, 0]) / np.sqrt(2), atol=1e-12)
+  np.testing.assert_allclose(vis['geom_rgba'][0], [1, 0, 0, 1])
+  with pytest.raises(ValueError):
+    model.name2id('nope', 'camera')
+
+
+def test_ray_primitives_against_closed_forms():
+  o = np.array([[0.0, 0, 5.0], [0.3, 0, 5.0], [2.0, 0, 5.0]]); d = np.tile([0.0, 0, -1.0], (3, 1))
+  t, n = ro.ray_primitive(2, np.array([1.0, 0, 0]), o, d, 1e-9)
+  np.testing.assert_allclose(t[:2], [4.0, 5 - np.sqrt(1 - 0.09)]); assert np.isinf(t[2])
+  t, _ = ro.ray_primitive(3, np.array([0.5, 1.0, 0]), o, d, 1e-9)           # capsule along z: cap top at 1.5
+  np.testing.assert_allclose(t[0], 3.5); assert np.isinf(t[2])
+  t, _ = ro.ray_primitive(5, np.array([0.5, 1.0, 0]), o, d, 1e-9)           # cylinder: flat cap at 1
+  np.testing.assert_allclose(t[:2], [4.0, 4.0])
+  t, n = ro.ray_primitive(6, np.array([0.5, 0.5, 0.25]), o, d, 1e-9)
+  np.testing.assert_allclose(t[:2], [4.75, 4.75]); np.testing.assert_allclose(n[0], [0, 0, 1])
+  t, _ = ro.ray_primitive(4, np.array([1.0, 1.0, 2.0]), o, d, 1e-9)         # ellipsoid, semi-axis 2 along z
+  np.testing.assert_allclose(t[0], 3.0)
+  t, _ = ro.ray_primitive(0, np.array([1.0, 1.0, 0.1]), o, d, 1e-9)         # finite plane |x| <= 1
+  np.testing.assert_allclose(t[:2], [5.0, 5.0]); assert np.isinf(t[2])
+  t, _ = ro.ray_primitive(0, np.array([0.0, 0.0, 0.1]), o, -d, 1e-9)        # from behind / pointing away: no hit
+  assert np.isinf(t).all()
+
+
+# ---- GPU tier ---------------------------------------------------------------------------------------------------------
+
+def _gpu_physics(xml, B=2):
+  import torch
+  from dm_control_b200.physics import BatchedPhysics
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  phys = BatchedPhysics(mc.compile_xml(xml), batch=B)
+  phys.forward()
+  return phys
+
+
+@pytest.mark.gpu
+def test_gpu_depth_render_pin():
+  phys = _gpu_physics(PLANE_AND_BOX % DUMMY)
+  pixels = phys.render(height=200, width=200, camera_id='top', depth=True)
+  assert tuple(pixels.shape) == (2, 200, 200) and str(pixels.dtype) == 'torch.float32'
+  for e in range(2):
+    np.testing.assert_approx_equal(float(pixels[e].min()), 2.8, 3)
+    np.testing.assert_approx_equal(float(pixels[e].max()), 3.0, 3)
+
+
+@pytest.mark.gpu
+def test_gpu_segmentation_render_pin():
+  phys = _gpu_physics(BOX_FOUR_CORNERS % DUMMY)
+  pixels = phys.render(height=200, width=200, camera_id='top', segmentation=True).cpu().numpy()
+  assert pixels.shape == (2, 200, 200, 2)
+  for e in range(2):
+    _check_segmentation_pin(pixels[e], phys.model)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('camera_id,height,width', [('cam0', 200, 300), (1, 300, 200), (-1, 400, 400)])
+def test_gpu_camera_matrix_pin(camera_id, height, width):
+  from dm_control_b200 import render
+  phys = _gpu_physics(TWO_GEOMS_TWO_CAMERAS % DUMMY)
+  camera = render.Camera(phys, width=width, height=height, camera_id=camera_id)
+  if camera_id == -1:
+    camera.set_pose(*FREE_POSE)
+  cam = camera.matrix.cpu().numpy()
+  pixels = camera.render(segmentation=True).cpu().numpy()
+  gx = phys.data.geom_xpos.reshape(2, -1, 3).cpu().numpy()
+  for e in range(2):
+    for geom_id in (0, 1):
+      xs, ys, s = cam[e].dot(np.array([*gx[e, geom_id], 1.0]))
+      row, column = int(round(ys / s)), int(round(xs / s))
+      assert tuple(pixels[e, row, column]) == (geom_id, render.OBJ_GEOM)
+
+
+@pytest.mark.gpu
+def test_gpu_render_exceptions():
+  from dm_control_b200 import render
+  phys = _gpu_physics(TWO_GEOMS_TWO_CAMERAS % DUMMY)
+  with pytest.raises(ValueError, match='Only one of depth or segmentation'):      # engine_test.py:327-330
+    phys.render(depth=True, segmentation=True)
+  with pytest.raises(ValueError):
+    render.Camera(phys, camera_id=2)                                              # engine_test.py:304-315
+  with pytest.raises(ValueError):
+    render.Camera(phys, camera_id=-2)
+  with pytest.raises(NotImplementedError):
+    phys.render(overlays=('x',))
+  img = phys.render(height=48, width=64)                                          # engine_test.py:317-325: the Physics method
+  assert tuple(img.shape) == (2, 48, 64, 3) and str(img.dtype) == 'torch.uint8'
+  cam = render.Camera(phys, 24, 32)
+  before = cam.render().clone()
+  pose = cam.get_pose()
+  cam.set_pose(pose.lookat + np.array([0.01, 0.02, -0.03]), pose.distance * 1.5, pose.azimuth - 15, pose.elevation - 10)
+  assert cam.get_pose().distance == pose.distance * 1.5                           # engine_test.py:277-302
+  assert not bool((before == cam.render()).all())
+
+
+def _compare_with_oracle(phys, camera_id, H, W, envs):
+  """kernel vs numpy restatement on the engine's own frames: labels equal on all but silhouette pixels, depth to 1e-5."""
+  from dm_control_b200 import render
+  m, d, B = phys.model, phys.data, phys.batch
+  cam = render.Camera(phys, H, W, camera_id)
+  seg = cam.render(segmentation=True).cpu().numpy(); dep = cam.render(depth=True).cpu().numpy(); rgb = cam.render().cpu().numpy()
+  cp, cm = cam.pose()
+  cp, cm = cp.cpu().numpy(), cm.cpu().numpy()
+  sizes, stride = cam._sizes()
+  sizes = sizes.cpu().numpy()
+  gx = d.geom_xpos.reshape(B, -1, 3).cpu().numpy(); gm = d.geom_xmat.reshape(B, -1, 9).cpu().numpy()
+  sx = d.site_xpos.reshape(B, -1, 3).cpu().numpy(); sm = d.site_xmat.reshape(B, -1, 9).cpu().numpy()
+  for e in envs:
+    sz = sizes[e] if stride else sizes
+    o_rgb, o_dep, o_seg = ro.render(m.vis, np.asarray(m.geom_type), sz[:m.ngeom], gx[e], gm[e], np.asarray(m.site_type), sz[m.ngeom:],
+                                    sx[e], sm[e], cp[e], cm[e], cam._fovy, H, W)
+    same = (o_seg == seg[e]).all(-1)
+    assert same.mean() > 0.998, (e, same.mean())
+    assert (o_seg[..., 0] >= 0).mean() > 0.05                                    # the camera does see the model
+    np.testing.assert_allclose(dep[e][same], o_dep[same], rtol=2e-6, atol=1e-6)
+    assert np.abs(rgb[e][same].astype(int) - o_rgb[same].astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_gpu_render_matches_oracle_humanoid():
+  import torch
+  from dm_control_b200 import suite
+  env = suite.load('humanoid', 'run', batch=4, seed=1, outputs='all')
+  env.reset()
+  a = torch.zeros(4, env.physics.model.nu, dtype=torch.float64, device=env.physics.device)
+  for _ in range(3):
+    env.step(a)
+  phys = env.physics
+  ncam = int(phys.model.vis['cam_bodyid'].shape[0])
+  assert ncam >= 2                                                               # suite/humanoid.xml: back (trackcom), side (track)
+  for cid in range(ncam):
+    _compare_with_oracle(phys, cid, 60, 80, range(4))
+  _compare_with_oracle(phys, -1, 48, 48, [0])
+
+
+@pytest.mark.gpu
+def test_gpu_egocentric_camera_in_the_corridor():
+  """The CMU walker's head camera (cmu_humanoid.py:448-455) sees that environment's own walls (per-environment geoms)."""
+  import torch
+  from dm_control_b200 import locomotion
+  env = locomotion.load('cmu_humanoid_run_walls', batch=3, seed=2, egocentric_camera=True)
+  ts = env.reset()
+  img = ts.observation['walker/egocentric_camera']
+  assert tuple(img.shape) == (3, 64, 64, 3) and str(img.dtype) == 'torch.uint8'
+  assert not bool((img[0] == img[1]).all())                                     # different walls, different images
+  phys = env.physics
+  _compare_with_oracle(phys, phys.model.name2id('egocentric', 'camera'), 64, 64, range(3))
