@@ -1810,21 +1810,18 @@ __device__ __forceinline__ void dual_prepare(const Ctx& c, int nefc) {
   __syncwarp();
 }
 
-// grad, |grad|; search = -H^-1 grad through the dual form. Returns |grad|.
-__device__ __forceinline__ double newton_direction_dual(const Ctx& c, int nefc, int nact, bool refactor) {
+// search = -H^-1 grad through the dual form (grad: newton_gradient)
+__device__ __forceinline__ void newton_direction_dual(const Ctx& c, int nefc, int nact, bool refactor) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
   const int* alist = reinterpret_cast<const int*>(W(actlist));
   double* A = W(dS); double* S = A + nefc * nefc; double* sdinv = S + tri(c.L.drows); double* t = sdinv + c.L.drows; double* y = t + c.L.drows;
-  double gpart = 0;
   FOR_LANES(i, nv) {
-    const double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; gpart += g * g; W(grad)[i] = g;
     double u0 = W(qacc)[i] - W(qaccs)[i], u1 = 0;
     int a = 0;
     _Pragma("unroll 1") for (; a + 2 <= nact; a += 2) { const int r0 = alist[a], r1 = alist[a + 1]; u0 -= W(dV)[r0 * ld + i] * W(force)[r0]; u1 -= W(dV)[r1 * ld + i] * W(force)[r1]; }
     if (a < nact) { const int r0 = alist[a]; u0 -= W(dV)[r0 * ld + i] * W(force)[r0]; }
     W(tmpv)[i] = u0 + u1;
   }
-  const double gnorm = sqrt(warp_sum(gpart));
   __syncwarp();
   if (nact > 0) {
     FOR_LANES(a, nact) t[a] = dot_rows(W(J) + alist[a] * ld, W(tmpv), nv);
@@ -1852,24 +1849,29 @@ __device__ __forceinline__ double newton_direction_dual(const Ctx& c, int nefc, 
     W(search)[i] = -(s0 + s1); W(Mv)[i] = -(m0 + m1);
   }
   __syncwarp();
+}
+
+// (re)assemble H = M + J^T diag(SD) J and factor it only when the active set changed; search = -H^-1 grad.
+// The gradient comes first and alone: the stopping tests need only its norm, so the trip that ends the iteration
+// (one per physics step) skips the factorisation / substitutions of a direction nobody would use.
+__device__ __forceinline__ double newton_gradient(const Ctx& c) {
+  const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
+  double gpart = 0;
+  FOR_LANES(i, nv) { double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; W(grad)[i] = g; gpart += g * g; }
+  const double gnorm = sqrt(warp_sum(gpart));
+  __syncwarp();
   return gnorm;
 }
 
-// grad; (re)assemble H = M + J^T diag(SD) J and factor it only when the active set changed; search = -H^-1 grad.
-// Returns |grad|.
 template <int NVT>
-__device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int nact, bool refactor) {
+__device__ __forceinline__ void newton_direction(const Ctx& c, int nefc, int nact, bool refactor) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
-  if constexpr (NVT == 0) { if (c.L.dual) return newton_direction_dual(c, nefc, nact, refactor); }
-  double gpart = 0;
-  FOR_LANES(i, nv) { double g = W(Ma)[i] - W(smooth)[i] - W(qcon)[i]; W(grad)[i] = g; gpart += g * g; }
-  double gnorm = sqrt(warp_sum(gpart));
+  if constexpr (NVT == 0) { if (c.L.dual) { newton_direction_dual(c, nefc, nact, refactor); return; } }
   if constexpr (NVT > 0) {
-    __syncwarp();
     if (refactor) tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(grad), W(search), W(J), W(efcSD), reinterpret_cast<const int*>(W(actlist)), nact, W(colbuf));
     else tn_forward<NVT>(W(H), W(dinv), W(grad), W(search), lane);
     tn_back<NVT>(W(H), W(dinv), W(search), W(search), lane, 1);
-    return gnorm;
+    return;
   }
   if (refactor) {
     const int* alist = reinterpret_cast<const int*>(W(actlist));
@@ -1897,7 +1899,6 @@ __device__ __forceinline__ double newton_direction(const Ctx& c, int nefc, int n
   chol_back(W(H), W(dinv), W(search), W(search), nv, lane);
   FOR_LANES(i, nv) W(search)[i] = -W(search)[i];
   __syncwarp();
-  return gnorm;
 }
 
 __device__ __forceinline__ void ls_eval(const Ctx& c, int nefc, double alpha, const double* qg, double* d1, double* d2) {
@@ -2012,7 +2013,7 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
     // every warp of the CTA takes the same number of trips: finished environments idle at the barrier
     if (c.sync_level >= 3) { if (!__syncthreads_or(!done)) break; } else if (done) break;
     if (!done) {
-      double gnorm = newton_direction<NVT>(c, nefc, pr.nact, refactor);
+      const double gnorm = newton_gradient(c);
       bool stop = false;
       if (iter > 0) {
         double improvement = scale * (oldcost - pr.cost), gradient = scale * gnorm;
@@ -2020,7 +2021,7 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
       }
       if (iter >= m.iterations) stop = true;
       double alpha = 0;
-      if (!stop) { alpha = line_search<NVT>(c, nefc, pr); if (alpha == 0) stop = true; }
+      if (!stop) { newton_direction<NVT>(c, nefc, pr.nact, refactor); alpha = line_search<NVT>(c, nefc, pr); if (alpha == 0) stop = true; }
       if (stop) done = true;
       else {
         FOR_LANES(i, nv) { W(qacc)[i] += alpha * W(search)[i]; W(Ma)[i] += alpha * W(Mv)[i]; }
