@@ -70,6 +70,7 @@ struct Lay {
   int bias, passive, qfact, smooth, qaccs, qacc, qcon, Ma, grad, search, Mv, tmpv;
   int con;                               // contact records, 16 doubles each
   int cq;                                // collision: queue of candidate pairs that passed the bounding tests (64 ints)
+  int gcache, grb, gmg, gty;             // collision, models with many candidate pairs per geom: per-geom bounding radius / margin / type staged once per step
   int rk;                                // RK4 scratch: X0q, X0v, X0a, accv, acca, accd
   int sens;                              // sensordata staging
   int vold;                              // last-step acceleration kernel: qvel before integration (for rne_post_constraint)
@@ -1281,6 +1282,15 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
   // in any one step (CMU corridor: 2 113 candidates, a few dozen survivors), and the narrow phase is divergent code: run
   // per 32 candidates, every chunk with one survivor paid for a whole pass. Contacts come out in pair order as before.
   int* queue = reinterpret_cast<int*>(W(cq));
+  // With many candidate pairs per geom the per-pair chain  pair -> geom -> (type, margin, size / per-environment size ->
+  // bounding radius)  through global memory is what the bounding tests wait for (long-scoreboard stalls 4.1 per issue in
+  // the CMU corridor capture): stage the three per-geom quantities in shared memory once.
+  const bool gc = c.L.gcache != 0;
+  int* gty = reinterpret_cast<int*>(W(gty));
+  if (gc) {
+    FOR_LANES(g, m.ngeom) { double sz[3]; W(grb)[g] = geom_size_of(c, g, sz); W(gmg)[g] = m.geom_margin[g]; gty[g] = m.geom_type[g]; }
+    __syncwarp();
+  }
   int qn = 0, base = 0;
   _Pragma("unroll 1") while (base < m.npair || qn > 0) {
     _Pragma("unroll 1") while (qn < 32 && base < m.npair) {
@@ -1288,13 +1298,15 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
       bool keep = false;
       if (p < m.npair) {
         const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
-        const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-        const double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
+        const int t1 = gc ? gty[g1] : m.geom_type[g1], t2 = gc ? gty[g2] : m.geom_type[g2];
+        const double margin = gc ? fmax(W(gmg)[g1], W(gmg)[g2]) : fmax(m.geom_margin[g1], m.geom_margin[g2]);
         const double* p1 = W(gxpos) + 3 * g1; const double* p2 = W(gxpos) + 3 * g2;
         const double* m1 = W(gxmat) + 9 * g1; const double* m2 = W(gxmat) + 9 * g2;
         double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
         double s1[3], s2[3];
-        const double rb1 = geom_size_of(c, g1, s1), rb2 = geom_size_of(c, g2, s2);
+        double rb1, rb2;
+        if (gc) { rb1 = W(grb)[g1]; rb2 = W(grb)[g2]; }      // sizes: only boxes that pass the sphere test need them (below)
+        else { rb1 = geom_size_of(c, g1, s1); rb2 = geom_size_of(c, g2, s2); }
         if (t1 == BMJ_GEOM_PLANE) {
           double nr[3] = {m1[2], m1[5], m1[8]};
           keep = dot3(dif, nr) <= rb2 + margin;
@@ -1304,11 +1316,13 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
           // boxes (corridor walls: long, thin, with a bounding sphere that reaches most of the walker): the other geom's
           // bounding sphere against the box's slabs, in the box frame — conservative, so the contact set is unchanged
           if (keep && t2 == BMJ_GEOM_BOX) {
+            if (gc) geom_size_of(c, g2, s2);
             double loc[3]; matT_vec(loc, m2, dif);
             const double r = rb1 + margin;
             keep = fabs(loc[0]) <= s2[0] + r && fabs(loc[1]) <= s2[1] + r && fabs(loc[2]) <= s2[2] + r;
           }
           if (keep && t1 == BMJ_GEOM_BOX) {
+            if (gc) geom_size_of(c, g1, s1);
             double loc[3]; matT_vec(loc, m1, dif);
             const double r = rb2 + margin;
             keep = fabs(loc[0]) <= s1[0] + r && fabs(loc[1]) <= s1[1] + r && fabs(loc[2]) <= s1[2] + r;
@@ -2893,6 +2907,8 @@ static void build_layout(b200mj_model* M) {
   L.bias = take(nv); L.passive = take(nv); L.qfact = take(nv); L.smooth = take(nv); L.qaccs = take(nv); L.qacc = take(nv);
   L.qcon = take(nv); L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv); L.tmpv = take(nv);
   L.con = take(m.nconmax * CON_STRIDE); L.cq = take(m.npair > 0 ? 32 : 0);
+  L.gcache = (m.npair >= 16 * m.ngeom && m.ngeom > 0) ? 1 : 0;
+  L.grb = take(L.gcache ? m.ngeom : 0); L.gmg = take(L.gcache ? m.ngeom : 0); L.gty = take(L.gcache ? (m.ngeom + 1) / 2 : 0);
   L.rk = take(m.integrator == BMJ_INT_RK4 ? (m.nq + 3 * nv + 2 * m.na + 8) : 0);
   L.sens = take(m.nsensordata);
   const bool pgs = m.solver == BMJ_SOL_PGS;
@@ -2940,6 +2956,8 @@ static void build_layout(b200mj_model* M) {
     }
     P.tenlen = take(m.ntendon); P.tenJ = take(m.ntendon * ld);
     P.con = take(m.nconmax * CON_STRIDE); P.cq = take(m.npair > 0 ? 32 : 0);
+    P.gcache = (m.npair >= 16 * m.ngeom && m.ngeom > 0) ? 1 : 0;      // CMU corridor: 2 113 pairs over 73 geoms
+    P.grb = take(P.gcache ? m.ngeom : 0); P.gmg = take(P.gcache ? m.ngeom : 0); P.gty = take(P.gcache ? (m.ngeom + 1) / 2 : 0);
     P.total = o;
     M->smem_pos = (size_t)o * sizeof(double);
     // dual form of the Newton direction in the runtime-size kernels (B200MJ_DUAL_MIN_NV, default 32: the two-rows-per-lane

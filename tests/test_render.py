@@ -231,8 +231,10 @@ def test_gpu_render_exceptions():
     phys.render(overlays=('x',))
   img = phys.render(height=48, width=64)                                          # engine_test.py:317-325: the Physics method
   assert tuple(img.shape) == (2, 48, 64, 3) and str(img.dtype) == 'torch.uint8'
-  cam = render.Camera(phys, 24, 32)
+  cam = render.Camera(phys, 96, 128)
+  cam.set_pose(FREE_POSE[0], 0.3, 90.0, -45.0)                                    # 3 mm pixels: the 5 mm spheres cover some
   before = cam.render().clone()
+  assert int(before.max()) > 0
   pose = cam.get_pose()
   cam.set_pose(pose.lookat + np.array([0.01, 0.02, -0.03]), pose.distance * 1.5, pose.azimuth - 15, pose.elevation - 10)
   assert cam.get_pose().distance == pose.distance * 1.5                           # engine_test.py:277-302
@@ -250,11 +252,14 @@ def _compare_with_oracle(phys, camera_id, H, W, envs):
   sizes, stride = cam._sizes()
   sizes = sizes.cpu().numpy()
   gx = d.geom_xpos.reshape(B, -1, 3).cpu().numpy(); gm = d.geom_xmat.reshape(B, -1, 9).cpu().numpy()
-  sx = d.site_xpos.reshape(B, -1, 3).cpu().numpy(); sm = d.site_xmat.reshape(B, -1, 9).cpu().numpy()
+  if cam._sites:
+    sx = d.site_xpos.reshape(B, -1, 3).cpu().numpy(); sm = d.site_xmat.reshape(B, -1, 9).cpu().numpy()
+  else:
+    sx, sm = np.zeros((B, 0, 3)), np.zeros((B, 0, 9))
   for e in envs:
     sz = sizes[e] if stride else sizes
     o_rgb, o_dep, o_seg = ro.render(m.vis, np.asarray(m.geom_type), sz[:m.ngeom], gx[e], gm[e], np.asarray(m.site_type), sz[m.ngeom:],
-                                    sx[e], sm[e], cp[e], cm[e], cam._fovy, H, W)
+                                    sx[e], sm[e], cp[e], cm[e], cam._fovy, H, W, sites=cam._sites)
     same = (o_seg == seg[e]).all(-1)
     assert same.mean() > 0.998, (e, same.mean())
     assert (o_seg[..., 0] >= 0).mean() > 0.05                                    # the camera does see the model
@@ -290,4 +295,4 @@ def test_gpu_egocentric_camera_in_the_corridor():
   assert tuple(img.shape) == (3, 64, 64, 3) and str(img.dtype) == 'torch.uint8'
   assert not bool((img[0] == img[1]).all())                                     # different walls, different images
   phys = env.physics
-  _compare_with_oracle(phys, phys.model.name2id('egocentric', 'camera'), 64, 64, range(3))
+  _compare_with_oracle(phys, phys.model.name2id('egocentric', 'camera'), 64, 64, range(3))      # (this physics materialises no site frames)
