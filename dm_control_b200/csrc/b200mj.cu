@@ -51,6 +51,9 @@ struct DevModel {
   // actuator moments by dof (CSR, built by b200mj_model_create): joint and fixed-tendon transmissions have constant
   // moment arms, so qfrc_actuator[i] = sum over dof_act_id[dof_act_adr[i] .. dof_act_adr[i+1]) of coef * force
   const int* dof_act_adr; const int* dof_act_id; const double* dof_act_coef;
+  // dof tree (b200mj_model_create): ancestors of dof k, nearest first, at dof_anc_id[dof_anc_adr[k] .. dof_anc_adr[k+1]);
+  // dof_subsize[i] = dofs in the subtree of i, itself included (dofs are numbered depth-first: the subtree is i .. i+size-1)
+  const int* dof_anc_adr; const int* dof_anc_id; const int* dof_subsize;
   // per-environment geoms (b200mj_model_set_variable_geoms): geom_varid[g] = slot k of io.var_geom_pos / var_geom_size, or -1
   const int* geom_varid; int nvargeom;
   int ldv;          // padded row length of nv-wide matrices (odd => conflict-free column walks)
@@ -81,6 +84,7 @@ struct Lay {
   // active block R + A_aa and its right-hand side (aliases H, which is free between chol(M) and the Euler step)
   int dual, dV, dS, drows;
   int mglobal;                           // runtime-size acceleration kernels, nv >= 32: M stays in the handover row (no workspace copy)
+  int sparse;                            // ... and M, M + h B are factored as tree-sparse L'DL (ldl_factor) instead of dense Cholesky
   int total;
 };
 
@@ -583,6 +587,96 @@ __device__ __noinline__ void chol_solve_multi(const double* Lm, const double* di
     }
   }
   __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tree-sparse L'DL of the joint-space inertia (what mj_factorM / mj_solveM do, O(sum depth^2) instead of O(nv^3)).
+// M[i][j] != 0 only when j is an ancestor of i in the dof tree, and eliminating dofs from the leaves up creates no
+// fill-in: M = L' D L with L unit lower triangular of the same pattern. For the CMU humanoid (62 dofs, depth <= 25)
+// that is 8 288 multiply-adds against 39 721 for the dense factorisation, and the substitutions walk 890 entries
+// instead of 1 953. The factor lives in the same packed lower triangle as the dense one; entries off the tree are never
+// touched. Stored: H[k][k] = D_k, H[k][i] = L[k][i] D_k (unscaled: the scaling by dinv[k] = 1 / D_k happens on use, which
+// saves a barrier per eliminated dof).
+//   ldl_factor: for k = nv-1 .. 0, the rank-1 update of k's ancestor block, lanes over the (ancestor, ancestor) pairs;
+//   ldl_solve:  L' pass (k descending, lanes over k's ancestors), D^-1, L pass (i ascending, lanes over i's subtree).
+// Used by the runtime-size acceleration kernels for nv >= 32 (c.L.sparse): M for qacc_smooth and the rows of J M^-1 of the
+// dual Newton form, M + h B for the Euler step. The Newton Hessian itself is dense (two touching limbs couple).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tri_pair(int p, int& a, int& b) {      // p = b (b + 1) / 2 + a, a <= b
+  b = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+  while (((b + 1) * (b + 2)) >> 1 <= p) b++;
+  while ((b * (b + 1)) >> 1 > p) b--;
+  a = p - ((b * (b + 1)) >> 1);
+}
+
+__device__ __noinline__ void ldl_factor(const DevModel& m, double* H, double* dinv, int nv, int lane) {
+  _Pragma("unroll 1") for (int k = nv - 1; k >= 0; k--) {
+    const int a0 = m.dof_anc_adr[k], d = m.dof_anc_adr[k + 1] - a0;
+    const int* A = m.dof_anc_id + a0;
+    double* Hk = H + tri(k);
+    double Dk = Hk[k];
+    if (Dk < BMJ_MINVAL) Dk = BMJ_MINVAL;
+    const double inv = 1.0 / Dk;
+    if (lane == 0) dinv[k] = inv;
+    const int np = (d * (d + 1)) >> 1;
+    _Pragma("unroll 1") for (int p = lane; p < np; p += 32) {
+      int a, b; tri_pair(p, a, b);
+      const int i = A[a], j = A[b];      // j is i itself or one of its ancestors: j <= i < k
+      H[tri(i) + j] -= Hk[i] * inv * Hk[j];
+    }
+    __syncwarp();
+  }
+}
+
+// M x = b in place (x holds b on entry)
+__device__ __noinline__ void ldl_solve(const DevModel& m, const double* H, const double* dinv, double* x, int nv, int lane) {
+  __syncwarp();
+  _Pragma("unroll 1") for (int k = nv - 1; k > 0; k--) {        // x <- L^-T x
+    const int a0 = m.dof_anc_adr[k], d = m.dof_anc_adr[k + 1] - a0;
+    if (d == 0) continue;
+    const int* A = m.dof_anc_id + a0;
+    const double* Hk = H + tri(k);
+    const double xk = x[k] * dinv[k];
+    FOR_LANES(a, d) { const int i = A[a]; x[i] -= Hk[i] * xk; }
+    __syncwarp();
+  }
+  FOR_LANES(i, nv) x[i] *= dinv[i];
+  __syncwarp();
+  _Pragma("unroll 1") for (int i = 0; i < nv - 1; i++) {        // x <- L^-1 x: a finished x_i is pushed to its subtree
+    const int sz = m.dof_subsize[i];
+    if (sz <= 1) continue;
+    const double xi = x[i];
+    _Pragma("unroll 1") for (int k = i + 1 + lane; k < i + sz; k += 32) x[k] -= H[tri(k) + i] * dinv[k] * xi;
+    __syncwarp();
+  }
+}
+
+// M X = B for K right-hand sides (rows of stride ld), in place: the same three passes with lanes over (entry, right-hand side)
+__device__ __noinline__ void ldl_solve_multi(const DevModel& m, const double* H, const double* dinv, double* X, int ld, int K, int nv, int lane) {
+  int sh = 0;
+  while ((1 << sh) < K) sh++;                       // right-hand sides padded to a power of two: lane = (entry, rhs)
+  const int r = lane & ((1 << sh) - 1), e0 = lane >> sh, ne = 32 >> sh;
+  const bool on = r < K;
+  double* Xr = X + (on ? r : 0) * ld;
+  __syncwarp();
+  _Pragma("unroll 1") for (int k = nv - 1; k > 0; k--) {
+    const int a0 = m.dof_anc_adr[k], d = m.dof_anc_adr[k + 1] - a0;
+    if (d == 0) continue;
+    const int* A = m.dof_anc_id + a0;
+    const double* Hk = H + tri(k);
+    const double xk = on ? Xr[k] * dinv[k] : 0.0;
+    _Pragma("unroll 1") for (int a = e0; a < d; a += ne) if (on) { const int i = A[a]; Xr[i] -= Hk[i] * xk; }
+    __syncwarp();
+  }
+  _Pragma("unroll 1") for (int i = e0; i < nv; i += ne) if (on) Xr[i] *= dinv[i];
+  __syncwarp();
+  _Pragma("unroll 1") for (int i = 0; i < nv - 1; i++) {
+    const int sz = m.dof_subsize[i];
+    if (sz <= 1) continue;
+    const double xi = on ? Xr[i] : 0.0;
+    _Pragma("unroll 1") for (int k = i + 1 + e0; k < i + sz; k += ne) if (on) Xr[k] -= H[tri(k) + i] * dinv[k] * xi;
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1746,8 +1840,16 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
     tn_factor<NVT>(W(M), W(H), W(dinv), lane, W(smooth), W(qaccs), W(J), W(efcSD), reinterpret_cast<const int*>(W(actlist)), opaque_zero(), W(colbuf));
     tn_back<NVT>(W(H), W(dinv), W(qaccs), W(qaccs), lane, 0);
   } else {
-    chol_factor(c.Mc, W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
-    chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
+    if (c.L.sparse) {
+      copy_row(W(H), c.Mc, tri(nv), lane);
+      FOR_LANES(i, nv) W(qaccs)[i] = W(smooth)[i];
+      __syncwarp();
+      ldl_factor(m, W(H), W(dinv), nv, lane);
+      ldl_solve(m, W(H), W(dinv), W(qaccs), nv, lane);
+    } else {
+      chol_factor(c.Mc, W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
+      chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
+    }
   }
 }
 
@@ -1816,7 +1918,11 @@ __device__ __forceinline__ Primal constraint_update(const Ctx& c, int nefc) {
 // of ~5 x 5. Same iterates as the primal form up to rounding (tests/test_gpu_parity.py, tests/test_emu_kernel_parity.py).
 __device__ __forceinline__ void dual_prepare(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
-  chol_solve_multi(W(H), W(dinv), nv, W(J), W(dV), ld, nefc, lane);      // H holds chol(M) (fwd_acceleration)
+  if (c.L.sparse) {                                                      // H holds the factor of M (fwd_acceleration)
+    copy_row(W(dV), W(J), nefc * ld, lane);
+    ldl_solve_multi(m, W(H), W(dinv), W(dV), ld, nefc, nv, lane);
+    __syncwarp();
+  } else chol_solve_multi(W(H), W(dinv), nv, W(J), W(dV), ld, nefc, lane);
   double* A = W(dS);                                                    // may alias H: chol(M) is dead from here on
   _Pragma("unroll 1") for (int r = 0; r < nefc; r++) {
     if (lane <= r) { const double a = dot_rows(W(J) + r * ld, W(dV) + lane * ld, nv); A[r * nefc + lane] = a; A[lane * nefc + r] = a; }
@@ -2371,8 +2477,13 @@ __device__ __forceinline__ void euler_step(const Ctx& c, double* time) {
     __syncwarp();
     FOR_LANES(i, nv) W(H)[tri(i) + i] += h * m.dof_damping[i];
     __syncwarp();
-    chol_factor(W(H), W(H), W(dinv), nv, lane, W(tmpv), W(tmpv));
-    chol_back(W(H), W(dinv), W(tmpv), W(tmpv), nv, lane);
+    if (c.L.sparse) {
+      ldl_factor(m, W(H), W(dinv), nv, lane);
+      ldl_solve(m, W(H), W(dinv), W(tmpv), nv, lane);
+    } else {
+      chol_factor(W(H), W(H), W(dinv), nv, lane, W(tmpv), W(tmpv));
+      chol_back(W(H), W(dinv), W(tmpv), W(tmpv), nv, lane);
+    }
     FOR_LANES(i, nv) W(qvel)[i] += h * W(tmpv)[i];
   } else FOR_LANES(i, nv) W(qvel)[i] += h * W(qacc)[i];
   FOR_LANES(i, nv) W(qaccws)[i] = W(qacc)[i];
@@ -2965,8 +3076,13 @@ static void build_layout(b200mj_model* M) {
     int dual_min_nv = 32;
     if (const char* ev = getenv("B200MJ_DUAL_MIN_NV")) dual_min_nv = atoi(ev);
     auto tri_host = [](int i) { return (i * (i + 1)) / 2; };
-    int mglobal_on = 1;
+    // B200MJ_SPARSE_LDL=1: tree-sparse L'DL for M and M + h B (ldl_factor). OFF by default: measured SLOWER on the CMU corridor
+    // configuration (18.1 -> 20.0 ms per control step, profiles/r2_ab_s2_sparse_ldl.txt) although it executes a third of the
+    // multiply-adds — the kernel is bound by per-warp latency (1.5 warps per scheduler), and 62 dependent elimination steps of
+    // a few instructions each are a longer chain than 16 dense column blocks with eight independent accumulators.
+    int mglobal_on = 1, sparse_on = 0;
     if (const char* ev = getenv("B200MJ_M_GLOBAL")) mglobal_on = atoi(ev);
+    if (const char* ev = getenv("B200MJ_SPARSE_LDL")) sparse_on = atoi(ev);
     auto acc_layout = [&](Lay& A, int rows, bool with_sens) {
       memset(&A, 0, sizeof(A));
       o = 0;
@@ -2977,6 +3093,7 @@ static void build_layout(b200mj_model* M) {
       // storage for the position-stage dump that rne_post_constraint and the acceleration-stage sensors read.
       const int u0 = o;
       A.mglobal = (mglobal_on && !M->tn_nv && nv >= 32) ? 1 : 0;
+      A.sparse = (A.mglobal && sparse_on && m.dof_anc_adr) ? 1 : 0;
       A.M = take(A.mglobal ? 0 : ntri); A.H = take(ntri); A.dinv = take(nv);
       A.J = take(rows * ld); A.efcD = take(rows); A.efcSD = take(rows); A.aref = take(rows); A.jar = take(rows); A.jv = take(rows);
       A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
@@ -3190,13 +3307,39 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
     }
     adr[nv] = n;
     const int nn = n > 0 ? n : 1;
-    bool ok = cudaMalloc(&M->d_xi, (size_t)(nv + 1 + nn) * sizeof(int)) == cudaSuccess && cudaMalloc(&M->d_xr, (size_t)nn * sizeof(double)) == cudaSuccess;
+    // dof tree tables (ldl_factor / ldl_solve): ancestor lists, subtree sizes; valid when dofs are numbered depth-first
+    // (parent before child, subtrees contiguous), which the compiler guarantees — checked here, else the dense path stays
+    int* aadr = new int[nv + 1];
+    int* aid = new int[(size_t)nv * (nv > 0 ? nv : 1) / 2 + 1];
+    int* sub = new int[nv > 0 ? nv : 1];
+    int na = 0; bool tree_ok = true;
+    for (int k = 0; k < nv; k++) {
+      aadr[k] = na;
+      for (int i = hf.dof_parentid[k]; i >= 0; i = hf.dof_parentid[i]) { if (i >= k) { tree_ok = false; break; } aid[na++] = i; }
+      if (!tree_ok) break;
+      sub[k] = 1;
+    }
+    aadr[nv] = na;
+    if (tree_ok) {
+      for (int k = nv - 1; k >= 0; k--) if (hf.dof_parentid[k] >= 0) sub[hf.dof_parentid[k]] += sub[k];
+      for (int k = 0; k < nv && tree_ok; k++)      // contiguity: every dof in (k, k + sub[k]) must descend from k
+        for (int q = k + 1; q < k + sub[k]; q++) { int i = q; while (i > k) i = hf.dof_parentid[i]; if (i != k) { tree_ok = false; break; } }
+    }
+    const int naa = na > 0 ? na : 1;
+    bool ok = cudaMalloc(&M->d_xi, (size_t)(nv + 1 + nn + (nv + 1) + naa + (nv > 0 ? nv : 1)) * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&M->d_xr, (size_t)nn * sizeof(double)) == cudaSuccess;
+    int* d_aadr = M->d_xi + nv + 1 + nn; int* d_aid = d_aadr + nv + 1; int* d_sub = d_aid + naa;
     if (ok) ok = cudaMemcpy(M->d_xi, adr, (size_t)(nv + 1) * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
                  cudaMemcpy(M->d_xi + nv + 1, ids, (size_t)nn * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
                  cudaMemcpy(M->d_xr, coef, (size_t)nn * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
-    delete[] adr; delete[] ids; delete[] coef;
+    if (ok && tree_ok && nv > 0) ok = cudaMemcpy(d_aadr, aadr, (size_t)(nv + 1) * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(d_aid, aid, (size_t)naa * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(d_sub, sub, (size_t)nv * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    delete[] adr; delete[] ids; delete[] coef; delete[] aadr; delete[] aid; delete[] sub;
     if (!ok) { b200mj_model_destroy(M); return -2; }
     m.dof_act_adr = M->d_xi; m.dof_act_id = M->d_xi + nv + 1; m.dof_act_coef = M->d_xr;
+    if (tree_ok && nv > 0) { m.dof_anc_adr = d_aadr; m.dof_anc_id = d_aid; m.dof_subsize = d_sub; }
+    else { m.dof_anc_adr = nullptr; m.dof_anc_id = nullptr; m.dof_subsize = nullptr; }
   }
   M->nkey = h_sizes[BMJ_NKEY];
   M->tn_nv = tn_kernel(m.nv, false) ? m.nv : 0;
