@@ -83,6 +83,7 @@ struct Lay {
   // dV = rows of M^-1 J' [rows x ld]; dS = scratch [rows^2 + tri(rows) + 3 rows] for A = J M^-1 J', the factor of the
   // active block R + A_aa and its right-hand side (aliases H, which is free between chol(M) and the Euler step)
   int dual, dV, dS, drows;
+  int jalias;                            // dual form, small buckets: the workspace copy of J lives in H's storage (free once J M^-1 is there); J M^-1 is computed from the handover row
   int mglobal;                           // runtime-size acceleration kernels, nv >= 32: M stays in the handover row (no workspace copy)
   int sparse;                            // ... and M, M + h B are factored as tree-sparse L'DL (ldl_factor) instead of dense Cholesky
   int total;
@@ -241,12 +242,13 @@ struct Ctx {
   // where the position/velocity stage deposits what the acceleration stage consumes: the workspace itself in the
   // fused kernel, this environment's row of the L2-resident handover buffer in the split position kernel
   double *pM, *pJ, *pD, *pAref, *pBias, *pPassive; int* pEq; double* stage;
+  const double* Jg;     // acceleration stage: this environment's constraint Jacobian in the handover row (L.jalias)
   const double* Mc;     // acceleration stage: the joint-space inertia, read-only — the workspace copy, or (L.mglobal) the handover row in L2
   int env; const double* var_pos; const double* var_size;      // per-environment geoms (set_env)
   __device__ void set_env(int e, const b200mj_io& io) { env = e; var_pos = io.var_geom_pos; var_size = io.var_geom_size; }
   __device__ Ctx(const DevModel& m_, const Lay& L_, double* ws_, int lane_, int df, int sl) : m(m_), L(L_), ws(ws_), lane(lane_), disableflags(df), sync_level(sl), env(0), var_pos(nullptr), var_size(nullptr) {
     pM = ws_ + L_.M; pJ = ws_ + L_.J; pD = ws_ + L_.efcD; pAref = ws_ + L_.aref; pBias = ws_ + L_.bias; pPassive = ws_ + L_.passive;
-    pEq = reinterpret_cast<int*>(ws_ + L_.eqflag); stage = ws_ + L_.J; Mc = pM;
+    pEq = reinterpret_cast<int*>(ws_ + L_.eqflag); stage = ws_ + L_.J; Mc = pM; Jg = pJ;
   }
 };
 #define W(name) (c.ws + c.L.name)
@@ -1918,11 +1920,13 @@ __device__ __forceinline__ Primal constraint_update(const Ctx& c, int nefc) {
 // of ~5 x 5. Same iterates as the primal form up to rounding (tests/test_gpu_parity.py, tests/test_emu_kernel_parity.py).
 __device__ __forceinline__ void dual_prepare(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv, ld = m.ldv;
+  const double* Jsrc = c.L.jalias ? c.Jg : W(J);
   if (c.L.sparse) {                                                      // H holds the factor of M (fwd_acceleration)
-    copy_row(W(dV), W(J), nefc * ld, lane);
+    copy_row(W(dV), Jsrc, nefc * ld, lane);
     ldl_solve_multi(m, W(H), W(dinv), W(dV), ld, nefc, nv, lane);
     __syncwarp();
-  } else chol_solve_multi(W(H), W(dinv), nv, W(J), W(dV), ld, nefc, lane);
+  } else chol_solve_multi(W(H), W(dinv), nv, Jsrc, W(dV), ld, nefc, lane);
+  if (c.L.jalias) { copy_row(W(J), c.Jg, nefc * ld, lane); __syncwarp(); }      // over the factor of M, which nothing reads any more
   double* A = W(dS);                                                    // may alias H: chol(M) is dead from here on
   _Pragma("unroll 1") for (int r = 0; r < nefc; r++) {
     if (lane <= r) { const double a = dot_rows(W(J) + r * ld, W(dV) + lane * ld, nv); A[r * nefc + lane] = a; A[lane * nefc + r] = a; }
@@ -2889,7 +2893,8 @@ __device__ __forceinline__ void acc_kernel_body(const DevModel& m, const Lay& L,
   FOR_LANES(i, m.nu) W(ctrl)[i] = io.ctrl ? io.ctrl[e * m.nu + i] : 0.0;
   if (L.mglobal) c.Mc = hrow + H.M;      // read where the position kernel left it (L2): one factorisation, one product and the Euler copy
   else copy_row(W(M), hrow + H.M, tri(nv), lane);
-  copy_row(W(J), hrow + H.J, nefc * ld, lane);
+  c.Jg = hrow + H.J;
+  if (!L.jalias) copy_row(W(J), hrow + H.J, nefc * ld, lane);      // (jalias: dual_prepare brings it in once the factor of M is dead)
   FOR_LANES(r, nefc) { W(efcD)[r] = hrow[H.efcD + r]; W(aref)[r] = hrow[H.aref + r];
                        reinterpret_cast<int*>(W(eqflag))[r] = reinterpret_cast<const int*>(hrow + H.eqflag)[r]; W(efcSD)[r] = 0; }
   FOR_LANES(t, m.ntendon) W(tenlen)[t] = hrow[H.tenlen + t];
@@ -3080,7 +3085,8 @@ static void build_layout(b200mj_model* M) {
     // configuration (18.1 -> 20.0 ms per control step, profiles/r2_ab_s2_sparse_ldl.txt) although it executes a third of the
     // multiply-adds — the kernel is bound by per-warp latency (1.5 warps per scheduler), and 62 dependent elimination steps of
     // a few instructions each are a longer chain than 16 dense column blocks with eight independent accumulators.
-    int mglobal_on = 1, sparse_on = 0;
+    int mglobal_on = 1, sparse_on = 0, jalias_on = 1;
+    if (const char* ev = getenv("B200MJ_J_ALIAS")) jalias_on = atoi(ev);
     if (const char* ev = getenv("B200MJ_M_GLOBAL")) mglobal_on = atoi(ev);
     if (const char* ev = getenv("B200MJ_SPARSE_LDL")) sparse_on = atoi(ev);
     auto acc_layout = [&](Lay& A, int rows, bool with_sens) {
@@ -3095,14 +3101,18 @@ static void build_layout(b200mj_model* M) {
       A.mglobal = (mglobal_on && !M->tn_nv && nv >= 32) ? 1 : 0;
       A.sparse = (A.mglobal && sparse_on && m.dof_anc_adr) ? 1 : 0;
       A.M = take(A.mglobal ? 0 : ntri); A.H = take(ntri); A.dinv = take(nv);
-      A.J = take(rows * ld); A.efcD = take(rows); A.efcSD = take(rows); A.aref = take(rows); A.jar = take(rows); A.jv = take(rows);
+      // dual form with few rows: J's workspace copy aliases H (dual_prepare), so that seven CMU environments fit an SM
+      const bool will_dual = dual_min_nv > 0 && !M->tn_nv && nv >= dual_min_nv && rows <= 32 && m.solver == BMJ_SOL_NEWTON;
+      const int dneed = rows * rows + tri_host(rows) + 3 * rows + 2;
+      A.jalias = (will_dual && jalias_on && rows * ld + dneed <= ntri) ? 1 : 0;
+      A.J = A.jalias ? A.H : take(rows * ld); A.efcD = take(rows); A.efcSD = take(rows); A.aref = take(rows); A.jar = take(rows); A.jv = take(rows);
       A.eqflag = take((rows + 1) / 2); A.actlist = take((rows + 1) / 2);
       A.bias = take(nv); A.passive = take(nv); A.qfact = take(nv); A.smooth = take(nv); A.qaccs = take(nv);
       A.qcon = take(nv); A.Ma = take(nv); A.grad = take(nv); A.search = take(nv); A.Mv = take(nv); A.tmpv = take(nv);
       if (dual_min_nv > 0 && !M->tn_nv && nv >= dual_min_nv && rows <= 32 && m.solver == BMJ_SOL_NEWTON) {
         A.dual = 1; A.drows = rows; A.dV = take(rows * ld);
         const int need = rows * rows + tri_host(rows) + 3 * rows + 2;
-        A.dS = need <= ntri ? A.H : take(need);
+        A.dS = A.jalias ? A.H + ((rows * ld + 1) & ~1) : (need <= ntri ? A.H : take(need));
       }
       if (with_sens) {
         const int acc_end = o;
@@ -3589,7 +3599,7 @@ int b200mj_step(const b200mj_model* Mc, const b200mj_io* io, int batch, int nste
         if (compact) {
           static int per_bucket[4] = {0, 0, 0, 0}, parsed = 0;     // B200MJ_ACC_WARPS_B="4,3,2,2": warps per CTA by bucket (experiments)
           if (!parsed) { parsed = 1; if (const char* e = getenv("B200MJ_ACC_WARPS_B")) sscanf(e, "%d%*c%d%*c%d%*c%d", &per_bucket[0], &per_bucket[1], &per_bucket[2], &per_bucket[3]); }
-          const int want = per_bucket[b] > 0 ? per_bucket[b] : acc_warps;
+          const int want = per_bucket[b] > 0 ? per_bucket[b] : (M->tn_nv ? acc_warps : 8);      // runtime-size kernels (__launch_bounds__(256)): whatever fills the SM
           int cap = (int)((227 * 1024) / ws); if (cap > want) cap = want; if (M->tn_nv && cap > 4) cap = 4; if (cap < 1) cap = 1;
           // as many resident warps per SM as 227 KB allow (CMU corridor, 37 KB per warp: two CTAs of 3 instead of one of 4); ties: the larger CTA
           int best = 0;
