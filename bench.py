@@ -453,8 +453,14 @@ def run_gpu(args):
       e = locomotion.load('cmu_humanoid_run_walls', batch=2048, seed=3, device=dev)
       configs['locomotion.cmu_humanoid run-through-corridor (walls)'] = _time_env(e, 10, 10, 5, e.physics.model.nu, dev)
       e.physics.free()
+      # the same with the walker's 64 x 64 egocentric camera observable, ray-cast on the device every control step (b200mj_render)
+      e = locomotion.load('cmu_humanoid_run_walls', batch=2048, seed=3, device=dev, egocentric_camera=True)
+      r = _time_env(e, 10, 10, 5, e.physics.model.nu, dev)
+      r['observation'] = 'walker/egocentric_camera [2048, 64, 64, 3] uint8 per step (ray-cast hand-off, not MuJoCo GL pixels)'
+      configs['locomotion.cmu_humanoid run-through-corridor (walls) + egocentric camera'] = r
+      e.physics.free()
     except Exception as ex:
-      configs['locomotion.cmu_humanoid run-through-corridor (walls)'] = dict(error=repr(ex))
+      configs['locomotion.cmu_humanoid run-through-corridor (walls)' + (' + egocentric camera' if 'locomotion.cmu_humanoid run-through-corridor (walls)' in configs else '')] = dict(error=repr(ex))
 
   if rank == 0:
     peak, peak_src = _peaks()
