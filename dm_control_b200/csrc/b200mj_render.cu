@@ -19,7 +19,7 @@
 
 namespace {
 
-struct Obj { double pos[3], mat[9], size[3]; float rgb[3]; int type, kind, id; };
+struct Obj { double pos[3], mat[9], size[3], rb2; float rgb[3]; int type, kind, id; };      // rb2: squared bounding radius, < 0 for planes
 
 __device__ __forceinline__ void pick(double t1, double t2, double tmin, double& t) {
   const double a = t1 > tmin ? t1 : INFINITY, b = t2 > tmin ? t2 : INFINITY;
@@ -144,6 +144,17 @@ b200mj_render_kernel(const __grid_constant__ b200mj_render_scene sc, int height,
     double pp[3] = {p[0], p[1], p[2]};
     for (int c = 0; c < 9; c++) ob.mat[c] = m[c];
     for (int c = 0; c < 3; c++) { ob.size[c] = s[c]; ob.pos[c] = pp[c]; }
+    // bounding sphere for the world-frame rejection test ahead of the frame change + primitive test (most rays miss most objects)
+    double rb;
+    switch (ob.type) {
+      case BMJ_GEOM_SPHERE: rb = s[0]; break;
+      case BMJ_GEOM_CAPSULE: rb = s[0] + s[1]; break;
+      case BMJ_GEOM_CYLINDER: rb = sqrt(s[0] * s[0] + s[1] * s[1]); break;
+      case BMJ_GEOM_ELLIPSOID: rb = fmax(s[0], fmax(s[1], s[2])); break;
+      case BMJ_GEOM_BOX: rb = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]); break;
+      default: rb = -1; break;
+    }
+    ob.rb2 = rb < 0 ? -1.0 : rb * rb * (1.0 + 1e-9);
   }
   __syncthreads();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,10 +167,16 @@ b200mj_render_kernel(const __grid_constant__ b200mj_render_scene sc, int height,
   double d[3], o[3] = {cp[0], cp[1], cp[2]};
   for (int r = 0; r < 3; r++) d[r] = cm[3 * r] * dc[0] + cm[3 * r + 1] * dc[1] + cm[3 * r + 2] * dc[2];
   double best = sc.zfar; int bid = -1, bkind = -1; float col[3] = {0, 0, 0};
-  const double dnorm = sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
+  const double dd2 = d[0]*d[0] + d[1]*d[1] + d[2]*d[2], dnorm = sqrt(dd2);
   for (int k = 0; k < nvis; k++) {
     const Obj& ob = objs[k];
     double ol[3], dl[3], rel[3] = {o[0] - ob.pos[0], o[1] - ob.pos[1], o[2] - ob.pos[2]};
+    if (ob.rb2 >= 0) {      // the ray's closest approach to the centre lies outside the bounding sphere, or the sphere is behind / beyond the best hit
+      const double b = rel[0] * d[0] + rel[1] * d[1] + rel[2] * d[2], cc = rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2] - ob.rb2;
+      const double disc = b * b - dd2 * cc;
+      if (disc < 0 || (cc > 0 && b > 0)) continue;
+      if (cc > 0 && (-b - sqrt(disc)) > best * dd2) continue;
+    }
     for (int c = 0; c < 3; c++) {      // R^T v
       ol[c] = ob.mat[c] * rel[0] + ob.mat[3 + c] * rel[1] + ob.mat[6 + c] * rel[2];
       dl[c] = ob.mat[c] * d[0] + ob.mat[3 + c] * d[1] + ob.mat[6 + c] * d[2];
