@@ -437,11 +437,13 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
   // of the eight dot products left of the block shares its loads (2 own-row + 4 pivot-row loads per 8 multiply-adds; one
   // column at a time with a dot product per row took 4 loads per 2), the eight accumulators are independent chains,
   // and inside the block pivots and cross terms travel by shuffle. Rows 0..31 are finished once the block start passes
-  // 32: from there on only the second row of every lane is updated. The right-hand side takes a separate pass.
+  // 32: from there on only the second row of every lane is updated.
   const int i0 = lane, i1 = lane + 32, ti0 = tri(i0), ti1 = tri(i1);
-  const bool in1 = i1 < n;
-  const double* A0 = A + ti0; const double* A1 = in1 ? A + ti1 : A;
-  double* L0 = Lm + ti0; double* L1 = in1 ? Lm + ti1 : Lm;      // idle second rows read row 0, never write
+  // the right-hand side rides along as row n (the second row of lane n - 32) when there is a spare row: y = L^-1 b for free
+  const bool ride = b != nullptr && n < 64, isrhs = ride && i1 == n;
+  const bool in1 = i1 < n || isrhs;
+  const double* A0 = A + ti0; const double* A1 = isrhs ? b : (in1 ? A + ti1 : A);
+  double* L0 = Lm + ti0; double* L1 = isrhs ? y : (in1 ? Lm + ti1 : Lm);      // idle second rows read row 0, never write
   int tj0 = 0;
   _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += 4) {
     const int j1 = min(j0 + 1, n - 1), j2 = min(j0 + 2, n - 1), j3 = min(j0 + 3, n - 1);
@@ -521,24 +523,29 @@ __device__ __noinline__ void chol_factor(const double* A, double* Lm, double* di
     __syncwarp();
     tj0 += 4 * j0 + 10;
   }
-  if (b) chol_forward(Lm, dinv, b, y, n, lane);
+  if (b && !ride) chol_forward(Lm, dinv, b, y, n, lane);
 }
 
 // M X = B for K right-hand sides at once (M = L L^T, L packed, n <= 64; B, X: K rows of stride ld, may alias).
 // The K substitutions share every load of L and run as independent dependency chains, eight at a time: one pass of
 // 2 n steps serves eight right-hand sides (a single substitution is latency-bound: one shuffle + one DFMA per step).
 // Lanes own rows `lane` and `lane + 32` of the unknowns. Serves the dual form of the Newton direction (rows of M^-1 J').
-__device__ __noinline__ void chol_solve_multi(const double* Lm, const double* dinv, int n, const double* Bm, double* Xm, int ld, int K, int lane) {
+// `xb` / `xx` (optional): one more right-hand side / solution living elsewhere (qacc_smooth = M^-1 qfrc_smooth rides along with
+// the rows of J M^-1: no separate forward / backward pass).
+__device__ __noinline__ void chol_solve_multi(const double* Lm, const double* dinv, int n, const double* Bm, double* Xm, int ld, int K, int lane,
+                                              const double* xb, double* xx) {
+  const int Kall = K + (xb ? 1 : 0);
   const int i0 = lane, i1 = lane + 32;
   const bool in0 = i0 < n, in1 = i1 < n;
   const double* L0 = Lm + tri(i0); const double* L1 = Lm + tri(i1);
-  _Pragma("unroll 1") for (int r0 = 0; r0 < K; r0 += 8) {
+  _Pragma("unroll 1") for (int r0 = 0; r0 < Kall; r0 += 8) {
     double a0[8], a1[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int r = r0 + q;
-      a0[q] = (r < K && in0) ? Bm[r * ld + i0] : 0.0;
-      a1[q] = (r < K && in1) ? Bm[r * ld + i1] : 0.0;
+      const double* src = r < K ? Bm + r * ld : xb;
+      a0[q] = (r < Kall && in0) ? src[i0] : 0.0;
+      a1[q] = (r < Kall && in1) ? src[i1] : 0.0;
     }
     // forward: L y = b
     _Pragma("unroll 1") for (int j = 0; j < n; j++) {
@@ -584,8 +591,9 @@ __device__ __noinline__ void chol_solve_multi(const double* Lm, const double* di
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int r = r0 + q;
-      if (r < K && in0) Xm[r * ld + i0] = a0[q];
-      if (r < K && in1) Xm[r * ld + i1] = a1[q];
+      double* dst = r < K ? Xm + r * ld : xx;
+      if (r < Kall && in0) dst[i0] = a0[q];
+      if (r < Kall && in1) dst[i1] = a1[q];
     }
   }
   __syncwarp();
@@ -1848,6 +1856,8 @@ __device__ __forceinline__ void fwd_acceleration(const Ctx& c, const b200mj_io& 
       __syncwarp();
       ldl_factor(m, W(H), W(dinv), nv, lane);
       ldl_solve(m, W(H), W(dinv), W(qaccs), nv, lane);
+    } else if (c.L.dual) {
+      chol_factor(c.Mc, W(H), W(dinv), nv, lane, nullptr, nullptr);      // qacc_smooth: one more right-hand side of dual_prepare's substitution pass
     } else {
       chol_factor(c.Mc, W(H), W(dinv), nv, lane, W(smooth), W(qaccs));
       chol_back(W(H), W(dinv), W(qaccs), W(qaccs), nv, lane);
@@ -1925,7 +1935,8 @@ __device__ __forceinline__ void dual_prepare(const Ctx& c, int nefc) {
     copy_row(W(dV), Jsrc, nefc * ld, lane);
     ldl_solve_multi(m, W(H), W(dinv), W(dV), ld, nefc, nv, lane);
     __syncwarp();
-  } else chol_solve_multi(W(H), W(dinv), nv, Jsrc, W(dV), ld, nefc, lane);
+  } else chol_solve_multi(W(H), W(dinv), nv, Jsrc, W(dV), ld, nefc, lane, W(smooth), W(qaccs));      // + qacc_smooth (fwd_acceleration left it to this pass)
+  if (nefc == 0) return;
   if (c.L.jalias) { copy_row(W(J), c.Jg, nefc * ld, lane); __syncwarp(); }      // over the factor of M, which nothing reads any more
   double* A = W(dS);                                                    // may alias H: chol(M) is dead from here on
   _Pragma("unroll 1") for (int r = 0; r < nefc; r++) {
@@ -2096,7 +2107,7 @@ __device__ __forceinline__ int solve_newton(const Ctx& c, int nefc) {
   const DevModel& m = c.m; int lane = c.lane; int nv = m.nv;
   Primal pr; pr.cost = 0; pr.gauss = 0; pr.nact = 0; pr.changed = 1;
   const bool active = nefc > 0;
-  if constexpr (NVT == 0) { if (active && c.L.dual) dual_prepare(c, nefc); }
+  if constexpr (NVT == 0) { if (c.L.dual) dual_prepare(c, nefc); }
   if (active) {
     // start point: the warm start if it has lower cost than the unconstrained acceleration (MuJoCo's rule).
     // candidates: 0 = qacc_warmstart, 1 = qacc_smooth, 2 = qacc_warmstart restored (only when it won)
