@@ -3142,7 +3142,10 @@ static void build_layout(b200mj_model* M) {
     // measured on the humanoid workload (tools/knob_sweep.sh): {10, 16, 32, njmax} 5.56 ms per kernel group, {10, 24, njmax} 5.70
     int caps[4] = {10, 16, 32, nj};
     int ncap = 4;
-    if (nj > 96) { caps[0] = 12; caps[1] = 32; caps[2] = 72; caps[3] = nj; }   // large capacities (CMU corridor)
+    // large capacities (CMU corridor, njmax 200; 91 % of the environments carry <= 12 rows, 99.6 % <= 32): every populated bucket launch
+    // costs one per-environment latency and the launches cannot share SMs (shared memory), so three buckets beat four
+    // (profiles/r2_cmu_knobs_s2.txt: 17.23 vs 17.47 ms per control step)
+    if (nj > 96) { caps[0] = 12; caps[1] = 32; caps[2] = nj; ncap = 3; }
     if (const char* ev = getenv("B200MJ_BUCKETS")) {
       int a1 = 0, a2 = 0, a3 = 0;
       int got = sscanf(ev, "%d,%d,%d", &a1, &a2, &a3);
