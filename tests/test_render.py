@@ -168,6 +168,42 @@ def test_ray_primitives_against_closed_forms():
   assert np.isinf(t).all()
 
 
+def test_camera_modes_of_the_oracle():
+  """fixed / track / trackcom / targetbody poses from body frames (mjtCamLight semantics) on a two-body toy model."""
+  xml = """
+  <mujoco>
+    <worldbody>
+      <body name="a" pos="0 0 1">
+        <freejoint/>
+        <geom name="ga" size=".1"/>
+        <camera name="fixed" pos="0 -2 0" xyaxes="1 0 0 0 0 1"/>
+        <camera name="track" pos="0 -2 0" xyaxes="1 0 0 0 0 1" mode="track"/>
+        <camera name="trackcom" pos="0 -2 0" xyaxes="1 0 0 0 0 1" mode="trackcom"/>
+        <camera name="target" pos="0 -2 1" mode="targetbody" target="b"/>
+        <body name="b" pos="1 0 0"><joint type="hinge" axis="0 0 1"/><geom name="gb" size=".1" mass="3"/></body>
+      </body>
+    </worldbody>
+  </mujoco>"""
+  model = mc.compile_xml(xml)
+  vis = model.vis
+  assert vis['cam_mode'].tolist() == [0, 1, 2, 3] and int(vis['cam_targetbodyid'][3]) == model.name2id('b', 'body')
+  # body a moved to (2, 0, 1) and yawed by 90 degrees; b hangs 1 m along a's x axis -> world (2, 1, 1)
+  Rz = np.array([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+  xpos = np.array([[0, 0, 0], [2.0, 0, 1], [2.0, 1, 1]]); xmat = np.stack([np.eye(3).reshape(-1), Rz.reshape(-1), Rz.reshape(-1)])
+  com = np.array([[0, 0, 0], [2.0, 0.75, 1.0], [2.0, 1, 1]])
+  p, R = ro.camera_pose(vis, 0, xpos, xmat, com)                 # fixed: rides the body frame
+  np.testing.assert_allclose(p, [4.0, 0, 1], atol=1e-12); np.testing.assert_allclose(R[:, 2], Rz @ np.array([0, -1.0, 0]), atol=1e-12)
+  p, R = ro.camera_pose(vis, 1, xpos, xmat, com)                 # track: world offset from the body origin and world orientation at qpos0
+  np.testing.assert_allclose(p, [2.0, -2, 1], atol=1e-12); np.testing.assert_allclose(R[:, 2], [0, -1.0, 0], atol=1e-12)
+  p, R = ro.camera_pose(vis, 2, xpos, xmat, com)                 # trackcom: the same offset, from the subtree's centre of mass
+  np.testing.assert_allclose(p, com[1] + vis['cam_poscom0'][2], atol=1e-12)
+  m_a = 1000 * 4 / 3 * np.pi * 0.1 ** 3                          # default density; b's geom has mass 3 at x = 1
+  np.testing.assert_allclose(vis['cam_poscom0'][2], [-3 / (3 + m_a), -2.0, 0.0], atol=1e-12)
+  p, R = ro.camera_pose(vis, 3, xpos, xmat, com)                 # targetbody: -z points at b, x horizontal
+  to_b = xpos[2] - p
+  np.testing.assert_allclose(-R[:, 2], to_b / np.linalg.norm(to_b), atol=1e-12); assert abs(R[2, 0]) < 1e-12
+
+
 # ---- GPU tier ---------------------------------------------------------------------------------------------------------
 
 def _gpu_physics(xml, B=2):
