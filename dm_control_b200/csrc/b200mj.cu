@@ -59,6 +59,7 @@ struct DevModel {
   int ldv;          // padded row length of nv-wide matrices (odd => conflict-free column walks)
   int integrator, iterations, ls_iterations, disableflags, solver;
   int any_damping, acc_sensors;
+  int cvx_warp;     // convex pairs resolved by the whole warp (cvx_pair_warp; B200MJ_CVX_WARP=0: one pair per lane, cvx_pair)
   double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
 };
 
@@ -1168,6 +1169,144 @@ __device__ __forceinline__ void raw_sphere_sphere(double* stg, int& n, double ma
   stage_contact(stg, n, dist, pos, nrm);
 }
 
+// ------------------------------------------------------------------------------------------------
+// cvx_pair (include/b200mj_convex.h) with the WHOLE WARP on one pair: same arithmetic, same answer, a fifth of the
+// latency. A convex contact costs up to ~900 support evaluations in sequence (12 frame axes + a 96-point lattice for the
+// start directions, three descents of <= 32 steps with <= 8 step halvings each, MPR before and after); with one pair
+// per lane a single touching ellipsoid kept its environment — and, through the phase barriers, its CTA and the whole
+// launch — waiting (CMU corridor: 2.4 of 17.1 ms per control step). Here the 108 start-direction evaluations run one per
+// lane, the three descents run side by side in three groups of eight lanes and every group evaluates its eight halvings
+// of a step at once; selections replicate the scalar code's order (first index among equal minima, first accepted
+// halving), so the contact is bit-identical to cvx_pair's (tests/test_convex_pairs.py, emulated kernel vs oracle).
+// The two MPR passes stay sequential and are executed redundantly by all lanes (no divergence, no broadcast).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int first_bit(unsigned b) { return __popc((b & (0u - b)) - 1u); }
+__device__ __forceinline__ void warp_argmin(double& h, int& k) {      // smallest h, smallest k among equals; h >= 1e300 / NaN never win
+  if (!(h < 1e300)) { h = 1e300; k = 1 << 20; }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double oh = __shfl_xor_sync(FULL, h, off); const int ok = __shfl_xor_sync(FULL, k, off);
+    if (oh < h || (oh == h && ok < k)) { h = oh; k = ok; }
+  }
+}
+
+__device__ __noinline__ int cvx_pair_warp(int lane, int t1, const double* p1, const double* m1, const double* s1, int t2, const double* p2,
+                                          const double* m2, const double* s2, double margin, double* dist, double* pos, double* nrm) {
+  CvxGeom g1 = {t1, p1, m1, s1, 0.5 * margin}, g2 = {t2, p2, m2, s2, 0.5 * margin};
+  double depth;
+  if (!cvx_mpr(g1, g2, (const double*)0, &depth, nrm, pos)) return 0;
+  double start[9] = {nrm[0], nrm[1], nrm[2], nrm[0], nrm[1], nrm[2], nrm[0], nrm[1], nrm[2]};
+  {   // best frame axis of the two geoms: k = lane < 12
+    double hk = 1e300; int kk = lane;
+    if (lane < 12) {
+      const double* mm = lane < 6 ? m1 : m2;
+      const int ax = (lane % 6) >> 1; const double sg = (lane & 1) ? -1.0 : 1.0;
+      const double dk[3] = {sg * mm[ax], sg * mm[3 + ax], sg * mm[6 + ax]};
+      CvxSup sk; cvx_support(g1, g2, dk, sk);
+      hk = cvx_dot(sk.v, dk);
+    }
+    warp_argmin(hk, kk);
+    if (kk < 12) {
+      const double* mm = kk < 6 ? m1 : m2;
+      const int ax = (kk % 6) >> 1; const double sg = (kk & 1) ? -1.0 : 1.0;
+      start[3] = sg * mm[ax]; start[4] = sg * mm[3 + ax]; start[5] = sg * mm[6 + ax];
+    }
+  }
+  {   // best point of the 96-point Fibonacci lattice: k = lane, lane + 32, lane + 64
+    double hb = 1e300; int kb = 1 << 20;
+    _Pragma("unroll 1") for (int k = lane; k < 96; k += 32) {
+      const double z = 1.0 - (2.0 * k + 1.0) / 96.0, rr = sqrt(1.0 - z * z), ph = 2.399963229728653 * k;
+      const double dk[3] = {rr * cos(ph), rr * sin(ph), z};
+      CvxSup sk; cvx_support(g1, g2, dk, sk);
+      const double hk = cvx_dot(sk.v, dk);
+      if (hk < hb) { hb = hk; kb = k; }
+    }
+    warp_argmin(hb, kb);
+    if (kb < 96) {
+      const double z = 1.0 - (2.0 * kb + 1.0) / 96.0, rr = sqrt(1.0 - z * z), ph = 2.399963229728653 * kb;
+      start[6] = rr * cos(ph); start[7] = rr * sin(ph); start[8] = z;
+    }
+  }
+  // three descents side by side: group = lane / 8 (the fourth group repeats the third and is ignored), eight halvings per step at once
+  const int grp = lane >> 3, c = grp < 3 ? grp : 2, hf = lane & 7;
+  double d[3] = {start[3 * c], start[3 * c + 1], start[3 * c + 2]};
+  CvxSup sf; cvx_support(g1, g2, d, sf);
+  double hd = cvx_dot(sf.v, d), eta = 0;
+  bool active = true;
+  _Pragma("unroll 1") for (int it = 0; it < 32; it++) {
+    double g[3] = {sf.v[0] - hd * d[0], sf.v[1] - hd * d[1], sf.v[2] - hd * d[2]};
+    if (active && cvx_dot(g, g) < 1e-20) active = false;
+    if (!__any_sync(FULL, active)) break;
+    if (active && it == 0) {
+      const double nd[3] = {-d[0], -d[1], -d[2]};
+      CvxSup sb; cvx_support(g1, g2, nd, sb);
+      const double hb = cvx_dot(sb.v, nd);
+      eta = 2.0 / (hb - hd > 1e-9 ? hb - hd : 1e-9);
+    }
+    double eh = eta;
+    for (int q = 0; q < hf; q++) eh *= 0.5;                 // the scalar code's `eta *= 0.5`, hf times
+    double dn[3] = {d[0] - eh * g[0], d[1] - eh * g[1], d[2] - eh * g[2]};
+    cvx_normalize(dn);
+    CvxSup sn; cvx_support(g1, g2, dn, sn);
+    const double hn = cvx_dot(sn.v, dn);
+    const unsigned acc = (__ballot_sync(FULL, active && hn < hd - 1e-14) >> (8 * grp)) & 0xffu;
+    if (active && acc == 0) active = false;
+    const int src = (active ? 8 * grp + first_bit(acc) : lane);
+    // the accepted candidate of this group (its first accepted halving) becomes the group's state
+    const double a_dn0 = __shfl_sync(FULL, dn[0], src), a_dn1 = __shfl_sync(FULL, dn[1], src), a_dn2 = __shfl_sync(FULL, dn[2], src);
+    const double a_hn = __shfl_sync(FULL, hn, src), a_eh = __shfl_sync(FULL, eh, src);
+    CvxSup a_sn;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { a_sn.v[i] = __shfl_sync(FULL, sn.v[i], src); a_sn.a[i] = __shfl_sync(FULL, sn.a[i], src); a_sn.b[i] = __shfl_sync(FULL, sn.b[i], src); }
+    if (active) {
+      const double a_dn[3] = {a_dn0, a_dn1, a_dn2};
+      const double gn[3] = {a_sn.v[0] - a_hn * a_dn[0], a_sn.v[1] - a_hn * a_dn[1], a_sn.v[2] - a_hn * a_dn[2]};
+      const double dd[3] = {a_dn[0] - d[0], a_dn[1] - d[1], a_dn[2] - d[2]}, dg[3] = {gn[0] - g[0], gn[1] - g[1], gn[2] - g[2]};
+      const double sy = cvx_dot(dd, dg), ss = cvx_dot(dd, dd);
+      d[0] = a_dn[0]; d[1] = a_dn[1]; d[2] = a_dn[2]; sf = a_sn; hd = a_hn;
+      eta = (sy > 1e-12 * ss && ss > 0) ? ss / sy : 2 * a_eh;
+    }
+  }
+  // the lowest end point wins, first descent first
+  double dbest[3] = {nrm[0], nrm[1], nrm[2]}, hbest = 1e300;
+  CvxSup sbest; cvx_support(g1, g2, dbest, sbest);
+#pragma unroll
+  for (int cc = 0; cc < 3; cc++) {
+    const double h_c = __shfl_sync(FULL, hd, 8 * cc);
+    double d_c[3]; CvxSup s_c;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { d_c[i] = __shfl_sync(FULL, d[i], 8 * cc); s_c.v[i] = __shfl_sync(FULL, sf.v[i], 8 * cc); s_c.a[i] = __shfl_sync(FULL, sf.a[i], 8 * cc); s_c.b[i] = __shfl_sync(FULL, sf.b[i], 8 * cc); }
+    if (h_c < hbest) { hbest = h_c; dbest[0] = d_c[0]; dbest[1] = d_c[1]; dbest[2] = d_c[2]; sbest = s_c; }
+  }
+  if (hbest < depth - 1e-9) {
+    const double nd[3] = {-dbest[0], -dbest[1], -dbest[2]};
+    CvxSup sb; cvx_support(g1, g2, nd, sb);
+    const double ext = cvx_dot(sb.v, nd);
+    double d2 = 1e300, n2[3], p2v[3];
+    int hit = 0;
+    if (ext > 1e-12) {
+      const double inner[3] = {0.5 * ext * nd[0], 0.5 * ext * nd[1], 0.5 * ext * nd[2]};
+      hit = cvx_mpr(g1, g2, inner, &d2, n2, p2v);
+    }
+    if (hit && d2 <= hbest + 1e-9) {
+      depth = d2;
+      for (int i = 0; i < 3; i++) { nrm[i] = n2[i]; pos[i] = p2v[i]; }
+    } else {
+      depth = hbest;
+      for (int i = 0; i < 3; i++) { nrm[i] = dbest[i]; pos[i] = 0.5 * (sbest.a[i] + sbest.b[i]); }
+    }
+  }
+  *dist = margin - depth;
+  return 1;
+}
+
+// geom-type pairs that narrowphase<true> resolves with cvx_pair (everything without a closed form; t1 <= t2)
+__device__ __forceinline__ bool pair_is_mpr(int t1, int t2) {
+  if (t1 == BMJ_GEOM_PLANE || t1 == BMJ_GEOM_SPHERE && (t2 == BMJ_GEOM_SPHERE || t2 == BMJ_GEOM_CAPSULE || t2 == BMJ_GEOM_BOX)) return false;
+  if (t1 == BMJ_GEOM_CAPSULE && (t2 == BMJ_GEOM_CAPSULE || t2 == BMJ_GEOM_BOX)) return false;
+  return t1 >= BMJ_GEOM_SPHERE && t2 <= BMJ_GEOM_BOX;
+}
+
 // returns the number of raw contacts staged for this lane's pair (normal points from geom1 to geom2)
 // CVX = false: the model's candidate pairs are all analytic primitive pairs (decided at model_create), so the convex routines
 // (cvx_capsule_box / cvx_pair: ~50 registers and 0.8 KB of stack in the position kernels) are compiled out.
@@ -1441,14 +1580,33 @@ __device__ __forceinline__ int collision(const Ctx& c, int* warn_contactfull) {
     __syncwarp();
     const int take = qn < 32 ? qn : 32;
     int n = 0, g1 = 0, g2 = 0;
+    bool mpr_lane = false;      // this lane's pair has no closed form: resolved below by the whole warp (cvx_pair_warp)
     if (lane < take) {
       const int p = queue[lane];
       g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
       const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-      const double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
-      double s1[3], s2[3];
-      geom_size_of(c, g1, s1); geom_size_of(c, g2, s2);
-      n = narrowphase<CVX>(stg, t1, t2, margin, W(gxpos) + 3 * g1, W(gxmat) + 9 * g1, s1, W(gxpos) + 3 * g2, W(gxmat) + 9 * g2, s2);
+      if constexpr (CVX) mpr_lane = m.cvx_warp && pair_is_mpr(t1, t2);
+      if (mpr_lane) { STG_TAN(0) = 0; STG_TAN(1) = 0; STG_TAN(2) = 0; }
+      else {
+        const double margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
+        double s1[3], s2[3];
+        geom_size_of(c, g1, s1); geom_size_of(c, g2, s2);
+        n = narrowphase<CVX>(stg, t1, t2, margin, W(gxpos) + 3 * g1, W(gxmat) + 9 * g1, s1, W(gxpos) + 3 * g2, W(gxmat) + 9 * g2, s2);
+      }
+    }
+    if constexpr (CVX) {
+      unsigned todo = __ballot_sync(FULL, mpr_lane);
+      _Pragma("unroll 1") while (todo) {
+        const int src = first_bit(todo);
+        todo &= todo - 1;
+        const int a = __shfl_sync(FULL, g1, src), b = __shfl_sync(FULL, g2, src);
+        const double margin = fmax(m.geom_margin[a], m.geom_margin[b]);
+        double s1[3], s2[3], dist, cpos[3], cnrm[3];
+        geom_size_of(c, a, s1); geom_size_of(c, b, s2);
+        const int hit = cvx_pair_warp(lane, m.geom_type[a], W(gxpos) + 3 * a, W(gxmat) + 9 * a, s1, m.geom_type[b], W(gxpos) + 3 * b, W(gxmat) + 9 * b, s2,
+                                      margin, &dist, cpos, cnrm);
+        if (lane == src && hit) stage_contact(stg, n, dist, cpos, cnrm);
+      }
     }
     // the queue's remainder moves to the front
     const int rest = qn - take;
@@ -3365,6 +3523,7 @@ int b200mj_model_create(const int32_t* idata, int ni, const double* rdata, int n
     if (tree_ok && nv > 0) { m.dof_anc_adr = d_aadr; m.dof_anc_id = d_aid; m.dof_subsize = d_sub; }
     else { m.dof_anc_adr = nullptr; m.dof_anc_id = nullptr; m.dof_subsize = nullptr; }
   }
+  { const char* ev = getenv("B200MJ_CVX_WARP"); m.cvx_warp = ev ? atoi(ev) : 1; }
   M->nkey = h_sizes[BMJ_NKEY];
   M->tn_nv = tn_kernel(m.nv, false) ? m.nv : 0;
   build_layout(M);

@@ -229,6 +229,10 @@ BMJ_HD int cvx_pair(int t1, const double* p1, const double* m1, const double* s1
   CvxGeom g1 = {t1, p1, m1, s1, 0.5 * margin}, g2 = {t2, p2, m2, s2, 0.5 * margin};
   double depth;
   if (!cvx_mpr(g1, g2, (const double*)0, &depth, nrm, pos)) return 0;
+#ifdef BMJ_CVX_SKIP_REFINE      /* timing experiments only: what the refinement below costs (results differ) */
+  *dist = margin - depth;
+  return 1;
+#endif
   /* MPR measures the overlap along the ray from its interior point through the origin, which is the minimum
    * translation (what GJK/EPA returns) only when that ray is parallel to the contact normal. So: (1) walk the direction
    * downhill on h(d) = max over the Minkowski difference of x.d — the overlap along d, whose minimum over unit d is the

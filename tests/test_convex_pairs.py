@@ -122,3 +122,57 @@ def test_capsule_on_box_contact_pattern(narrow):
   assert any(abs(p[0] - .5) < .06 for d, p, n in cross)
   # clear of the box
   assert narrow(CAPSULE, [0, 0, .5], I3, [.05, .2, 0], BOX, box_p, I3, box_s) == []
+
+
+# ---- the engine's warp-cooperative form of cvx_pair (b200mj.cu: cvx_pair_warp) ------------------------------------------
+_WARP_CHILD = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests/emu')
+import b200mj_emu as emu
+from dm_control_b200 import mjcf_compile as mc
+from oracle import oracle as om
+om.build()
+TYPES = [('ellipsoid', '.3 .2 .15'), ('cylinder', '.2 .25'), ('box', '.25 .2 .15'), ('capsule', '.15 .25'), ('sphere', '.2')]
+rs = np.random.RandomState(%(seed)d)
+worst, ncontact, nmis = 0.0, 0, 0
+for ta, sa in TYPES[:3]:
+  for tb, sb in TYPES:
+    xml = f"""<mujoco><option gravity="0 0 0"/><worldbody>
+      <body name="a" pos="0 0 0"><freejoint/><geom name="ga" type="{ta}" size="{sa}"/></body>
+      <body name="b" pos="0.3 0 0"><freejoint/><geom name="gb" type="{tb}" size="{sb}"/></body>
+    </worldbody></mujoco>"""
+    m = mc.compile_xml(xml)
+    B = 8
+    p = emu.EmuPhysics(m, B)
+    q = np.zeros((B, 14))
+    for e in range(B):
+      qa = rs.randn(4); qa /= np.linalg.norm(qa); qb = rs.randn(4); qb /= np.linalg.norm(qb)
+      off = rs.randn(3); off *= rs.uniform(0.1, 0.45) / np.linalg.norm(off)
+      q[e] = np.concatenate([[0, 0, 0], qa, off, qb])
+    p.data.qpos[:] = q; p.forward()
+    for e in range(B):
+      o = om.OraclePhysics(m); o.qpos[:] = q[e]; o.forward()
+      if int(p.data.ncon[e]) != o.ncon:
+        nmis += 1; continue
+      for k in range(o.ncon):
+        cd = o.contact[k]
+        worst = max(worst, abs(p.data.contact_dist[e, k] - cd.dist), float(np.abs(p.data.contact_pos[e, k] - np.asarray(cd.pos)).max()),
+                    float(np.abs(p.data.contact_frame[e, k][:3] - np.asarray(cd.frame)[:3]).max()))
+        ncontact += 1
+print(json.dumps(dict(worst=worst, contacts=ncontact, mismatches=nmis)))
+'''
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('warp', ['1', '0'])
+def test_engine_convex_contacts_equal_the_oracles_bitwise(warp):
+  """15 type pairs x 8 random poses through the kernel source on the CPU emulation: the warp-cooperative cvx_pair_warp
+  (B200MJ_CVX_WARP=1, default) and the one-pair-per-lane cvx_pair give the oracle's contact EXACTLY (same arithmetic,
+  same selection order) — distance, position and normal to the last bit."""
+  import json, os, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, '-c', _WARP_CHILD % dict(root=root, seed=5)], env=dict(os.environ, B200MJ_CVX_WARP=warp),
+                     capture_output=True, text=True, timeout=800)
+  assert r.returncode == 0, r.stderr[-2000:]
+  out = json.loads(r.stdout.strip().splitlines()[-1])
+  assert out['contacts'] > 80 and out['mismatches'] == 0 and out['worst'] == 0.0, out
