@@ -14,6 +14,8 @@ per-environment walls.
 The scenes are the reference's XML strings; the engine needs at least one degree of freedom, so the GPU twins add an
 invisible free body far away from the scene.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -206,7 +208,13 @@ def test_camera_modes_of_the_oracle():
 
 # ---- GPU tier ---------------------------------------------------------------------------------------------------------
 
+EMULATE = os.environ.get('B200MJ_EMULATE_GPU') == '1'
+no_renderer_in_emulation = pytest.mark.skipif(EMULATE, reason='the CPU emulation build (tests/emu) holds the physics kernels only: no b200mj_render')
+
+
 def _gpu_physics(xml, B=2):
+  if EMULATE:
+    pytest.skip('the CPU emulation build (tests/emu) holds the physics kernels only: no b200mj_render')
   import torch
   from dm_control_b200.physics import BatchedPhysics
   if not torch.cuda.is_available():
@@ -304,6 +312,7 @@ def _compare_with_oracle(phys, camera_id, H, W, envs):
 
 
 @pytest.mark.gpu
+@no_renderer_in_emulation
 def test_gpu_render_matches_oracle_humanoid():
   import torch
   from dm_control_b200 import suite
@@ -321,6 +330,7 @@ def test_gpu_render_matches_oracle_humanoid():
 
 
 @pytest.mark.gpu
+@no_renderer_in_emulation
 def test_gpu_egocentric_camera_in_the_corridor():
   """The CMU walker's head camera (cmu_humanoid.py:448-455) sees that environment's own walls (per-environment geoms)."""
   import torch
