@@ -206,6 +206,69 @@ def test_camera_modes_of_the_oracle():
   np.testing.assert_allclose(-R[:, 2], to_b / np.linalg.norm(to_b), atol=1e-12); assert abs(R[2, 0]) < 1e-12
 
 
+def test_host_camera_poses_and_matrices_match_the_oracle():
+  """`render.Camera.pose / matrices / matrix` (torch, the product's host code) on CPU tensors against the numpy restatement,
+  for every camera mode and the free camera — no kernel involved (the physics object is a stub holding body frames)."""
+  import types
+  import torch
+  from dm_control_b200 import render
+  xml = """
+  <mujoco>
+    <visual><global fovy="50"/></visual>
+    <worldbody>
+      <body name="a" pos="0 0 1">
+        <freejoint/>
+        <geom name="ga" size=".1"/>
+        <camera name="fixed" pos="0 -2 0.3" xyaxes="1 0 0 0 0.2 1" fovy="30"/>
+        <camera name="track" pos="0 -2 0" xyaxes="1 0 0 0 0 1" mode="track"/>
+        <camera name="trackcom" pos="1 -2 0" xyaxes="1 0 0 0 0 1" mode="trackcom"/>
+        <camera name="target" pos="0 -2 1" mode="targetbody" target="b"/>
+        <camera name="targetcom" pos="0.5 -2 1" mode="targetbodycom" target="a"/>
+        <body name="b" pos="1 0 0"><joint type="hinge" axis="0 0 1"/><geom name="gb" size=".1" mass="3"/></body>
+      </body>
+    </worldbody>
+  </mujoco>"""
+  model = mc.compile_xml(xml)
+  B, rs = 3, np.random.RandomState(0)
+  xpos = rs.uniform(-1, 1, (B, model.nbody, 3)); com = rs.uniform(-1, 1, (B, model.nbody, 3))
+  xmat = np.zeros((B, model.nbody, 9))
+  for e in range(B):
+    for b in range(model.nbody):
+      q = rs.randn(4); xmat[e, b] = ro.quat_to_mat(q / np.linalg.norm(q)).reshape(-1)
+  t = lambda a: torch.as_tensor(a.reshape(B, -1).copy())
+  data = types.SimpleNamespace(xpos=t(xpos), xmat=t(xmat), subtree_com=t(com), geom_xpos=torch.zeros(B, model.ngeom * 3, dtype=torch.float64),
+                               geom_xmat=torch.zeros(B, model.ngeom * 9, dtype=torch.float64))
+  phys = types.SimpleNamespace(model=model, data=data, batch=B, device=torch.device('cpu'), is_dirty=False)
+  H, W = 48, 64
+  for cid in range(5):
+    cam = render.Camera(phys, H, W, cid)
+    pos, mat = cam.pose()
+    full = cam.matrix.numpy()
+    for e in range(B):
+      p_o, R_o = ro.camera_pose(model.vis, cid, xpos[e], xmat[e], com[e])
+      np.testing.assert_allclose(pos[e].numpy(), p_o, atol=1e-12); np.testing.assert_allclose(mat[e].numpy(), R_o, atol=1e-12)
+      image, focal, rotation, translation = ro.camera_matrix(p_o, R_o, float(model.vis['cam_fovy'][cid]), H, W)
+      np.testing.assert_allclose(full[e], image @ focal @ rotation @ translation, atol=1e-9)
+  cam = render.Camera(phys, H, W, -1)
+  cam.set_pose([0.1, 0.2, 0.3], 2.5, 30.0, -20.0)
+  pos, mat = cam.pose()
+  p_o, R_o = ro.free_camera_pose([0.1, 0.2, 0.3], 2.5, 30.0, -20.0)
+  np.testing.assert_allclose(pos[0].numpy(), p_o, atol=1e-12); np.testing.assert_allclose(mat[0].numpy(), R_o, atol=1e-12)
+  image, focal, rotation, translation = ro.camera_matrix(p_o, R_o, 50.0, H, W)
+  np.testing.assert_allclose(cam.matrix[0].numpy(), image @ focal @ rotation @ translation, atol=1e-9)
+  with pytest.raises(ValueError):
+    render.Camera(phys, H, W, 5)
+  with pytest.raises(ValueError):
+    render.Camera(phys, H, W, 0).set_pose([0, 0, 0], 1, 0, 0)
+  # the hand-off to an external renderer: MuJoCo-named host arrays for the chosen environments
+  st = render.scene_state(phys, env_ids=[2, 0])
+  assert st['geom_xpos'].shape == (2, model.ngeom, 3) and st['geom_xmat'].shape == (2, model.ngeom, 9)
+  assert st['cam_xpos'].shape == (2, 5, 3) and st['cam_xmat'].shape == (2, 5, 9)
+  p_o, R_o = ro.camera_pose(model.vis, 3, xpos[2], xmat[2], com[2])
+  np.testing.assert_allclose(st['cam_xpos'][0, 3], p_o, atol=1e-12); np.testing.assert_allclose(st['cam_xmat'][0, 3].reshape(3, 3), R_o, atol=1e-12)
+  np.testing.assert_array_equal(st['geom_type'], model.geom_type); assert st['geom_rgba'].shape == (model.ngeom, 4)
+
+
 # ---- GPU tier ---------------------------------------------------------------------------------------------------------
 
 EMULATE = os.environ.get('B200MJ_EMULATE_GPU') == '1'
