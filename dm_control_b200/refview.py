@@ -83,6 +83,11 @@ class SingleEnvPhysics:
     named_model = _index.NamedIndexStructs(types.SimpleNamespace(model=model, data=types.SimpleNamespace())).model
     self.named = types.SimpleNamespace(data=_index._Struct(data_get, model, False), model=named_model)
     self._pull()
+    self._reload_from_data(self.data)
+
+  def _reload_from_data(self, data):
+    """The hook `mujoco.Physics.__init__` / `reload_from_*` / `__setstate__` run when a Physics is bound to its data
+    (engine.py:116-123, 370-392). Domain subclasses override it to reset caches (suite/quadruped.py:148-152) and call up."""
 
   # ---- construction (engine.py:451-503) ----
   @classmethod

@@ -8,6 +8,8 @@
     `dm_control.suite.base`, `dm_control.suite.common`, `dm_control.suite.utils.randomizers`, `dm_control.utils.rewards`
     ... execute the reference's own files, unmodified, without running the package `__init__`s that would pull in
     `mujoco`, `lxml`, OpenGL, ...;
+  * `lxml.etree` (absent from this image): the few ElementTree calls suite/cartpole.py, suite/quadruped.py and
+    utils/xml_tools.py make, on top of xml.etree.ElementTree;
   * `dm_control.mujoco`: a stand-in module whose `Physics` is `dm_control_b200.refview.SingleEnvPhysics` (the reference's
     numpy Physics API on a B = 1 view of the batched CUDA engine), plus `action_spec` and the `wrapper.mjbindings.enums`
     the randomizers read.
@@ -76,6 +78,70 @@ def _make_dm_env():
   return m, specs
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# lxml.etree stand-in (absent from this image): the handful of calls suite/cartpole.py, suite/quadruped.py and
+# utils/xml_tools.py make — fromstring / XML / XMLParser / Element / SubElement / tostring, find / findall with
+# [@name='..'] predicates, getparent() — on top of xml.etree.ElementTree
+# ---------------------------------------------------------------------------------------------------------------
+def _make_lxml():
+  import xml.etree.ElementTree as ET
+
+  class Element(ET.Element):
+    _parent = None
+
+    def getparent(self):
+      return self._parent
+
+    def append(self, child):
+      super().append(child); child._parent = self
+
+    def insert(self, index, child):
+      super().insert(index, child); child._parent = self
+
+    def remove(self, child):
+      super().remove(child); child._parent = None
+
+  def _link(root):
+    for parent in root.iter():
+      for child in parent:
+        child._parent = parent
+    return root
+
+  class XMLParser:
+    def __init__(self, remove_blank_text=False, **unused):
+      self.remove_blank_text = remove_blank_text
+
+  def fromstring(text, parser=None):
+    builder = ET.TreeBuilder(element_factory=Element)
+    p = ET.XMLParser(target=builder)
+    p.feed(text)
+    root = _link(p.close())
+    if parser is not None and parser.remove_blank_text:
+      for e in root.iter():
+        if e.text is not None and not e.text.strip(): e.text = None
+        if e.tail is not None and not e.tail.strip(): e.tail = None
+    return root
+
+  def SubElement(parent, tag, attrib=None, **extra):
+    child = Element(tag, dict(attrib or {}, **extra))
+    parent.append(child)
+    return child
+
+  def tostring(element, pretty_print=False, **unused):
+    if pretty_print:
+      ET.indent(element)
+    return ET.tostring(element)
+
+  lxml = types.ModuleType('lxml')
+  etree = types.ModuleType('lxml.etree')
+  etree.Element, etree.SubElement, etree.XMLParser = Element, SubElement, XMLParser
+  etree.fromstring = etree.XML = fromstring
+  etree.tostring = tostring
+  etree.parse = lambda file_obj, parser=None: types.SimpleNamespace(getroot=lambda r=fromstring(file_obj.read(), parser): r)
+  lxml.etree = etree
+  return lxml, etree
+
+
 def _package(name, path):
   p = types.ModuleType(name)
   p.__path__ = [path]
@@ -93,6 +159,11 @@ def install():
     sys.path.insert(0, root)
   dm_env, specs = _make_dm_env()
   sys.modules['dm_env'], sys.modules['dm_env.specs'] = dm_env, specs
+  if 'lxml' not in sys.modules:
+    try:
+      import lxml.etree      # noqa: F401  (the real one, where installed)
+    except ImportError:
+      sys.modules['lxml'], sys.modules['lxml.etree'] = _make_lxml()
   ref = os.path.join(REFERENCE, 'dm_control')
   for name, sub in (('dm_control', ''), ('dm_control.rl', 'rl'), ('dm_control.suite', 'suite'), ('dm_control.suite.utils', 'suite/utils'),
                     ('dm_control.utils', 'utils')):
@@ -115,8 +186,11 @@ def install():
   mj.action_spec = action_spec
   wrapper = types.ModuleType('dm_control.mujoco.wrapper')
   mjb = types.ModuleType('dm_control.mujoco.wrapper.mjbindings')
-  enums = types.SimpleNamespace(mjtJoint=types.SimpleNamespace(mjJNT_FREE=0, mjJNT_BALL=1, mjJNT_SLIDE=2, mjJNT_HINGE=3))
+  enums = types.SimpleNamespace(mjtJoint=types.SimpleNamespace(mjJNT_FREE=0, mjJNT_BALL=1, mjJNT_SLIDE=2, mjJNT_HINGE=3),
+                                mjtSensor=types.SimpleNamespace(mjSENS_TOUCH=0, mjSENS_ACCELEROMETER=1, mjSENS_VELOCIMETER=2, mjSENS_GYRO=3,
+                                                                mjSENS_FORCE=4, mjSENS_TORQUE=5, mjSENS_MAGNETOMETER=6, mjSENS_RANGEFINDER=7))
   mjb.enums = enums
+  mjb.mjlib = types.SimpleNamespace()      # suite/quadruped.py binds the name at import; only its `escape` task (hfield upload) calls into it
   wrapper.mjbindings = mjb
   mj.wrapper = wrapper
   sys.modules['dm_control.mujoco'] = mj

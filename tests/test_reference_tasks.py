@@ -1,8 +1,10 @@
 """north_star: "suite tasks run unchanged". The UNMODIFIED reference sources — dm_control/rl/control.py (Environment),
-dm_control/suite/humanoid.py (task + Physics subclass), suite/base.py, suite/common, suite/utils/randomizers.py,
-utils/rewards.py, utils/containers.py — are imported from /root/reference (tests/refshim wires the few absent third-party
-modules) and drive a B = 1 view of the batched CUDA engine (dm_control_b200/refview.py) for 100 control steps.
-The trajectory is checked against the CPU oracle stepped from the same post-reset state with the same actions.
+dm_control/suite/{humanoid,cartpole,cheetah,quadruped}.py (tasks + Physics subclasses, incl. the model editing cartpole.py
+and quadruped.py do with lxml), suite/base.py, suite/common, suite/utils/randomizers.py, utils/rewards.py,
+utils/containers.py, utils/xml_tools.py — are imported from /root/reference (tests/refshim wires the few absent
+third-party modules) and drive a B = 1 view of the batched CUDA engine (dm_control_b200/refview.py): humanoid:run for 100
+control steps, the other BASELINE suite configs for 40. The trajectory is checked against the CPU oracle stepped from the
+same post-reset state with the same actions.
 
 /root/reference exists in the build container only: the tests skip where it is absent (GPU box).
   * `-m gpu` twin: runs on the device (or under B200MJ_EMULATE_GPU=1);
@@ -53,6 +55,69 @@ def run_unmodified_humanoid(nsteps=100):
   assert abs(env.physics.time() - nsteps * 0.025) < 1e-9
   assert worst < 1e-6, worst
   return worst
+
+
+def run_unmodified(domain, task, nsteps=40, seed=5):
+  """Any of the BASELINE suite configs through the reference's own task file: build (the file's own model editing where it
+  has any: cartpole.py:104-127, quadruped.py:55-93), reset (its own randomisation), step with random actions; the
+  trajectory against the oracle stepped from the same post-reset state. Convex (MPR) contacts end the comparison of an
+  episode (discontinuous in the pose)."""
+  import importlib
+  refshim.install()
+  mod = importlib.import_module('dm_control.suite.' + domain)
+  assert os.path.realpath(mod.__file__).startswith(os.path.realpath(refshim.REFERENCE))
+  from oracle import oracle as om
+  env = getattr(mod, task)(random=seed)
+  spec = env.action_spec()
+  ts = env.reset()
+  assert ts.first() and ts.reward is None
+  phys = env.physics
+  nsub = int(round(env.control_timestep() / phys.timestep()))
+  o = om.OraclePhysics(phys.model)
+  o.qpos[:] = phys.data.qpos; o.qvel[:] = phys.data.qvel
+  if phys.model.na:
+    o.act[:] = phys.data.act
+  o.forward()
+  gtype = np.asarray(phys.model.geom_type)
+  rs = np.random.RandomState(11)
+  worst, compared = 0.0, 0
+  for t in range(nsteps):
+    a = rs.uniform(spec.minimum, spec.maximum)
+    ts = env.step(a)
+    o.ctrl[:] = a; o.control_step(nsub)
+    assert ts.reward is not None and 0.0 <= ts.reward <= 1.0 + 1e-12
+    if any(gtype[c.geom1] != 0 and (gtype[c.geom1] > 3 or gtype[c.geom2] > 3) for c in o.contact):
+      break
+    worst = max(worst, float(np.abs(phys.data.qpos - o.qpos).max()), float(np.abs(phys.data.qvel - o.qvel).max()) * 0.1)
+    assert phys.data.ncon == o.ncon
+    assert [(c.geom1, c.geom2) for c in phys.data.contact] == [(c.geom1, c.geom2) for c in o.contact]
+    compared += 1
+  assert abs(env.physics.time() - (t + 1) * env.control_timestep()) < 1e-9
+  assert compared >= min(10, nsteps) and worst < 1e-6, (compared, worst)
+  return dict(worst=worst, compared=compared, nsub=nsub, obs=sorted(ts.observation))
+
+
+@needs_reference
+@pytest.mark.parametrize('domain,task,keys', [
+    ('cartpole', 'swingup', ['position', 'velocity']),                      # BASELINE.json config 0
+    ('cartpole', 'balance', ['position', 'velocity']),
+    ('cheetah', 'run', ['position', 'velocity']),                           # config 1
+    ('quadruped', 'walk', ['egocentric_state', 'force_torque', 'imu', 'torso_upright', 'torso_velocity']),      # config 3
+    ('humanoid', 'stand', None), ('humanoid', 'walk', None),
+])
+def test_unmodified_reference_suite_tasks_under_emulation(domain, task, keys):
+  """The reference's own suite/<domain>.py drives the engine (CPU emulation build of the kernels, child process)."""
+  code = ("import os, sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r);"
+          "import gpu_shim; gpu_shim.install();"
+          "import test_reference_tasks as t; print('RESULT', json.dumps(t.run_unmodified(%r, %r)))") % (
+              ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'emu'), domain, task)
+  env = dict(os.environ, B200MJ_EMULATE_GPU='1')
+  r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+  import json
+  out = json.loads(r.stdout.split('RESULT', 1)[1])
+  if keys is not None:
+    assert out['obs'] == sorted(keys), out
 
 
 @needs_reference
