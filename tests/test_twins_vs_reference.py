@@ -67,3 +67,56 @@ def test_compute_n_steps_equals_the_reference(ref):
     with pytest.raises(ValueError) as b:
       control.compute_n_steps(ct, pt)
     assert str(a.value) == str(b.value)
+
+
+# ---- the batched task layer (dm_control_b200/suite/*) against the reference's own task files ---------------------------
+_TASK_CHILD = r'''
+import os, sys, importlib, json
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests'); sys.path.insert(0, %(root)r + '/tests/emu')
+import gpu_shim; gpu_shim.install()
+import refshim; refshim.install()
+import numpy as np, torch
+from dm_control_b200 import suite as bsuite
+dom, task, B = %(dom)r, %(task)r, 4
+benv = bsuite.load(dom, task, batch=B, seed=2, outputs='all')
+benv.reset()
+nu = benv.physics.model.nu
+g = np.random.RandomState(0)
+mod = importlib.import_module('dm_control.suite.' + dom)            # /root/reference/dm_control/suite/<dom>.py, unmodified
+renv = getattr(mod, task)(random=0)
+renv.reset()
+rphys, rtask = renv.physics, renv.task
+worst = {}
+for t in range(8):
+  a = g.uniform(-1, 1, (B, nu))
+  ts = benv.step(torch.as_tensor(a, device=benv.physics.device))
+  d = benv.physics.data
+  for e in range(B):
+    with rphys.reset_context():                                       # the batched environment's state, on the reference-facing view
+      rphys.data.qpos[:] = d.qpos[e].cpu().numpy(); rphys.data.qvel[:] = d.qvel[e].cpu().numpy()
+      if benv.physics.model.na: rphys.data.act[:] = d.act[e].cpu().numpy()
+    rphys.set_control(a[e])
+    robs, rrew = rtask.get_observation(rphys), rtask.get_reward(rphys)   # the reference's own observation / reward code
+    assert set(robs) == set(ts.observation), (sorted(robs), sorted(ts.observation))
+    for k, v in robs.items():
+      if k in ('force_torque', 'imu'):      # acceleration-stage sensors: after a step they belong to the previous mj_forward, not to a fresh one
+        continue
+      got = ts.observation[k][e].cpu().numpy().reshape(-1)
+      worst[k] = max(worst.get(k, 0.0), float(np.abs(got - np.asarray(v).reshape(-1)).max()))
+    worst['reward'] = max(worst.get('reward', 0.0), abs(float(ts.reward[e]) - float(rrew)))
+print('RESULT', json.dumps(worst))
+'''
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('dom,task', [('cartpole', 'swingup'), ('cheetah', 'run'), ('humanoid', 'run'), ('humanoid', 'stand'), ('quadruped', 'walk')])
+def test_batched_tasks_equal_the_reference_task_code(dom, task):
+  """Observations and rewards of the batched tasks after random-action steps == what the reference's own
+  `suite/<domain>.py` task computes on the same state (B = 1 reference-facing view; kernels from the CPU emulation build)."""
+  import json, subprocess
+  r = subprocess.run([sys.executable, '-c', _TASK_CHILD % dict(root=ROOT, dom=dom, task=task)], env=dict(os.environ, B200MJ_EMULATE_GPU='1'),
+                     capture_output=True, text=True, timeout=800)
+  assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-3000:])
+  worst = json.loads(r.stdout.split('RESULT', 1)[1])
+  assert 'reward' in worst and len(worst) >= 3, worst
+  assert max(worst.values()) < 1e-12, worst
