@@ -120,3 +120,47 @@ def test_batched_tasks_equal_the_reference_task_code(dom, task):
   worst = json.loads(r.stdout.split('RESULT', 1)[1])
   assert 'reward' in worst and len(worst) >= 3, worst
   assert max(worst.values()) < 1e-12, worst
+
+
+_LOOP_CHILD = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests'); sys.path.insert(0, %(root)r + '/tests/emu')
+import gpu_shim; gpu_shim.install()
+import refshim; refshim.install()
+import numpy as np, torch
+from dm_control_b200 import suite as bsuite
+import dm_control.suite.cartpole as ref_cartpole
+TL = 0.055                                       # 5.5 control steps of 0.01 s: the episode ends on the 6th
+renv = ref_cartpole.balance(time_limit=TL, random=0)
+benv = bsuite.load('cartpole', 'balance', batch=3, seed=0, time_limit=TL)
+rseq, bseq = [], []
+ts = renv.reset(); rseq.append((int(ts.step_type), ts.discount))
+tb = benv.reset(); bseq.append((int(tb.step_type[0]), None))
+a = np.zeros(1)
+for t in range(9):
+  ts = renv.step(a); rseq.append((int(ts.step_type), None if ts.discount is None else float(ts.discount)))
+  tb = benv.step(torch.zeros(3, 1, dtype=torch.float64, device=benv.physics.device))
+  bseq.append((int(tb.step_type[1]), None if tb.discount is None else float(tb.discount[1])))
+print('RESULT', json.dumps(dict(ref=rseq, batched=bseq)))
+'''
+
+
+@pytest.mark.timeout(900)
+def test_environment_loop_equals_the_reference_loop():
+  """step_type / discount sequence across a time limit and the automatic reset that follows: `BatchedEnvironment`
+  (dm_control_b200/control.py) next to the reference's `control.Environment` (rl/control.py:77-127) on cartpole:balance."""
+  import json, subprocess
+  r = subprocess.run([sys.executable, '-c', _LOOP_CHILD % dict(root=ROOT)], env=dict(os.environ, B200MJ_EMULATE_GPU='1'),
+                     capture_output=True, text=True, timeout=800)
+  assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-3000:])
+  out = json.loads(r.stdout.split('RESULT', 1)[1])
+  ref, got = out['ref'], out['batched']
+  assert [s for s, _ in ref].count(2) >= 1 and [s for s, _ in ref].count(0) >= 2      # an end and a restart were seen
+  # identical up to and including the LAST step (same step count to the time limit, discount 1.0 there) ...
+  k = [s for s, _ in ref].index(2)
+  assert ref[:k + 1] == got[:k + 1], out
+  # ... then the one documented difference of a lock-stepped batch: the reference's next call only resets and returns
+  # FIRST (rl/control.py:101-102), the batched environment resets that environment in place AND takes the step (the other
+  # environments of the batch cannot wait), so its sequence is the reference's without that FIRST entry
+  assert ref[k + 1][0] == 0
+  assert ref[k + 2:] == got[k + 1:len(ref) - 1], out
