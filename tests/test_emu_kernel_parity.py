@@ -195,22 +195,32 @@ def test_launch_knobs_do_not_change_results():
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout.strip().splitlines()[-1]
   # the default path: acceleration kernels with nv fixed at compile time (register-resident algebra)
-  ref = digest()
-  for knobs in (dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_BUCKETS='6,12,24'), dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'),
+  from concurrent.futures import ThreadPoolExecutor      # the variants are independent child processes: run them side by side
+  pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2))
+  ref_f = pool.submit(digest)
+  variants = (dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_BUCKETS='6,12,24'), dict(B200MJ_BUCKET_ORDER='1'), dict(B200MJ_EPB_POS='2'),
                 # acceleration launches: one-warp CTAs, compacted lists with 2 / 4 warps, with / without phase barriers, two
                 # iteration-count classes per bucket: scheduling only
                 dict(B200MJ_COMPACT='0'), dict(B200MJ_ACC_WARPS='2'), dict(B200MJ_ACC_SYNC='0'), dict(B200MJ_ACC_SYNC='1'),
                 dict(B200MJ_NITER_SPLIT='3'), dict(B200MJ_NITER_SPLIT='2', B200MJ_ACC_WARPS='3'),
                 # the emulator running the lanes of every block in descending instead of ascending order: a cross-lane
                 # dependency through shared memory that no collective or barrier separates would change the result
-                dict(B200MJ_EMU_ORDER='reverse')):
-    assert digest(**knobs) == ref, knobs
+                dict(B200MJ_EMU_ORDER='reverse'),
+                # convex pairs one per lane instead of by the whole warp (cvx_pair vs cvx_pair_warp): the same contact to the last bit
+                dict(B200MJ_CVX_WARP='0'))
+  futs = [(k, pool.submit(digest, **k)) for k in variants]
   # B200MJ_TN=0: the runtime-size acceleration kernels share their arithmetic with the fused kernel, so there the
   # fused, hybrid and all-split paths must agree bit for bit as well
-  ref0 = digest(B200MJ_TN='0')
-  for knobs in (dict(B200MJ_SPLIT='0'), dict(B200MJ_SPLIT='1'), dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_ENVS_PER_BLOCK='2', B200MJ_SPLIT='0'),
-                dict(B200MJ_SYNC_LEVEL='0', B200MJ_SPLIT='0'), dict(B200MJ_EMU_ORDER='reverse', B200MJ_SPLIT='0')):
-    assert digest(B200MJ_TN='0', **knobs) == ref0, knobs
+  ref0_f = pool.submit(digest, B200MJ_TN='0')
+  variants0 = (dict(B200MJ_SPLIT='0'), dict(B200MJ_SPLIT='1'), dict(B200MJ_BUCKETS='4,16'), dict(B200MJ_ENVS_PER_BLOCK='2', B200MJ_SPLIT='0'),
+               dict(B200MJ_SYNC_LEVEL='0', B200MJ_SPLIT='0'), dict(B200MJ_EMU_ORDER='reverse', B200MJ_SPLIT='0'))
+  futs0 = [(k, pool.submit(digest, B200MJ_TN='0', **k)) for k in variants0]
+  ref, ref0 = ref_f.result(), ref0_f.result()
+  for knobs, f in futs:
+    assert f.result() == ref, knobs
+  for knobs, f in futs0:
+    assert f.result() == ref0, knobs
+  pool.shutdown()
 
 
 _TN_SCRIPT = r'''
