@@ -104,6 +104,7 @@ def run_unmodified(domain, task, nsteps=40, seed=5):
     ('cheetah', 'run', ['position', 'velocity']),                           # config 1
     ('quadruped', 'walk', ['egocentric_state', 'force_torque', 'imu', 'torso_upright', 'torso_velocity']),      # config 3
     ('humanoid', 'stand', None), ('humanoid', 'walk', None),
+    ('humanoid_CMU', 'stand', None),      # a domain with no batched twin here: the 62-dof CMU model, compiled on the fly from the reference XML
 ])
 def test_unmodified_reference_suite_tasks_under_emulation(domain, task, keys):
   """The reference's own suite/<domain>.py drives the engine (CPU emulation build of the kernels, child process)."""
