@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 _COLS = {3: ['x', 'y', 'z'], 4: ['qw', 'qx', 'qy', 'qz'], 9: ['xx', 'xy', 'xz', 'yx', 'yy', 'yz', 'zx', 'zy', 'zz']}
+_RGBA = {'geom_rgba', 'site_rgba'}      # columns r g b a (index.py:103-175 `rgba`); visual tables, Model.vis
 _XYZ = {'body_pos', 'body_ipos', 'body_inertia', 'jnt_pos', 'jnt_axis', 'geom_size', 'geom_pos', 'site_size', 'site_pos',
         'xpos', 'xipos', 'xanchor', 'xaxis', 'geom_xpos', 'site_xpos', 'subtree_com', 'subtree_linvel'}
 _QUAT = {'body_quat', 'body_iquat', 'geom_quat', 'site_quat', 'xquat'}
@@ -23,8 +24,9 @@ _ROW_KIND = {
                            'body_pos', 'body_quat', 'body_ipos', 'body_iquat', 'body_mass', 'body_inertia',
                            'body_parentid', 'body_rootid', 'body_subtreemass')},
     **{f: 'geom' for f in ('geom_xpos', 'geom_xmat', 'geom_size', 'geom_pos', 'geom_quat', 'geom_type', 'geom_bodyid',
-                           'geom_friction', 'geom_rbound', 'geom_condim')},
-    **{f: 'site' for f in ('site_xpos', 'site_xmat', 'site_pos', 'site_quat', 'site_size', 'site_bodyid')},
+                           'geom_friction', 'geom_rbound', 'geom_condim', 'geom_rgba', 'geom_group')},
+    **{f: 'site' for f in ('site_xpos', 'site_xmat', 'site_pos', 'site_quat', 'site_size', 'site_bodyid', 'site_rgba', 'site_group')},
+    **{f: 'camera' for f in ('cam_pos', 'cam_quat', 'cam_fovy', 'cam_bodyid', 'cam_mode', 'cam_targetbodyid')},
     **{f: 'joint' for f in ('jnt_type', 'jnt_range', 'jnt_limited', 'jnt_pos', 'jnt_axis', 'jnt_stiffness', 'jnt_qposadr',
                             'jnt_dofadr', 'jnt_bodyid')},
     **{f: 'actuator' for f in ('ctrl', 'actuator_force', 'actuator_ctrlrange', 'actuator_gear', 'actuator_ctrllimited')},
@@ -68,9 +70,11 @@ class FieldIndexer:
     elif self._ragged:
       self._rows = _ragged(model, kind)
     else:
-      self._rows = {n: i for i, n in enumerate(model.ordered_names[kind])}
+      self._rows = {n: i for i, n in enumerate(model.ordered_names.get(kind, []))}
     ncol = array.shape[-1] if array.ndim - (1 if batched else 0) >= 2 else 0
     self._cols = {c: i for i, c in enumerate(_COLS.get(ncol, []))} if (name in _XYZ or name in _QUAT or name in _MAT) else {}
+    if name in _RGBA:
+      self._cols = {'r': 0, 'g': 1, 'b': 2, 'a': 3}
 
   def _row_key(self, k):
     if isinstance(k, str):
@@ -155,6 +159,8 @@ class NamedIndexStructs:
 
     def model_get(name):
       a = m.fields.get(name)
+      if a is None:
+        a = getattr(m, 'vis', {}).get(name)      # colours, groups, cameras: visual tables outside the physics blob
       if a is None:
         return None
       w = {'body_pos': 3, 'body_quat': 4, 'body_ipos': 3, 'body_iquat': 4, 'body_inertia': 3, 'geom_size': 3, 'geom_pos': 3,

@@ -113,8 +113,13 @@ class Model:
     key = name.upper()
     if key in SIZE:
       return int(fields['sizes'][SIZE[key]])
+    vis = self.__dict__.get('vis') or {}
+    if name in vis and name not in ('stat_center', 'stat_extent', 'global_fovy'):
+      return vis[name]                                  # geom_rgba, site_rgba, geom_group, cam_*: writable (host-side only)
     if name == 'stat':
-      return types.SimpleNamespace(meaninertia=float(fields['opt_real'][OPTR['MEANINERTIA']]))
+      return types.SimpleNamespace(meaninertia=float(fields['opt_real'][OPTR['MEANINERTIA']]),
+                                   extent=float(vis['stat_extent'][0]) if 'stat_extent' in vis else None,
+                                   center=vis.get('stat_center'))
     raise AttributeError(name)
 
   def set(self, field, value, index=slice(None)):

@@ -63,13 +63,33 @@ class _HostData:
     arrays[name][...] = value          # `physics.data.time = t`, `physics.data.qpos = q`: in place, views stay valid
 
 
+class _WritableModel:
+  """`physics.model` as the reference hands it out: arrays a task may write in place (`physics.model.wrap_prm[i] = w`,
+  suite/point_mass.py:101-112; `named.model.geom_rgba[...] = ...`). The batched facade refuses raw array writes because it
+  could not see them; this B = 1 conformance view takes the other route: every array handed out marks the model as
+  modified, so the next engine call re-uploads it (cheap for one small model, and never on the throughput path)."""
+
+  def __init__(self, model):
+    object.__setattr__(self, '_m', model)
+
+  def __getattr__(self, name):
+    m = object.__getattribute__(self, '_m')
+    if name in m.fields:
+      m.touch()
+      return m.fields[name]
+    return getattr(m, name)
+
+  def __setattr__(self, name, value):
+    setattr(object.__getattribute__(self, '_m'), name, value)
+
+
 class SingleEnvPhysics:
   legacy_step = True
 
   def __init__(self, model, device=None):
     self._b = BatchedPhysics(model, batch=1, device=device, outputs='all')
     self._b.enable_applied_forces(True)
-    self.model = model
+    self.model = _WritableModel(model)
     self.data = _HostData(self._b)
     arrays = self.data._arrays
     def data_get(name):

@@ -137,7 +137,14 @@ def _make_lxml():
   etree.Element, etree.SubElement, etree.XMLParser = Element, SubElement, XMLParser
   etree.fromstring = etree.XML = fromstring
   etree.tostring = tostring
-  etree.parse = lambda file_obj, parser=None: types.SimpleNamespace(getroot=lambda r=fromstring(file_obj.read(), parser): r)
+  class _Tree:
+    def __init__(self, root): self._root = root
+    def getroot(self): return self._root
+    def find(self, path): return self._root.find(path)
+    def findall(self, path): return self._root.findall(path)
+    def iter(self, *a): return self._root.iter(*a)
+  etree.parse = lambda file_obj, parser=None: _Tree(fromstring(file_obj.read(), parser))
+  etree.tostring = lambda element, pretty_print=False, **kw: tostring(element.getroot() if isinstance(element, _Tree) else element, pretty_print)
   lxml.etree = etree
   return lxml, etree
 

@@ -3,7 +3,8 @@ dm_control/suite/{humanoid,cartpole,cheetah,quadruped}.py (tasks + Physics subcl
 and quadruped.py do with lxml), suite/base.py, suite/common, suite/utils/randomizers.py, utils/rewards.py,
 utils/containers.py, utils/xml_tools.py — are imported from /root/reference (tests/refshim wires the few absent
 third-party modules) and drive a B = 1 view of the batched CUDA engine (dm_control_b200/refview.py): humanoid:run for 100
-control steps, the other BASELINE suite configs for 40. The trajectory is checked against the CPU oracle stepped from the
+control steps, the other BASELINE suite configs and eight further domains for 20 (tools/probe_reference_suite.py sweeps all 47
+tasks of the reference suite: 30 run, 17 are refused for a named unsupported feature). The trajectory is checked against the CPU oracle stepped from the
 same post-reset state with the same actions.
 
 /root/reference exists in the build container only: the tests skip where it is absent (GPU box).
@@ -57,7 +58,7 @@ def run_unmodified_humanoid(nsteps=100):
   return worst
 
 
-def run_unmodified(domain, task, nsteps=40, seed=5):
+def run_unmodified(domain, task, nsteps=20, seed=5):
   """Any of the BASELINE suite configs through the reference's own task file: build (the file's own model editing where it
   has any: cartpole.py:104-127, quadruped.py:55-93), reset (its own randomisation), step with random actions; the
   trajectory against the oracle stepped from the same post-reset state. Convex (MPR) contacts end the comparison of an
@@ -97,26 +98,46 @@ def run_unmodified(domain, task, nsteps=40, seed=5):
   return dict(worst=worst, compared=compared, nsub=nsub, obs=sorted(ts.observation))
 
 
-@needs_reference
-@pytest.mark.parametrize('domain,task,keys', [
+_SUITE_CASES = [
     ('cartpole', 'swingup', ['position', 'velocity']),                      # BASELINE.json config 0
     ('cartpole', 'balance', ['position', 'velocity']),
     ('cheetah', 'run', ['position', 'velocity']),                           # config 1
     ('quadruped', 'walk', ['egocentric_state', 'force_torque', 'imu', 'torso_upright', 'torso_velocity']),      # config 3
     ('humanoid', 'stand', None), ('humanoid', 'walk', None),
-    ('humanoid_CMU', 'stand', None),      # a domain with no batched twin here: the 62-dof CMU model, compiled on the fly from the reference XML
-])
-def test_unmodified_reference_suite_tasks_under_emulation(domain, task, keys):
-  """The reference's own suite/<domain>.py drives the engine (CPU emulation build of the kernels, child process)."""
-  code = ("import os, sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r);"
-          "import gpu_shim; gpu_shim.install();"
-          "import test_reference_tasks as t; print('RESULT', json.dumps(t.run_unmodified(%r, %r)))") % (
-              ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'emu'), domain, task)
-  env = dict(os.environ, B200MJ_EMULATE_GPU='1')
-  r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900)
-  assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    # domains with no batched twin here: the reference's file + this repo's compiler and engine are all there is
+    ('humanoid_CMU', 'stand', None),      # the 62-dof CMU model
+    ('acrobot', 'swingup', None), ('fish', 'upright', None), ('hopper', 'hop', None), ('pendulum', 'swingup', None),
+    ('point_mass', 'hard', None),         # writes physics.model.wrap_prm in place (point_mass.py:101-112)
+    ('reacher', 'hard', None), ('walker', 'run', None), ('cartpole', 'three_poles', None),
+]
+
+
+@pytest.fixture(scope='module')
+def emulated_suite_results():
+  """ONE child process (CPU emulation build of the kernels) runs every case; the parametrized tests read their entry."""
   import json
-  out = json.loads(r.stdout.split('RESULT', 1)[1])
+  cases = [(d, t) for d, t, _ in _SUITE_CASES]
+  code = ("import os, sys, json, traceback; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r);"
+          "import gpu_shim; gpu_shim.install();"
+          "import test_reference_tasks as t\n"
+          "out = {}\n"
+          "for d, k in %r:\n"
+          "  try: out[d + ':' + k] = t.run_unmodified(d, k)\n"
+          "  except BaseException as ex: out[d + ':' + k] = dict(error=traceback.format_exc()[-1500:])\n"
+          "print('RESULT', json.dumps(out))") % (ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'emu'), cases)
+  env = dict(os.environ, B200MJ_EMULATE_GPU='1')
+  r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=1500)
+  assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+  return json.loads(r.stdout.split('RESULT', 1)[1])
+
+
+@needs_reference
+@pytest.mark.parametrize('domain,task,keys', _SUITE_CASES)
+def test_unmodified_reference_suite_tasks_under_emulation(domain, task, keys, emulated_suite_results):
+  """The reference's own suite/<domain>.py drives the engine (CPU emulation build of the kernels, child process)."""
+  out = emulated_suite_results[f'{domain}:{task}']
+  assert 'error' not in out, out.get('error')
+  assert out['compared'] >= 10 and out['worst'] < 1e-6, out
   if keys is not None:
     assert out['obs'] == sorted(keys), out
 
