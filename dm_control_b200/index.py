@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _COLS = {3: ['x', 'y', 'z'], 4: ['qw', 'qx', 'qy', 'qz'], 9: ['xx', 'xy', 'xz', 'yx', 'yy', 'yz', 'zx', 'zy', 'zz']}
-_RGBA = {'geom_rgba', 'site_rgba'}      # columns r g b a (index.py:103-175 `rgba`); visual tables, Model.vis
+_RGBA = {'geom_rgba', 'site_rgba', 'mat_rgba'}      # columns r g b a (index.py:103-175 `rgba`); visual tables, Model.vis
 _XYZ = {'body_pos', 'body_ipos', 'body_inertia', 'jnt_pos', 'jnt_axis', 'geom_size', 'geom_pos', 'site_size', 'site_pos',
         'xpos', 'xipos', 'xanchor', 'xaxis', 'geom_xpos', 'site_xpos', 'subtree_com', 'subtree_linvel'}
 _QUAT = {'body_quat', 'body_iquat', 'geom_quat', 'site_quat', 'xquat'}
@@ -27,6 +27,7 @@ _ROW_KIND = {
                            'geom_friction', 'geom_rbound', 'geom_condim', 'geom_rgba', 'geom_group')},
     **{f: 'site' for f in ('site_xpos', 'site_xmat', 'site_pos', 'site_quat', 'site_size', 'site_bodyid', 'site_rgba', 'site_group')},
     **{f: 'camera' for f in ('cam_pos', 'cam_quat', 'cam_fovy', 'cam_bodyid', 'cam_mode', 'cam_targetbodyid')},
+    'mat_rgba': 'material',
     **{f: 'joint' for f in ('jnt_type', 'jnt_range', 'jnt_limited', 'jnt_pos', 'jnt_axis', 'jnt_stiffness', 'jnt_qposadr',
                             'jnt_dofadr', 'jnt_bodyid')},
     **{f: 'actuator' for f in ('ctrl', 'actuator_force', 'actuator_ctrlrange', 'actuator_gear', 'actuator_ctrllimited')},

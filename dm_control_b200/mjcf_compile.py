@@ -291,12 +291,18 @@ class _Compiler:
                                   'key', 'camera')}
     # visual-only tables (rendering hand-off, dm_control_b200/render.py): material colours; they never reach the physics blob
     self.material_rgba = {}
+    self.materials, self.textures, self.lights = [], [], []      # (name or placeholder) per element, in document order
     for asset in root.findall('asset'):
       for mat in asset.findall('material'):
         a = self.defaults.get('material', mat.attrib.get('class'))
         a.update(mat.attrib)
-        if 'name' in a:
-          self.material_rgba[a['name']] = _floats(a.get('rgba', '1 1 1 1'), 4)
+        name = a.get('name', f'_material{len(self.materials)}')
+        self.materials.append(name)
+        self.material_rgba[name] = _floats(a.get('rgba', '1 1 1 1'), 4)
+      for tex in asset.findall('texture'):
+        self.textures.append(tex.attrib.get('name', f'_texture{len(self.textures)}'))
+    self.custom = {k: [e.attrib.get('name', f'_{k}{i}') for i, e in enumerate(e for cu in root.findall('custom') for e in cu.findall(k))]
+                   for k in ('numeric', 'text', 'tuple')}
 
   # ---- attribute helpers -------------------------------------------------------------------
   def _merged(self, tag, elem, childclass):
@@ -354,6 +360,8 @@ class _Compiler:
         self._add_site(child, bid, childclass)
       elif child.tag == 'camera':
         self._add_camera(child, bid, childclass)
+      elif child.tag == 'light':
+        self.lights.append(child.attrib.get('name', f'_light{len(self.lights)}'))
       elif child.tag == 'inertial':
         a = child.attrib
         inert = dict(pos=_floats(a['pos'], 3), quat=self._frame_quat(a), mass=float(a['mass']))
@@ -1004,10 +1012,16 @@ def _finish(c, root, nconmax, njmax):
   _set_const(F, nq, nv, nbody, tendons, jnt_qposadr, jnt_dofadr)
 
   names = {k: dict(v) for k, v in c.names.items()}
+  names['model'] = {root.get('model', 'MuJoCo Model'): 0}
+  extra = dict(light=c.lights, material=c.materials, texture=c.textures, numeric=c.custom['numeric'], text=c.custom['text'],
+               tuple=c.custom['tuple'], equality=[e_['name'] for e_ in eqs] if eqs and isinstance(eqs[0], dict) and 'name' in eqs[0] else
+               sorted(c.names.get('equality', {}), key=c.names.get('equality', {}).get))
+  for k_, lst in extra.items():
+    names[k_] = {n: i for i, n in enumerate(lst)}
   ordered = dict(body=[b['name'] for b in c.bodies], joint=[j['name'] for j in J], geom=[g['name'] for g in G],
                  site=[s['name'] for s in S], actuator=[a['name'] for a in acts],
                  tendon=[t['name'] for t in tendons], sensor=[s['name'] for s in sens],
-                 camera=[cam['name'] for cam in c.cameras])
+                 camera=[cam['name'] for cam in c.cameras], **extra)
   return _model.Model(F, names, ordered, vis=_visual_tables(c, root, F, G, S))
 
 
@@ -1068,6 +1082,7 @@ def _visual_tables(c, root, F, G, S):
       cam_fovy=np.array([cam['fovy'] if cam['fovy'] is not None else fovy0 for cam in c.cameras], dtype=np.float64),
       cam_pos0=cam_pos0 - (xpos0[[cam['body'] for cam in c.cameras]] if ncam else np.zeros((0, 3))),
       cam_poscom0=cam_poscom0, cam_mat0=cam_mat0,
+      mat_rgba=np.array([c.material_rgba[n] for n in c.materials], dtype=np.float32).reshape(-1, 4),
       global_fovy=np.array([fovy0]), stat_center=np.asarray(center, dtype=np.float64), stat_extent=np.array([extent]))
 
 
@@ -1156,7 +1171,12 @@ def _set_const(F, nq, nv, nbody, tendons, jnt_qposadr, jnt_dofadr):
     M += F['body_mass'][b] * jp.T @ jp + jr.T @ Iw @ jr
   M += np.diag(F['dof_armature'])
   F['opt_real'][_model.OPTR['MEANINERTIA']] = float(np.mean(np.diag(M))) if nv else 1.0
-  Minv = np.linalg.inv(M) if nv else np.zeros((0, 0))
+  try:
+    Minv = np.linalg.inv(M) if nv else np.zeros((0, 0))
+  except np.linalg.LinAlgError:
+    # a singular inertia matrix at qpos0 (e.g. several hinges about one axis on one body, as in the reference's
+    # randomizers_test.py:76-86): MuJoCo still compiles such a model; the inverse weights come from the pseudo-inverse
+    Minv = np.linalg.pinv(M)
   dof_inv = np.zeros(nv)
   for j in range(F['jnt_type'].shape[0]):
     t, d = F['jnt_type'][j], jnt_dofadr[j]

@@ -42,7 +42,12 @@ NOPTI = len(_OPTI) - 1
 
 # MuJoCo mjtObj names accepted by name2id/id2name (reference: wrapper/core.py:334-387)
 _OBJ_ALIASES = dict(body='body', xbody='body', joint='joint', geom='geom', site='site', actuator='actuator',
-                    tendon='tendon', sensor='sensor', equality='equality', key='key', camera='camera')
+                    tendon='tendon', sensor='sensor', equality='equality', key='key', camera='camera', light='light',
+                    material='material', texture='texture', mesh='mesh', hfield='hfield', numeric='numeric', text='text',
+                    tuple='tuple')
+# sizes that are not part of the physics blob: counted from the name tables the compiler keeps for visual / custom elements
+_NAME_SIZES = dict(ncam='camera', nlight='light', nmat='material', ntex='texture', nmesh='mesh', nhfield='hfield', nnumeric='numeric',
+                   ntext='text', ntuple='tuple', nsensor='sensor', neq='equality', ntendon='tendon')
 
 
 class _Opt:
@@ -113,6 +118,10 @@ class Model:
     key = name.upper()
     if key in SIZE:
       return int(fields['sizes'][SIZE[key]])
+    if name in _NAME_SIZES and 'ordered_names' in self.__dict__:
+      return len(self.ordered_names.get(_NAME_SIZES[name], []))
+    if name == 'name':
+      return next(iter(self.names.get('model', {})), 'MuJoCo Model')      # <mujoco model="...">
     vis = self.__dict__.get('vis') or {}
     if name in vis and name not in ('stat_center', 'stat_extent', 'global_fovy'):
       return vis[name]                                  # geom_rgba, site_rgba, geom_group, cam_*: writable (host-side only)
@@ -142,7 +151,7 @@ class Model:
 
   def id2name(self, object_id, object_type):
     kind = _OBJ_ALIASES[str(object_type).replace('mjOBJ_', '').lower()]
-    return self.ordered_names[kind][object_id]
+    return self.ordered_names.get(kind, [])[object_id]
 
   _DISABLE_NAMES = dict(constraint=1 << 0, equality=1 << 1, frictionloss=1 << 2, limit=1 << 3, contact=1 << 4,
                         passive=1 << 5, gravity=1 << 6, clampctrl=1 << 7, warmstart=1 << 8, filterparent=1 << 9,

@@ -79,6 +79,12 @@ class _WritableModel:
       return m.fields[name]
     return getattr(m, name)
 
+  def id2name(self, object_id, object_type):
+    """MuJoCo's answer: the empty string for an element the MJCF left unnamed (the compiler's internal `_geom12`-style
+    placeholders are not names)."""
+    n = object.__getattribute__(self, '_m').id2name(object_id, object_type)
+    return '' if n.startswith('_') else n
+
   def __setattr__(self, name, value):
     setattr(object.__getattribute__(self, '_m'), name, value)
 
@@ -191,17 +197,19 @@ class SingleEnvPhysics:
   def timestep(self):
     return self._b.timestep()
 
+  # engine.py:589-614: each returns a COPY (the reference's own suite_test.py checks that consecutive observations do not
+  # share memory)
   def control(self):
-    return self.data._arrays['ctrl']
+    return self.data._arrays['ctrl'].copy()
 
   def activation(self):
-    return self.data._arrays['act']
+    return self.data._arrays['act'].copy()
 
   def position(self):
-    return self.data._arrays['qpos']
+    return self.data._arrays['qpos'].copy()
 
   def velocity(self):
-    return self.data._arrays['qvel']
+    return self.data._arrays['qvel'].copy()
 
   def state(self):
     a = self.data._arrays

@@ -197,7 +197,19 @@ def install():
                                 mjtSensor=types.SimpleNamespace(mjSENS_TOUCH=0, mjSENS_ACCELEROMETER=1, mjSENS_VELOCIMETER=2, mjSENS_GYRO=3,
                                                                 mjSENS_FORCE=4, mjSENS_TORQUE=5, mjSENS_MAGNETOMETER=6, mjSENS_RANGEFINDER=7))
   mjb.enums = enums
-  mjb.mjlib = types.SimpleNamespace()      # suite/quadruped.py binds the name at import; only its `escape` task (hfield upload) calls into it
+  # suite/quadruped.py binds the name at import (only its `escape` task, hfield upload, calls into it); the randomizers
+  # and their test use two quaternion helpers of MuJoCo's C API, restated here (mju_axisAngle2Quat, mju_rotVecQuat)
+  def mju_axisAngle2Quat(res, axis, angle):
+    s = np.sin(0.5 * angle)
+    res[0] = np.cos(0.5 * angle); res[1:4] = np.asarray(axis, dtype=float) * s
+
+  def mju_rotVecQuat(res, vec, quat):
+    w, x, y, z = quat
+    R = np.array([[w*w + x*x - y*y - z*z, 2*(x*y - w*z), 2*(x*z + w*y)],
+                  [2*(x*y + w*z), w*w - x*x + y*y - z*z, 2*(y*z - w*x)],
+                  [2*(x*z - w*y), 2*(y*z + w*x), w*w - x*x - y*y + z*z]])
+    res[:] = R @ np.asarray(vec, dtype=float)
+  mjb.mjlib = types.SimpleNamespace(mju_axisAngle2Quat=mju_axisAngle2Quat, mju_rotVecQuat=mju_rotVecQuat)
   wrapper.mjbindings = mjb
   mj.wrapper = wrapper
   sys.modules['dm_control.mujoco'] = mj
