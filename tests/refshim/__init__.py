@@ -156,6 +156,28 @@ def _package(name, path):
   return p
 
 
+def install_suite_package():
+  """After install(): make `dm_control.suite` the REAL package — execute the reference's own suite/__init__.py (which imports
+  all 19 domain files and builds ALL_TASKS / BENCHMARKING / `suite.load`) — and provide what the reference's own
+  suite_test.py imports besides (`mock`, `mjbindings.constants`, the mjtConstraint names suite/dog.py reads at import)."""
+  import unittest.mock
+  sys.modules.setdefault('mock', unittest.mock)
+  mjb = sys.modules['dm_control.mujoco.wrapper.mjbindings']
+  mjb.enums.mjtConstraint = types.SimpleNamespace(mjCNSTR_EQUALITY=0, mjCNSTR_FRICTION_DOF=1, mjCNSTR_FRICTION_TENDON=2,
+                                                  mjCNSTR_LIMIT_JOINT=3, mjCNSTR_LIMIT_TENDON=4, mjCNSTR_CONTACT_FRICTIONLESS=5,
+                                                  mjCNSTR_CONTACT_PYRAMIDAL=6, mjCNSTR_CONTACT_ELLIPTIC=7)
+  consts = types.ModuleType('dm_control.mujoco.wrapper.mjbindings.constants')
+  consts.mjMAXVAL, consts.mjMINVAL = 1e10, 1e-15
+  mjb.constants = consts
+  sys.modules['dm_control.mujoco.wrapper.mjbindings.constants'] = consts
+  pkg = sys.modules['dm_control.suite']
+  if not hasattr(pkg, 'ALL_TASKS'):
+    init = os.path.join(REFERENCE, 'dm_control', 'suite', '__init__.py')
+    pkg.__file__ = init
+    exec(compile(open(init).read(), init, 'exec'), pkg.__dict__)
+  return pkg
+
+
 def install():
   if not available():
     raise RuntimeError(f'{REFERENCE}/dm_control not found')
