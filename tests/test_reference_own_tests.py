@@ -2,6 +2,7 @@
 
   * dm_control/suite/utils/randomizers_test.py — `randomize_limited_and_rotational_joints` on models the test compiles
     from inline MJCF (every joint type, limited ball joints, a singular inertia matrix): 5 tests;
+  * dm_control/suite/loader_test.py — `suite.load` and the task-tag constants: 3 tests;
   * dm_control/suite/suite_test.py — the suite's conformance tests (named components, >= 2 cameras, observations /
     rewards / discounts conform to the specs, determinism, reward visualisation through material colours, environment
     kwargs, observations do not share memory / hold no constant elements over 2 x 1000 steps, randomised initial state),
@@ -67,6 +68,11 @@ def _run(module, select):
 def test_reference_randomizers_test_passes_unmodified():
   out = _run('dm_control.suite.utils.randomizers_test', None)
   assert out['run'] == 5 and out['bad'] == [], out
+
+
+def test_reference_loader_test_passes_unmodified():
+  out = _run('dm_control.suite.loader_test', None)      # suite.load with and without task kwargs, the tag constants
+  assert out['run'] == 3 and out['bad'] == [], out
 
 
 @pytest.mark.timeout(1800)
