@@ -18,6 +18,7 @@ import torch
 
 from . import index as _index
 from . import mjcf_compile
+from . import lib as _lib
 from .physics import BatchedPhysics, PhysicsError
 
 _STATE = ('qpos', 'qvel', 'act', 'ctrl', 'time', 'qacc_warmstart', 'qfrc_applied', 'xfrc_applied')
@@ -117,12 +118,30 @@ class SingleEnvPhysics:
 
   # ---- construction (engine.py:451-503) ----
   @classmethod
+  def _with_full_capacity(cls, model):
+    """MuJoCo sizes its constraint arena dynamically; the compiler's default `njmax` is capped for the throughput path's
+    shared-memory budget (160 rows). This single-environment view asks for every row the model can produce (equality +
+    friction + limits + 4 per contact slot) when the workspace still fits, so that e.g. the CMU humanoid lying on the floor
+    (56 limited joints, dozens of contacts) does not hit mjWARN_CNSTRFULL where the reference would not."""
+    need = int(6 * model.neq + np.count_nonzero(np.asarray(model.dof_frictionloss) > 0) + np.count_nonzero(model.jnt_limited) + 4 * model.nconmax)
+    for rows in (need, (3 * need + model.njmax) // 4, (need + model.njmax) // 2, (need + 3 * model.njmax) // 4):
+      if rows <= model.njmax:
+        break
+      big = model.copy()
+      big.set_capacity(njmax=rows)
+      try:
+        return cls(big)
+      except _lib.EngineError:
+        continue        # does not fit 227 KB of shared memory: try fewer rows, in the end the default capacity
+    return cls(model)
+
+  @classmethod
   def from_xml_string(cls, xml_string, assets=None):
-    return cls(mjcf_compile.compile_xml(xml_string, assets=assets))
+    return cls._with_full_capacity(mjcf_compile.compile_xml(xml_string, assets=assets))
 
   @classmethod
   def from_xml_path(cls, path):
-    return cls(mjcf_compile.compile_file(path))
+    return cls._with_full_capacity(mjcf_compile.compile_file(path))
 
   # ---- host <-> device ----
   def _push(self):
